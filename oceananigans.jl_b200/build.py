@@ -1,0 +1,73 @@
+"""Build libocean_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+The fused tendency kernels are instantiated per (float type, scheme kind, buffer) in separate
+translation units (csrc/tend_inst.cu) so that the build runs in parallel; everything is linked into
+ONE shared library that exports the C ABI of include/ocean_b200.h.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libocean_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH
+
+INSTANCES = [("double", "f64", 0, 0), ("float", "f32", 0, 0)]
+INSTANCES += [(t, tn, 1, nb) for t, tn in (("double", "f64"), ("float", "f32")) for nb in (1, 2, 3)]
+INSTANCES += [(t, tn, 2, nb) for t, tn in (("double", "f64"), ("float", "f32")) for nb in (2, 3, 4, 5)]
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "ocean_b200.h"))
+    return hs
+
+
+def _stale(out, deps):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return r.stdout + r.stderr
+
+
+def build(force=False, verbose=False, jobs=None):
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = _headers()
+    jobs_list = []
+    objs = []
+    main_o = os.path.join(OBJ, "ocean_b200.o")
+    src = os.path.join(CSRC, "ocean_b200.cu")
+    objs.append(main_o)
+    if force or _stale(main_o, [src] + hdrs):
+        jobs_list.append([NVCC, *FLAGS, "-c", src, "-o", main_o])
+    inst = os.path.join(CSRC, "tend_inst.cu")
+    for t, tn, kind, nb in INSTANCES:
+        o = os.path.join(OBJ, "tend_%s_k%d_n%d.o" % (tn, kind, nb))
+        objs.append(o)
+        if force or _stale(o, [inst] + hdrs):
+            jobs_list.append([NVCC, *FLAGS, "-DOB_TI_T=%s" % t, "-DOB_TI_TN=%s" % tn, "-DOB_TI_KIND=%d" % kind,
+                              "-DOB_TI_NB=%d" % nb, "-c", inst, "-o", o])
+    if jobs_list:
+        with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
+            for out in ex.map(_run, jobs_list):
+                if verbose and out.strip():
+                    print(out)
+    if jobs_list or not os.path.exists(LIB):
+        _run([NVCC, "-shared", *ARCH, "-o", LIB, *objs, "-lcufft", "-lnccl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,286 @@
+// kernels.cuh -- streaming kernels of the time step: halo fills (K5/K6), flux-BC tendencies (K7), hydrostatic
+// pressure scan (K8), RK3/AB2 update fused with the G⁻ <- Gⁿ cache (K3+K4), Poisson source term (K10),
+// pressure correction (K16).  All are HBM-bound, coalesced along x, batched over fields so that one launch
+// serves every prognostic field (the reference launches one kernel per field: SURVEY.md §2a).
+#pragma once
+#include "common.cuh"
+
+namespace ob {
+
+// ------------------------------------------------------------------------------------------------------------
+// Halo fills.  Bit-exact restatement of fill_halo_regions_periodic.jl:5-27, _flux.jl:9-27,
+// _value_gradient.jl:7-119, _normal_flow.jl:2-27 with the reference's launch extents
+// (periodic: full parent extent of the tangential dims; others: interior extent, one halo cell).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct HaloTask {
+    T *p;          // parent array
+    int P[3];      // parent sizes
+    int n[3];      // interior sizes (N or N+1)
+    int face;      // field is Face-located along `dir`
+    int bc_lo, bc_hi;
+    T v_lo, v_hi;  // constant value / gradient
+    T d_lo, d_hi;  // Δ at the boundary (flipped location) for Value/Gradient
+};
+#define OB_MAX_HALO_TASKS 24
+template <typename T>
+struct HaloBatch {
+    HaloTask<T> t[OB_MAX_HALO_TASKS];
+    int count, dir, N, H, fill_normal;
+    int Hother[3];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloBatch<T> B) {
+    const HaloTask<T> &t = B.t[blockIdx.y];
+    const int d = B.dir, N = B.N, H = B.H;
+    const int da = d == 0 ? 1 : 0, db = d == 2 ? 1 : 2;  // tangential dims, da the faster one
+    const long sx = 1, sy = t.P[0], sz = (long)t.P[0] * t.P[1];
+    const long sd = d == 0 ? sx : d == 1 ? sy : sz;
+    const long sa = da == 0 ? sx : sy, sb = db == 1 ? sy : sz;
+    const bool periodic = t.bc_lo == BC_PERIODIC;
+    const int A = periodic ? t.P[da] : t.n[da];
+    const int Bn = periodic ? t.P[db] : t.n[db];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long)A * Bn) return;
+    const int a = (int)(tid % A), b = (int)(tid / A);
+    T *q;
+    if (periodic) {
+        q = t.p + a * sa + b * sb;
+#pragma unroll 1
+        for (int h = 0; h < H; h++) {
+            q[h * sd] = q[(N + h) * sd];          // parent[i] = parent[N+i]
+            q[(N + H + h) * sd] = q[(H + h) * sd];  // parent[N+H+i] = parent[H+i]
+        }
+        return;
+    }
+    q = t.p + (a + B.Hother[da]) * sa + (b + B.Hother[db]) * sb;  // interior window of the tangential dims
+    // logical index l along d -> parent index l - 1 + H
+#define AT(l) q[((l) - 1 + H) * sd]
+    // low side
+    switch (t.bc_lo) {
+        case BC_FLUX: AT(0) = AT(1); break;
+        case BC_IMPENETRABLE: if (B.fill_normal) AT(1) = T(0); break;
+        case BC_GRADIENT: { T c = AT(1); AT(0) = c + t.v_lo * (-t.d_lo); } break;
+        case BC_VALUE: { T c = AT(1); T g = (c - t.v_lo) / (t.d_lo / 2); AT(0) = c + g * (-t.d_lo); } break;
+        default: break;
+    }
+    switch (t.bc_hi) {
+        case BC_FLUX: AT(N + 1) = AT(N); break;
+        case BC_IMPENETRABLE: if (B.fill_normal) AT(N + 1) = T(0); break;
+        case BC_GRADIENT: { T c = AT(N); AT(N + 1) = c + t.v_hi * t.d_hi; } break;
+        case BC_VALUE: { T c = AT(N); T g = (t.v_hi - c) / (t.d_hi / 2); AT(N + 1) = c + g * t.d_hi; } break;
+        default: break;
+    }
+#undef AT
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7: constant-flux boundary contributions (compute_flux_bcs.jl:113-162): Gc[1] += flux*A/V ; Gc[N] -= flux*A/V
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct FluxBcTask {
+    Fld<T> G;
+    int dir, side;   // side 0 = low (+=), 1 = high (-=)
+    int loc[3];      // 1 = face, 0 = center
+    T flux;
+};
+template <typename T>
+__global__ void flux_bc_kernel(GridD<T> g, FluxBcTask<T> t) {
+    const int d = t.dir;
+    const int da = d == 0 ? 1 : 0, db = d == 2 ? 1 : 2;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (a >= g.N[da] || b >= g.N[db]) return;
+    int idx[3];
+    idx[da] = a + 1; idx[db] = b + 1;
+    const int n_int = t.side == 0 ? 1 : g.N[d];
+    const int n_face = t.side == 0 ? 1 : g.N[d] + 1;
+    idx[d] = n_int;
+    auto sp = [&](int dd, int face, int l) -> T {
+        if (dd == 0) return g.dx;
+        if (dd == 1) return g.dy;
+        return face ? g.dzF(l) : g.dzC(l);
+    };
+    // area normal to d: tangential spacings at the field's locations (z index = own index if tangential)
+    T sa = sp(da, t.loc[da], idx[da]), sb = sp(db, t.loc[db], idx[db]);
+    T sn = sp(d, t.loc[d], n_int);
+    (void)n_face;
+    T area = sa * sb;  // Ax = Δy*Δz ; Ay = Δx*Δz ; Az = Δx*Δy  (da < db always)
+    T vol = d == 0 ? (sn * sa) * sb : d == 1 ? (sa * sn) * sb : (sa * sb) * sn;  // V = (Δx*Δy)*Δz
+    T term = t.flux * area / vol;
+    T &G = t.G(idx[0], idx[1], idx[2]);
+    G = t.side == 0 ? G + term : G - term;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K8: hydrostatic pressure anomaly (update_hydrostatic_pressure.jl:11-39), columns i,j in (-H+2 : N+H-1)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct HydroP {
+    GridD<T> g;
+    Fld<T> pHY, b, Tt, Ss;
+    int buoy;
+    T grav, alpha, beta;
+    int i0, i1, j0, j1;
+};
+template <typename T>
+__global__ void hydrostatic_pressure_kernel(HydroP<T> P) {
+    const int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = P.j0 + blockIdx.y;
+    if (i > P.i1 || j > P.j1) return;
+    const int Nz = P.g.N[2];
+    auto bp = [&](int k) -> T {
+        if (P.buoy == BUOY_TRACER) return P.b.ld(i, j, k);
+        return P.grav * (P.alpha * P.Tt.ld(i, j, k) - P.beta * P.Ss.ld(i, j, k));
+    };
+    T bk = bp(Nz + 1), bkm = bp(Nz);
+    T pk = -(T(0.5) * (bkm + bk)) * P.g.dzF(Nz + 1);
+    P.pHY(i, j, Nz) = pk;
+    for (int k = Nz - 1; k >= 1; k--) {
+        bk = bkm;          // b[k+1]
+        bkm = bp(k);       // b[k]
+        pk = pk - (T(0.5) * (bkm + bk)) * P.g.dzF(k + 1);
+        P.pHY(i, j, k) = pk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3 + K4: RK3 / AB2 update of every prognostic field, fused with the G⁻ <- Gⁿ cache
+// (runge_kutta_3.jl:196-204, quasi_adams_bashforth_2.jl:134-147, cache_nonhydrostatic_tendencies.jl:8-31).
+// The update skips boundary-normal faces of u, v, w (exclude_periphery); the cache covers 1..N.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct UpdateP {
+    Fld<T> U[3 + OB_MAXTR], Gn[3 + OB_MAXTR], Gm[3 + OB_MAXTR];
+    int lo[3 + OB_MAXTR][3];  // first updated index per dim (2 for the wall-normal component on Bounded)
+    int N[3];
+    int nfields;
+    int mode;       // 0: rk3 first stage, 1: rk3 with zeta, 2: ab2
+    int do_cache;   // also write G⁻ = Gⁿ
+    T dt, gamma, zeta, chi;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ UpdateP<T> P) {
+    const int f = blockIdx.y;
+    int i, j, k;
+    if (!cell_from_block(P.N[0], P.N[1], i, j, k)) return;
+    const long ig = P.Gn[f].idx(i, j, k);
+    const T gn = P.Gn[f].p[ig];
+    const long im = P.Gm[f].idx(i, j, k);
+    const bool active = (i >= P.lo[f][0]) & (j >= P.lo[f][1]) & (k >= P.lo[f][2]);
+    if (active) {
+        T &u = P.U[f](i, j, k);
+        if (P.mode == 0) {
+            u += P.dt * P.gamma * gn;
+        } else if (P.mode == 1) {
+            u += P.dt * (P.gamma * gn + P.zeta * P.Gm[f].p[im]);
+        } else {
+            const T a = T(1.5) + P.chi, b = T(0.5) + P.chi;
+            const bool not_euler = P.chi != T(-0.5);
+            T G = not_euler ? a * gn - b * P.Gm[f].p[im] : a * gn - T(0);
+            u += P.dt * G;
+        }
+    }
+    if (P.do_cache) P.Gm[f].p[im] = gn;
+}
+
+template <typename T>
+struct CopyP {
+    Fld<T> dst[3 + OB_MAXTR], src[3 + OB_MAXTR];
+    int N[3], nfields;
+};
+template <typename T>
+__global__ void cache_kernel(const __grid_constant__ CopyP<T> P) {
+    const int f = blockIdx.y;
+    int i, j, k;
+    if (!cell_from_block(P.N[0], P.N[1], i, j, k)) return;
+    P.dst[f](i, j, k) = P.src[f](i, j, k);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K10: Poisson source term rhs = divᶜᶜᶜ(U★) (solve_for_pressure.jl:12-18), × Δzᶜ for the tridiagonal solver
+// (:36-42).  Written as REAL numbers into the solver's input (the reference writes complex storage).
+// `out` has logical layout (Nx,Ny,Nz) with leading dimension ldx (padded for in-place real-to-complex FFTs).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct SourceP {
+    GridD<T> g;
+    Fld<T> u, v, w;
+    T *out;
+    long ldx, ldxy;
+    int times_dz;
+    int cplx;  // write complex (re, 0) pairs instead of reals
+};
+template <typename T>
+__global__ void __launch_bounds__(256) source_term_kernel(const __grid_constant__ SourceP<T> P) {
+    int i, j, k;
+    if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
+    const T dzc = P.g.dzC(k);
+    const T Ax = P.g.dy * dzc, Ay = P.g.dx * dzc, Az = P.g.dx * P.g.dy;
+    const T ddx = P.g.topo[0] == FLAT ? T(0) : Ax * P.u.ld(i + 1, j, k) - Ax * P.u.ld(i, j, k);
+    const T ddy = P.g.topo[1] == FLAT ? T(0) : Ay * P.v.ld(i, j + 1, k) - Ay * P.v.ld(i, j, k);
+    const T ddz = P.g.topo[2] == FLAT ? T(0) : Az * P.w.ld(i, j, k + 1) - Az * P.w.ld(i, j, k);
+    const T Vi = 1 / ((P.g.dx * P.g.dy) * dzc);
+    T div = Vi * (ddx + ddy + ddz);
+    if (P.times_dz) div = dzc * div;
+    const long o = (i - 1) + (j - 1) * P.ldx + (long)(k - 1) * P.ldxy;
+    if (P.cplx) { P.out[2 * o] = div; P.out[2 * o + 1] = T(0); }
+    else P.out[o] = div;
+}
+
+// K15: p <- real solution (copy_real_component!, fft_based_poisson_solver.jl:128-136), with a scale factor
+// that carries the unnormalised cuFFT inverse (1/N per transformed dimension).
+template <typename T>
+struct CopyRealP {
+    Fld<T> p;
+    const T *in;
+    long ldx, ldxy;
+    int N[3];
+    int cplx;
+    T scale;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) copy_real_kernel(const __grid_constant__ CopyRealP<T> P) {
+    int i, j, k;
+    if (!cell_from_block(P.N[0], P.N[1], i, j, k)) return;
+    const long o = (i - 1) + (j - 1) * P.ldx + (long)(k - 1) * P.ldxy;
+    P.p(i, j, k) = (P.cplx ? P.in[2 * o] : P.in[o]) * P.scale;
+}
+
+// K16: u -= ∂x(pΔτ), v -= ∂y(pΔτ), w -= ∂z(pΔτ) over :xyz (pressure_correction.jl:67-73)
+template <typename T>
+struct CorrectP {
+    GridD<T> g;
+    Fld<T> u, v, w, p;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) pressure_correct_kernel(const __grid_constant__ CorrectP<T> P) {
+    int i, j, k;
+    if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
+    const T pc = P.p.ld(i, j, k);
+    if (P.g.topo[0] != FLAT) P.u(i, j, k) -= (pc - P.p.ld(i - 1, j, k)) * (1 / P.g.dx);
+    if (P.g.topo[1] != FLAT) P.v(i, j, k) -= (pc - P.p.ld(i, j - 1, k)) * (1 / P.g.dy);
+    if (P.g.topo[2] != FLAT) P.w(i, j, k) -= (pc - P.p.ld(i, j, k - 1)) * (1 / P.g.dzF(k));
+}
+
+// pNHS ./= Δt over the whole parent array (pressure_correction.jl:101-103)
+template <typename T>
+__global__ void scale_kernel(T *p, long n, T denom) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) p[t] = p[t] / denom;
+}
+template <typename T>
+__global__ void fill_kernel(T *p, long n, T v) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) p[t] = v;
+}
+template <typename T>
+__global__ void any_nan_kernel(const T *p, long n, int *flag) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; t < n; t += stride) bad |= isnan(p[t]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+}  // namespace ob

@@ -1,0 +1,978 @@
+// ocean_b200.cu -- libocean_b200.so: host orchestration + C ABI (include/ocean_b200.h).
+//
+// The time-step driver mirrors the reference call stack:
+//   time_step! RK3/AB2     src/TimeSteppers/runge_kutta_3.jl:103-168, quasi_adams_bashforth_2.jl:90-126
+//   rk3_substep!/ab2_step! src/Models/NonhydrostaticModels/nonhydrostatic_rk3_substep.jl:31-63, nonhydrostatic_ab2_step.jl:10-57
+//   pressure correction    .../pressure_correction.jl:6-106, solve_for_pressure.jl:12-126
+//   update_state!          .../update_nonhydrostatic_model_state.jl:22-83
+// but every step is a hand-written sm_100a kernel (or a cuFFT batched transform), batched over fields.
+// There is no CPU fallback anywhere in this file.
+#include "../../include/ocean_b200.h"
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "poisson.cuh"
+#include "stencils.cuh"
+#include "tendency.cuh"
+#include "closures.cuh"
+#include "tend_launch.h"
+
+using namespace ob;
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int32_t fail(int32_t code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(x)                                                                                      \
+    do {                                                                                                 \
+        cudaError_t e_ = (x);                                                                            \
+        if (e_ != cudaSuccess) return fail(OB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define CUFFT_TRY(x)                                                                                     \
+    do {                                                                                                 \
+        cufftResult r_ = (x);                                                                            \
+        if (r_ != CUFFT_SUCCESS) return fail(OB_ERR_CUFFT, "%s:%d %s: cufft error %d", __FILE__, __LINE__, #x, (int)r_); \
+    } while (0)
+#define OB_TRY(x)              \
+    do {                       \
+        int32_t s_ = (x);      \
+        if (s_ != OB_OK) return s_; \
+    } while (0)
+
+extern "C" const char *ob_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+struct ob_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int *d_flag = nullptr;
+    int rank = 0, world = 1;
+    void *comm = nullptr;  // ncclComm_t (dist.cuh)
+};
+
+extern "C" int32_t ob_device_count(int32_t *n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return fail(OB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n = c;
+    return OB_OK;
+}
+
+extern "C" int32_t ob_init(int32_t device, ob_ctx **out) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess || c == 0)
+        return fail(OB_ERR_NO_DEVICE, "no CUDA device: libocean_b200 has no CPU fallback");
+    if (device < 0 || device >= c) return fail(OB_ERR_INVALID, "device %d out of range (%d devices)", device, c);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(OB_ERR_NO_DEVICE, "device %d is sm_%d%d; libocean_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    ob_ctx *ctx = new ob_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));
+    *out = ctx;
+    return OB_OK;
+}
+extern "C" int32_t ob_shutdown(ob_ctx *ctx) {
+    if (!ctx) return OB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_flag);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return OB_OK;
+}
+extern "C" int32_t ob_sync(ob_ctx *ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return OB_OK;
+}
+extern "C" int32_t ob_malloc(ob_ctx *ctx, size_t bytes, void **ptr) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMalloc(ptr, bytes ? bytes : 1));
+    CUDA_TRY(cudaMemsetAsync(*ptr, 0, bytes, ctx->stream));
+    return OB_OK;
+}
+extern "C" int32_t ob_free(ob_ctx *ctx, void *ptr) {
+    (void)ctx;
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    return OB_OK;
+}
+extern "C" int32_t ob_malloc_host(ob_ctx *ctx, size_t bytes, void **ptr) {
+    (void)ctx;
+    CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return OB_OK;
+}
+extern "C" int32_t ob_free_host(ob_ctx *ctx, void *ptr) {
+    (void)ctx;
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return OB_OK;
+}
+extern "C" int32_t ob_memcpy_h2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return OB_OK;
+}
+extern "C" int32_t ob_memcpy_d2h(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return OB_OK;
+}
+extern "C" int32_t ob_memcpy_d2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return OB_OK;
+}
+static inline unsigned nblk(long n, int b) { return (unsigned)((n + b - 1) / b); }
+extern "C" int32_t ob_fill(ob_ctx *ctx, void *ptr, size_t n, int32_t ft, double value) {
+    if (n == 0) return OB_OK;
+    if (ft == OB_F64) fill_kernel<double><<<nblk(n, 256), 256, 0, ctx->stream>>>((double *)ptr, (long)n, value);
+    else fill_kernel<float><<<nblk(n, 256), 256, 0, ctx->stream>>>((float *)ptr, (long)n, (float)value);
+    CUDA_TRY(cudaGetLastError());
+    return OB_OK;
+}
+extern "C" int32_t ob_any_nan(ob_ctx *ctx, const void *ptr, size_t n, int32_t ft, int32_t *flag) {
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    unsigned blocks = std::min<unsigned>(nblk(n, 256), 148 * 8);
+    if (n) {
+        if (ft == OB_F64) any_nan_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double *)ptr, (long)n, ctx->d_flag);
+        else any_nan_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float *)ptr, (long)n, ctx->d_flag);
+    }
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *flag = h;
+    return OB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Poisson solver (host side)
+// ---------------------------------------------------------------------------------------------------------------
+struct ob_solver {
+    ob_ctx *ctx = nullptr;
+    int ft = OB_F64;
+    int N[3] = {1, 1, 1}, topo[3] = {0, 0, 0};
+    double L[3] = {1, 1, 1};
+    bool tridiag = false;
+    int64_t launches = 0;
+    virtual ~ob_solver() {}
+    // rhs has been written (as complex numbers) into storage(); result is left in storage(), to be scaled by `scale()`
+    virtual int32_t solve_in_storage() = 0;
+    virtual void *storage() = 0;
+    virtual double scale() = 0;
+};
+
+template <typename T>
+struct SolverT : ob_solver {
+    using C = typename Cx<T>::type;
+    C *S = nullptr, *B = nullptr;
+    T *lam[3] = {nullptr, nullptr, nullptr};
+    C *tw_f[3] = {nullptr, nullptr, nullptr}, *tw_b[3] = {nullptr, nullptr, nullptr};
+    T *diag = nullptr, *lower = nullptr, *tscr = nullptr;
+    cufftHandle plan_x = 0, plan_y = 0, plan_z = 0, plan_xy = 0;
+    bool has_x = false, has_y = false, has_z = false, has_xy = false;
+    double scale_ = 1.0;
+
+    static constexpr cufftType CT = std::is_same<T, double>::value ? CUFFT_Z2Z : CUFFT_C2C;
+
+    int32_t exec(cufftHandle p, C *data, int dir) {
+        launches++;
+        if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2Z(p, data, data, dir));
+        else CUFFT_TRY(cufftExecC2C(p, data, data, dir));
+        return OB_OK;
+    }
+
+    int32_t init(ob_ctx *c, const ob_grid_desc *g) {
+        ctx = c;
+        ft = g->float_type;
+        for (int d = 0; d < 3; d++) { N[d] = g->N[d]; topo[d] = g->topology[d]; L[d] = g->L[d]; }
+        tridiag = g->dzf_host != nullptr;
+        if (tridiag && topo[2] != OB_BOUNDED) return fail(OB_ERR_UNSUPPORTED, "FourierTridiagonalPoissonSolver needs a Bounded stretched direction");
+        const long n = (long)N[0] * N[1] * N[2];
+        CUDA_TRY(cudaMalloc(&S, sizeof(C) * n));
+        CUDA_TRY(cudaMemsetAsync(S, 0, sizeof(C) * n, ctx->stream));
+        bool any_bounded = false;
+        const int ndim_t = tridiag ? 2 : 3;
+        for (int d = 0; d < ndim_t; d++) any_bounded |= topo[d] == OB_BOUNDED;
+        if (any_bounded) CUDA_TRY(cudaMalloc(&B, sizeof(C) * n));
+        // eigenvalues (poisson_eigenvalues.jl:8-32), computed in Float64 then converted to FT
+        for (int d = 0; d < 3; d++) {
+            std::vector<T> h(N[d]);
+            for (int i = 0; i < N[d]; i++) {
+                double v = 0;
+                if (topo[d] == OB_PERIODIC) { double s = 2 * sin(i * M_PI / N[d]) / (L[d] / N[d]); v = s * s; }
+                else if (topo[d] == OB_BOUNDED) { double s = 2 * sin(i * M_PI / (2.0 * N[d])) / (L[d] / N[d]); v = s * s; }
+                h[i] = (T)v;
+            }
+            CUDA_TRY(cudaMalloc(&lam[d], sizeof(T) * N[d]));
+            CUDA_TRY(cudaMemcpy(lam[d], h.data(), sizeof(T) * N[d], cudaMemcpyHostToDevice));
+            if (topo[d] == OB_BOUNDED && d < ndim_t) {  // twiddles ω_4N^{±k} (discrete_transforms.jl:48-78)
+                std::vector<C> f(N[d]), b(N[d]);
+                for (int k = 0; k < N[d]; k++) {
+                    double a = -2 * M_PI * k / (4.0 * N[d]);
+                    f[k].x = (T)cos(a); f[k].y = (T)sin(a);
+                    b[k].x = (T)cos(-a); b[k].y = (T)sin(-a);
+                }
+                b[0].x *= (T)0.5; b[0].y *= (T)0.5;
+                CUDA_TRY(cudaMalloc(&tw_f[d], sizeof(C) * N[d]));
+                CUDA_TRY(cudaMalloc(&tw_b[d], sizeof(C) * N[d]));
+                CUDA_TRY(cudaMemcpy(tw_f[d], f.data(), sizeof(C) * N[d], cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(tw_b[d], b.data(), sizeof(C) * N[d], cudaMemcpyHostToDevice));
+            }
+        }
+        // plans
+        auto transformed = [&](int d) { return d < ndim_t && topo[d] != OB_FLAT && N[d] > 1; };
+        scale_ = 1.0;
+        for (int d = 0; d < 3; d++) if (transformed(d)) scale_ /= N[d];
+        if (transformed(0) && transformed(1) && topo[0] == OB_PERIODIC && topo[1] == OB_PERIODIC) {
+            int nn[2] = {N[1], N[0]};
+            CUFFT_TRY(cufftPlanMany(&plan_xy, 2, nn, nullptr, 1, N[0] * N[1], nullptr, 1, N[0] * N[1], CT, N[2]));
+            CUFFT_TRY(cufftSetStream(plan_xy, ctx->stream));
+            has_xy = true;
+        } else {
+            if (transformed(0)) {
+                int nn[1] = {N[0]};
+                CUFFT_TRY(cufftPlanMany(&plan_x, 1, nn, nn, 1, N[0], nn, 1, N[0], CT, N[1] * N[2]));
+                CUFFT_TRY(cufftSetStream(plan_x, ctx->stream));
+                has_x = true;
+            }
+            if (transformed(1)) {  // one z-plane per call: stride Nx, dist 1, batch Nx
+                int nn[1] = {N[1]};
+                CUFFT_TRY(cufftPlanMany(&plan_y, 1, nn, nn, N[0], 1, nn, N[0], 1, CT, N[0]));
+                CUFFT_TRY(cufftSetStream(plan_y, ctx->stream));
+                has_y = true;
+            }
+        }
+        if (transformed(2)) {
+            int nn[1] = {N[2]};
+            CUFFT_TRY(cufftPlanMany(&plan_z, 1, nn, nn, N[0] * N[1], 1, nn, N[0] * N[1], 1, CT, N[0] * N[1]));
+            CUFFT_TRY(cufftSetStream(plan_z, ctx->stream));
+            has_z = true;
+        }
+        if (tridiag) {
+            // main diagonal & lower diagonal (fourier_tridiagonal_poisson_solver.jl:199-229)
+            const int Nz = N[2], Hz = g->H[2];
+            const T *dzf = (const T *)g->dzf_host, *dzc = (const T *)g->dzc_host;
+            auto DZF = [&](int k) { return dzf[k + Hz]; };
+            auto DZC = [&](int k) { return dzc[k + Hz - 1]; };
+            std::vector<T> lx(N[0]), ly(N[1]);
+            CUDA_TRY(cudaMemcpy(lx.data(), lam[0], sizeof(T) * N[0], cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(ly.data(), lam[1], sizeof(T) * N[1], cudaMemcpyDeviceToHost));
+            std::vector<T> D((size_t)n), low(std::max(1, Nz - 1));
+            for (int k = 1; k <= Nz; k++)
+                for (int j = 0; j < N[1]; j++)
+                    for (int i = 0; i < N[0]; i++) {
+                        T l = lx[i] + ly[j];
+                        T v;
+                        if (k == 1) v = (T)-1 / DZF(2) - DZC(1) * l;
+                        else if (k == Nz) v = (T)-1 / DZF(Nz) - DZC(Nz) * l;
+                        else v = -((T)1 / DZF(k + 1) + (T)1 / DZF(k)) - DZC(k) * l;
+                        D[i + (size_t)N[0] * (j + (size_t)N[1] * (k - 1))] = v;
+                    }
+            for (int q = 1; q <= Nz - 1; q++) low[q - 1] = (T)1 / DZF(q + 1);
+            CUDA_TRY(cudaMalloc(&diag, sizeof(T) * n));
+            CUDA_TRY(cudaMalloc(&tscr, sizeof(T) * n));
+            CUDA_TRY(cudaMalloc(&lower, sizeof(T) * low.size()));
+            CUDA_TRY(cudaMemcpy(diag, D.data(), sizeof(T) * n, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(lower, low.data(), sizeof(T) * low.size(), cudaMemcpyHostToDevice));
+        }
+        return OB_OK;
+    }
+    ~SolverT() override {
+        cudaFree(S); cudaFree(B);
+        for (int d = 0; d < 3; d++) { cudaFree(lam[d]); cudaFree(tw_f[d]); cudaFree(tw_b[d]); }
+        cudaFree(diag); cudaFree(lower); cudaFree(tscr);
+        if (has_x) cufftDestroy(plan_x);
+        if (has_y) cufftDestroy(plan_y);
+        if (has_z) cufftDestroy(plan_z);
+        if (has_xy) cufftDestroy(plan_xy);
+    }
+    void *storage() override { return S; }
+    double scale() override { return scale_; }
+
+    int32_t fft_dim(C *data, int d, int dir) {
+        if (d == 0) return exec(plan_x, data, dir);
+        if (d == 2) return exec(plan_z, data, dir);
+        for (int k = 0; k < N[2]; k++) OB_TRY(exec(plan_y, data + (long)k * N[0] * N[1], dir));
+        return OB_OK;
+    }
+    int32_t solve_in_storage() override {
+        const long n = (long)N[0] * N[1] * N[2];
+        const unsigned nb = nblk(n, 256);
+        cudaStream_t st = ctx->stream;
+        const int ndim_t = tridiag ? 2 : 3;
+        auto transformed = [&](int d) { return d < ndim_t && topo[d] != OB_FLAT && N[d] > 1; };
+        // forward: Bounded dims first (plan_transforms.jl:160-199), then Periodic
+        for (int d = 0; d < ndim_t; d++)
+            if (transformed(d) && topo[d] == OB_BOUNDED) {
+                permute_kernel<C><<<nb, 256, 0, st>>>(S, B, N[0], N[1], N[2], d);
+                OB_TRY(fft_dim(B, d, CUFFT_FORWARD));
+                twiddle_fwd_kernel<T, C><<<nb, 256, 0, st>>>(B, S, tw_f[d], N[0], N[1], N[2], d);
+                launches += 2;
+            }
+        if (has_xy) OB_TRY(exec(plan_xy, S, CUFFT_FORWARD));
+        else {
+            if (transformed(0) && topo[0] == OB_PERIODIC) OB_TRY(fft_dim(S, 0, CUFFT_FORWARD));
+            if (transformed(1) && topo[1] == OB_PERIODIC) OB_TRY(fft_dim(S, 1, CUFFT_FORWARD));
+        }
+        if (transformed(2) && topo[2] == OB_PERIODIC) OB_TRY(fft_dim(S, 2, CUFFT_FORWARD));
+        if (tridiag) {
+            dim3 grid(nblk(N[0], 128), N[1]);
+            thomas_kernel<T, C><<<grid, 128, 0, st>>>(S, lower, diag, tscr, N[0], N[1], N[2], (T)(10 * std::numeric_limits<T>::epsilon()), 1);
+        } else {
+            eigen_divide_kernel<T, C><<<nb, 256, 0, st>>>(S, lam[0], lam[1], lam[2], N[0], N[1], N[2]);
+        }
+        launches++;
+        // backward: Periodic first, then Bounded
+        if (transformed(2) && topo[2] == OB_PERIODIC) OB_TRY(fft_dim(S, 2, CUFFT_INVERSE));
+        if (has_xy) OB_TRY(exec(plan_xy, S, CUFFT_INVERSE));
+        else {
+            if (transformed(1) && topo[1] == OB_PERIODIC) OB_TRY(fft_dim(S, 1, CUFFT_INVERSE));
+            if (transformed(0) && topo[0] == OB_PERIODIC) OB_TRY(fft_dim(S, 0, CUFFT_INVERSE));
+        }
+        for (int d = ndim_t - 1; d >= 0; d--)
+            if (transformed(d) && topo[d] == OB_BOUNDED) {
+                twiddle_bwd_kernel<T, C><<<nb, 256, 0, st>>>(S, B, tw_b[d], N[0], N[1], N[2], d);
+                OB_TRY(fft_dim(B, d, CUFFT_INVERSE));
+                unpermute_kernel<C><<<nb, 256, 0, st>>>(B, S, N[0], N[1], N[2], d);
+                launches += 2;
+            }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+};
+
+extern "C" int32_t ob_solver_create(ob_ctx *ctx, const ob_grid_desc *grid, ob_solver **out) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ob_solver *s = nullptr;
+    int32_t st;
+    if (grid->float_type == OB_F64) { auto *p = new SolverT<double>(); st = p->init(ctx, grid); s = p; }
+    else { auto *p = new SolverT<float>(); st = p->init(ctx, grid); s = p; }
+    if (st != OB_OK) { delete s; return st; }
+    *out = s;
+    return OB_OK;
+}
+extern "C" int32_t ob_solver_destroy(ob_solver *s) { delete s; return OB_OK; }
+
+template <typename T, typename C>
+__global__ void pack_real_kernel(const T *r, C *S, long n) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { C v; v.x = r[t]; v.y = 0; S[t] = v; }
+}
+template <typename T, typename C>
+__global__ void unpack_real_kernel(const C *S, T *r, long n, T scale) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) r[t] = S[t].x * scale;
+}
+extern "C" int32_t ob_poisson_solve(ob_solver *s, const void *rhs, void *phi) {
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const long n = (long)s->N[0] * s->N[1] * s->N[2];
+    cudaStream_t st = s->ctx->stream;
+    if (s->ft == OB_F64) pack_real_kernel<double, double2><<<nblk(n, 256), 256, 0, st>>>((const double *)rhs, (double2 *)s->storage(), n);
+    else pack_real_kernel<float, float2><<<nblk(n, 256), 256, 0, st>>>((const float *)rhs, (float2 *)s->storage(), n);
+    OB_TRY(s->solve_in_storage());
+    if (s->ft == OB_F64) unpack_real_kernel<double, double2><<<nblk(n, 256), 256, 0, st>>>((const double2 *)s->storage(), (double *)phi, n, s->scale());
+    else unpack_real_kernel<float, float2><<<nblk(n, 256), 256, 0, st>>>((const float2 *)s->storage(), (float *)phi, n, (float)s->scale());
+    CUDA_TRY(cudaGetLastError());
+    return OB_OK;
+}
+
+extern "C" int32_t ob_batched_tridiagonal_solve(ob_ctx *ctx, int32_t ft, int32_t is_complex, int32_t Nx, int32_t Ny, int32_t Nz,
+                                                const void *a, const void *b, const void *c, const void *f, void *phi, void *scratch) {
+    // BatchedTridiagonalSolver with a == c (symmetric off-diagonals as built by the Poisson solver); general a != c is
+    // outside the hot path.
+    if (a != c) return fail(OB_ERR_UNSUPPORTED, "ob_batched_tridiagonal_solve: only symmetric off-diagonals (a == c) are supported");
+    if (!is_complex) return fail(OB_ERR_UNSUPPORTED, "ob_batched_tridiagonal_solve: real right-hand sides: pass complex with zero imaginary part");
+    const long n = (long)Nx * Ny * Nz;
+    dim3 grid(nblk(Nx, 128), Ny);
+    if (ft == OB_F64) {
+        if (phi != f) CUDA_TRY(cudaMemcpyAsync(phi, f, sizeof(double2) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        thomas_kernel<double, double2><<<grid, 128, 0, ctx->stream>>>((double2 *)phi, (const double *)a, (const double *)b, (double *)scratch, Nx, Ny, Nz,
+                                                                      10 * std::numeric_limits<double>::epsilon(), 0);
+    } else {
+        if (phi != f) CUDA_TRY(cudaMemcpyAsync(phi, f, sizeof(float2) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        thomas_kernel<float, float2><<<grid, 128, 0, ctx->stream>>>((float2 *)phi, (const float *)a, (const float *)b, (float *)scratch, Nx, Ny, Nz,
+                                                                    10 * std::numeric_limits<float>::epsilon(), 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return OB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------------------
+enum Phase { PH_HALO = 0, PH_CLOSURE, PH_HYDRO, PH_TENDENCY, PH_UPDATE, PH_SOURCE, PH_SOLVE, PH_CORRECT, PH_COUNT };
+static const char *PHASE_NAMES[PH_COUNT] = {"halo", "closure_fields", "hydrostatic_pressure", "tendencies", "update", "poisson_source", "poisson_solve", "pressure_correct"};
+
+struct FieldInfo {
+    void *ptr = nullptr;
+    int loc[3] = {0, 0, 0};  // 1 = Face
+    int P[3] = {1, 1, 1}, n[3] = {1, 1, 1}, o[3] = {0, 0, 0};
+    ob_bc_desc bc;
+    bool exists = false;
+    long count() const { return (long)P[0] * P[1] * P[2]; }
+};
+
+struct ob_model {
+    ob_ctx *ctx = nullptr;
+    ob_model_desc desc;
+    int64_t launches = 0;
+    bool timing = false;
+    double phase_ms[PH_COUNT] = {0};
+    int64_t phase_calls[PH_COUNT] = {0};
+    struct Ev { int phase; cudaEvent_t a, b; };
+    std::vector<Ev> pending;
+    std::vector<cudaEvent_t> pool;
+    virtual ~ob_model() {}
+    virtual int32_t bind(int32_t id, void *p) = 0;
+    virtual int32_t fill_halo(int32_t id, int32_t fill_normal) = 0;
+    virtual int32_t update_state() = 0;
+    virtual int32_t compute_tendencies() = 0;
+    virtual int32_t compute_closure_fields() = 0;
+    virtual int32_t update_hydrostatic_pressure() = 0;
+    virtual int32_t rk3_substep(double dt, double gamma, double zeta, int has_zeta, bool cache) = 0;
+    virtual int32_t ab2_step(double dt, double chi, bool cache) = 0;
+    virtual int32_t cache_tendencies() = 0;
+    virtual int32_t compute_pressure_correction(double dtau) = 0;
+    virtual int32_t make_pressure_correction(double dtau) = 0;
+    virtual int32_t time_step_rk3(double dt, int first) = 0;
+    virtual int32_t time_step_ab2(double dt, int euler, int first) = 0;
+    virtual int32_t advection_timescale(double *tau) = 0;
+
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int ph, cudaEvent_t &a) { if (timing) { a = get_event(); cudaEventRecord(a, ctx->stream); } (void)ph; }
+    void end(int ph, cudaEvent_t a) {
+        if (timing) { cudaEvent_t b = get_event(); cudaEventRecord(b, ctx->stream); pending.push_back({ph, a, b}); }
+    }
+    void collect() {
+        if (pending.empty()) return;
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &e : pending) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e.a, e.b);
+            phase_ms[e.phase] += ms;
+            phase_calls[e.phase]++;
+            pool.push_back(e.a);
+            pool.push_back(e.b);
+        }
+        pending.clear();
+    }
+};
+struct PhaseScope {
+    ob_model *m; int ph; cudaEvent_t a = nullptr;
+    PhaseScope(ob_model *m_, int ph_) : m(m_), ph(ph_) { m->begin(ph, a); }
+    ~PhaseScope() { m->end(ph, a); }
+};
+
+template <typename T>
+struct ModelT : ob_model {
+    GridD<T> g;
+    T *d_dzf = nullptr, *d_dzc = nullptr;
+    std::vector<T> h_dzf, h_dzc;
+    int Hz_ = 0;
+    FieldInfo F[128];
+    SolverT<T> *solver = nullptr;
+    int ntr = 0, ncl = 0;
+    double *d_partial = nullptr;
+
+    ~ModelT() override {
+        cudaFree(d_dzf); cudaFree(d_dzc); cudaFree(d_partial);
+        delete solver;
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+
+    // ---- geometry -------------------------------------------------------------------------------------------
+    void setup_field(int id, int lx, int ly, int lz, const ob_bc_desc &bc) {
+        FieldInfo &f = F[id];
+        f.exists = true;
+        f.loc[0] = lx; f.loc[1] = ly; f.loc[2] = lz;
+        for (int d = 0; d < 3; d++) {
+            f.n[d] = g.N[d] + ((f.loc[d] && g.topo[d] == BOUNDED) ? 1 : 0);
+            f.P[d] = f.n[d] + 2 * g.H[d];
+            f.o[d] = g.H[d];
+        }
+        f.bc = bc;
+    }
+    Fld<T> fld(int id) const {
+        const FieldInfo &f = F[id];
+        Fld<T> v;
+        v.p = (T *)f.ptr;
+        v.sy = f.P[0];
+        v.sz = (long)f.P[0] * f.P[1];
+        v.off = (long)(f.o[0] - 1) + (long)(f.o[1] - 1) * v.sy + (long)(f.o[2] - 1) * v.sz;
+        return v;
+    }
+    T hDZF(int k) const { return h_dzf.empty() ? g.dz : h_dzf[k + Hz_]; }
+    T hDZC(int k) const { return h_dzc.empty() ? g.dz : h_dzc[k + Hz_ - 1]; }
+
+    int32_t init(ob_ctx *c, const ob_model_desc *d) {
+        ctx = c;
+        desc = *d;
+        const ob_grid_desc &gd = d->grid;
+        for (int k = 0; k < 3; k++) {
+            g.N[k] = gd.N[k]; g.topo[k] = gd.topology[k];
+            g.H[k] = gd.topology[k] == OB_FLAT ? 0 : gd.H[k];
+            if (gd.topology[k] == OB_FLAT && gd.N[k] != 1) return fail(OB_ERR_INVALID, "Flat dimension %d must have size 1", k);
+        }
+        g.dx = g.topo[0] == FLAT ? (T)1 : (T)gd.d[0];
+        g.dy = g.topo[1] == FLAT ? (T)1 : (T)gd.d[1];
+        g.dz = g.topo[2] == FLAT ? (T)1 : (T)gd.d[2];
+        g.dzf = g.dzc = nullptr;
+        Hz_ = g.H[2];
+        if (gd.dzf_host) {
+            if (!gd.dzc_host) return fail(OB_ERR_INVALID, "dzf given without dzc");
+            h_dzf.assign((const T *)gd.dzf_host, (const T *)gd.dzf_host + gd.n_dzf);
+            h_dzc.assign((const T *)gd.dzc_host, (const T *)gd.dzc_host + gd.n_dzc);
+            CUDA_TRY(cudaMalloc(&d_dzf, sizeof(T) * gd.n_dzf));
+            CUDA_TRY(cudaMalloc(&d_dzc, sizeof(T) * gd.n_dzc));
+            CUDA_TRY(cudaMemcpy(d_dzf, h_dzf.data(), sizeof(T) * gd.n_dzf, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(d_dzc, h_dzc.data(), sizeof(T) * gd.n_dzc, cudaMemcpyHostToDevice));
+            g.dzf = d_dzf + Hz_;       // logical k -> dzf[k + Hz]
+            g.dzc = d_dzc + Hz_ - 1;   // logical k -> dzc[k + Hz - 1]
+        }
+        ntr = d->n_tracers;
+        ncl = d->n_closures;
+        if (ntr > OB_MAXTR || ncl > OB_MAXCL) return fail(OB_ERR_INVALID, "too many tracers/closures");
+        // scope validation: anything else must be rejected, never silently approximated
+        if (d->advection_kind == OB_ADV_WENO && (d->advection_order < 3 || d->advection_order > 9 || d->advection_order % 2 == 0))
+            return fail(OB_ERR_UNSUPPORTED, "WENO order %d not supported (3,5,7,9)", d->advection_order);
+        if (d->advection_kind == OB_ADV_CENTERED && (d->advection_order < 2 || d->advection_order > 6 || d->advection_order % 2))
+            return fail(OB_ERR_UNSUPPORTED, "Centered order %d not supported (2,4,6)", d->advection_order);
+        const int nb = d->advection_kind == OB_ADV_WENO ? (d->advection_order + 1) / 2 : d->advection_kind == OB_ADV_CENTERED ? d->advection_order / 2 : 0;
+        for (int k = 0; k < 3; k++) {
+            if (g.topo[k] != FLAT && g.N[k] < nb) return fail(OB_ERR_UNSUPPORTED, "grid size %d along %d is smaller than the advection buffer %d (adapt_advection_order path)", g.N[k], k, nb);
+            if (g.topo[k] != FLAT && g.H[k] < nb) return fail(OB_ERR_INVALID, "halo %d along %d is smaller than the advection buffer %d", g.H[k], k, nb);
+            if (g.topo[k] != FLAT && g.H[k] < 1) return fail(OB_ERR_INVALID, "halo must be >= 1");
+            if (g.topo[k] == PERIODIC && g.N[k] < g.H[k]) return fail(OB_ERR_INVALID, "periodic size smaller than halo");
+        }
+        setup_field(OB_FIELD_U, 1, 0, 0, d->bcs_u);
+        setup_field(OB_FIELD_V, 0, 1, 0, d->bcs_v);
+        setup_field(OB_FIELD_W, 0, 0, 1, d->bcs_w);
+        setup_field(OB_FIELD_PNHS, 0, 0, 0, d->bcs_p);
+        if (d->has_hydrostatic_pressure) setup_field(OB_FIELD_PHY, 0, 0, 0, d->bcs_phy);
+        for (int t = 0; t < ntr; t++) setup_field(OB_FIELD_TRACER0 + t, 0, 0, 0, d->bcs_tracer[t]);
+        ob_bc_desc none;
+        memset(&none, 0, sizeof(none));
+        for (int n = 0; n < 3 + ntr; n++) {
+            int lx = n == 0, ly = n == 1, lz = n == 2;
+            setup_field(OB_FIELD_GN0 + n, lx, ly, lz, none);
+            setup_field(OB_FIELD_GM0 + n, lx, ly, lz, none);
+        }
+        for (int m = 0; m < ncl; m++) {
+            if (d->closures[m].kind != OB_CLOSURE_SCALAR_DIFFUSIVITY) setup_field(OB_FIELD_NUE0 + m, 0, 0, 0, d->bcs_nue[m]);
+            if (d->closures[m].kind == OB_CLOSURE_AMD)
+                for (int t = 0; t < ntr; t++) setup_field(OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t, 0, 0, 0, d->bcs_kappae[m][t]);
+        }
+        solver = new SolverT<T>();
+        OB_TRY(solver->init(ctx, &d->grid));
+        return OB_OK;
+    }
+
+    int32_t bind(int32_t id, void *p) override {
+        if (id < 0 || id >= 128 || !F[id].exists) return fail(OB_ERR_INVALID, "field id %d does not exist in this model", id);
+        F[id].ptr = p;
+        return OB_OK;
+    }
+    int32_t need(int id) const {
+        if (!F[id].exists || !F[id].ptr) return fail(OB_ERR_UNBOUND, "field id %d is not bound (ob_model_bind_field)", id);
+        return OB_OK;
+    }
+    int32_t need_all() const {
+        for (int id = 0; id < 128; id++)
+            if (F[id].exists && !F[id].ptr) return fail(OB_ERR_UNBOUND, "field id %d is not bound (ob_model_bind_field)", id);
+        return OB_OK;
+    }
+
+    // ---- halos --------------------------------------------------------------------------------------------------
+    // fill_halo_regions! for a list of fields: per direction ONE launch for all fields; Bounded directions first,
+    // then Periodic (boundary_condition_ordering.jl:17-46,116-142; within a class the reference order is z, y, x).
+    int32_t fill_halos(const std::vector<int> &ids, bool fill_normal) {
+        PhaseScope ps(this, PH_HALO);
+        for (int pass = 0; pass < 2; pass++)
+            for (int d = 2; d >= 0; d--) {
+                if (g.topo[d] == FLAT) continue;
+                const bool per = g.topo[d] == PERIODIC;
+                if ((pass == 0) == per) continue;
+                size_t pos = 0;
+                while (pos < ids.size()) {
+                    HaloBatch<T> B;
+                    B.count = 0; B.dir = d; B.N = g.N[d]; B.H = g.H[d]; B.fill_normal = fill_normal ? 1 : 0;
+                    for (int k = 0; k < 3; k++) B.Hother[k] = g.H[k];
+                    long maxthreads = 0;
+                    for (; pos < ids.size() && B.count < OB_MAX_HALO_TASKS; pos++) {
+                        const FieldInfo &f = F[ids[pos]];
+                        OB_TRY(need(ids[pos]));
+                        const int lo = f.bc.kind[2 * d], hi = f.bc.kind[2 * d + 1];
+                        if (lo == OB_BC_NONE && hi == OB_BC_NONE) continue;
+                        if ((lo == OB_BC_PERIODIC) != per || (hi == OB_BC_PERIODIC) != per)
+                            return fail(OB_ERR_INVALID, "boundary condition of field %d along %d does not match the topology", ids[pos], d);
+                        HaloTask<T> &t = B.t[B.count++];
+                        t.p = (T *)f.ptr;
+                        for (int k = 0; k < 3; k++) { t.P[k] = f.P[k]; t.n[k] = f.n[k]; }
+                        t.face = f.loc[d];
+                        t.bc_lo = lo; t.bc_hi = hi;
+                        t.v_lo = (T)f.bc.value[2 * d]; t.v_hi = (T)f.bc.value[2 * d + 1];
+                        // Δ at flip(loc) at the boundary index (fill_halo_regions_value_gradient.jl:35-119)
+                        auto sp = [&](int idx) -> T {
+                            if (d == 0) return g.dx;
+                            if (d == 1) return g.dy;
+                            return f.loc[2] ? hDZC(idx) : hDZF(idx);
+                        };
+                        t.d_lo = sp(1);
+                        t.d_hi = sp(g.N[d] + 1);
+                        const int da = d == 0 ? 1 : 0, db = d == 2 ? 1 : 2;
+                        long th = per ? (long)f.P[da] * f.P[db] : (long)f.n[da] * f.n[db];
+                        maxthreads = std::max(maxthreads, th);
+                    }
+                    if (B.count == 0) continue;
+                    dim3 grid(nblk(maxthreads, 256), B.count);
+                    halo_kernel<T><<<grid, 256, 0, ctx->stream>>>(B);
+                    launches++;
+                }
+            }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    int32_t fill_halo(int32_t id, int32_t fill_normal) override {
+        if (id < 0 || id >= 128 || !F[id].exists) return fail(OB_ERR_INVALID, "bad field id %d", id);
+        return fill_halos({id}, fill_normal != 0);
+    }
+
+    // ---- tendencies ---------------------------------------------------------------------------------------------
+    TendP<T> tend_params() const {
+        TendP<T> P;
+        memset(&P, 0, sizeof(P));
+        P.g = g;
+        P.u = fld(OB_FIELD_U); P.v = fld(OB_FIELD_V); P.w = fld(OB_FIELD_W);
+        P.Gu = fld(OB_FIELD_GN0); P.Gv = fld(OB_FIELD_GN0 + 1); P.Gw = fld(OB_FIELD_GN0 + 2);
+        for (int t = 0; t < ntr; t++) { P.c[t] = fld(OB_FIELD_TRACER0 + t); P.Gc[t] = fld(OB_FIELD_GN0 + 3 + t); }
+        P.has_pHY = desc.has_hydrostatic_pressure;
+        if (P.has_pHY) P.pHY = fld(OB_FIELD_PHY);
+        P.ntr = ntr; P.ncl = ncl;
+        for (int m = 0; m < ncl; m++) {
+            const ob_closure_desc &c = desc.closures[m];
+            ClosureD<T> &o = P.cl[m];
+            o.kind = c.kind; o.nu = (T)c.nu; o.cs = (T)c.cs; o.cb = (T)c.cb; o.lilly = c.lilly; o.Cnu = (T)c.Cnu; o.amd_has_cb = c.amd_has_cb;
+            for (int t = 0; t < OB_MAXTR; t++) { o.kappa[t] = (T)c.kappa[t]; o.Pr[t] = (T)c.Pr[t]; o.Ckappa[t] = (T)c.Ckappa[t]; }
+            if (c.kind != OB_CLOSURE_SCALAR_DIFFUSIVITY) P.nue[m] = fld(OB_FIELD_NUE0 + m);
+            if (c.kind == OB_CLOSURE_AMD) for (int t = 0; t < ntr; t++) P.kappae[m][t] = fld(OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t);
+        }
+        P.buoy = desc.buoyancy_kind; P.ib = desc.buoyancy_tracer; P.iT = desc.temperature_tracer; P.iS = desc.salinity_tracer;
+        P.grav = (T)desc.g; P.alpha = (T)desc.thermal_expansion; P.beta = (T)desc.haline_contraction;
+        P.has_cor = desc.has_coriolis; P.f = (T)desc.f;
+        return P;
+    }
+
+    int32_t compute_tendencies() override {
+        OB_TRY(need_all());
+        PhaseScope ps(this, PH_TENDENCY);
+        TendP<T> P = tend_params();
+        const int kind = desc.advection_kind;
+        const int nb = kind == OB_ADV_WENO ? (desc.advection_order + 1) / 2 : kind == OB_ADV_CENTERED ? desc.advection_order / 2 : 0;
+        int nl = 0;
+        cudaError_t e = launch_tendency(P, kind, nb, desc.weno_division == OB_DIV_RCP_NEWTON, ctx->stream, ctx->sm_count, &nl);
+        if (e == cudaErrorNotSupported) return fail(OB_ERR_UNSUPPORTED, "advection scheme kind %d buffer %d has no tendency kernel", kind, nb);
+        if (e != cudaSuccess) return fail(OB_ERR_CUDA, "tendency launch: %s", cudaGetErrorString(e));
+        launches += nl;
+        return OB_OK;
+    }
+
+    // ---- closure fields / hydrostatic pressure ---------------------------------------------------------------------
+    int32_t compute_closure_fields() override {
+        bool any = false;
+        for (int m = 0; m < ncl; m++) any |= desc.closures[m].kind != OB_CLOSURE_SCALAR_DIFFUSIVITY;
+        if (!any) return OB_OK;
+        PhaseScope ps(this, PH_CLOSURE);
+        TendP<T> P = tend_params();
+        for (int m = 0; m < ncl; m++) {
+            const int kind = desc.closures[m].kind;
+            if (kind == OB_CLOSURE_SCALAR_DIFFUSIVITY) continue;
+            const int bs = 128;
+            dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], 1);
+            if (kind == OB_CLOSURE_SMAGORINSKY) {
+                smagorinsky_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m);
+                launches++;
+            } else {
+                dim3 grid2(grid.x, 1 + ntr);
+                amd_kernel<T><<<grid2, bs, 0, ctx->stream>>>(P, m);
+                launches++;
+            }
+        }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    int32_t update_hydrostatic_pressure() override {
+        if (!desc.has_hydrostatic_pressure || g.topo[2] == FLAT) return OB_OK;
+        PhaseScope ps(this, PH_HYDRO);
+        HydroP<T> P;
+        memset(&P, 0, sizeof(P));
+        P.g = g;
+        P.pHY = fld(OB_FIELD_PHY);
+        P.buoy = desc.buoyancy_kind;
+        if (P.buoy == OB_BUOYANCY_TRACER) P.b = fld(OB_FIELD_TRACER0 + desc.buoyancy_tracer);
+        else { P.Tt = fld(OB_FIELD_TRACER0 + desc.temperature_tracer); P.Ss = fld(OB_FIELD_TRACER0 + desc.salinity_tracer); }
+        P.grav = (T)desc.g; P.alpha = (T)desc.thermal_expansion; P.beta = (T)desc.haline_contraction;
+        // surface_kernel_parameters: -H+2 : N+H-1 (interleave_communication_and_computation.jl:85-94); Flat => 1:1
+        P.i0 = g.topo[0] == FLAT ? 1 : -g.H[0] + 2; P.i1 = g.topo[0] == FLAT ? 1 : g.N[0] + g.H[0] - 1;
+        P.j0 = g.topo[1] == FLAT ? 1 : -g.H[1] + 2; P.j1 = g.topo[1] == FLAT ? 1 : g.N[1] + g.H[1] - 1;
+        dim3 grid(nblk(P.i1 - P.i0 + 1, 64), P.j1 - P.j0 + 1);
+        hydrostatic_pressure_kernel<T><<<grid, 64, 0, ctx->stream>>>(P);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+
+    int32_t update_state() override {
+        OB_TRY(need_all());
+        std::vector<int> prog = {OB_FIELD_U, OB_FIELD_V, OB_FIELD_W};
+        for (int t = 0; t < ntr; t++) prog.push_back(OB_FIELD_TRACER0 + t);
+        OB_TRY(fill_halos(prog, false));
+        OB_TRY(compute_closure_fields());
+        OB_TRY(update_hydrostatic_pressure());
+        std::vector<int> aux;
+        for (int m = 0; m < ncl; m++) {
+            if (F[OB_FIELD_NUE0 + m].exists) aux.push_back(OB_FIELD_NUE0 + m);
+            for (int t = 0; t < ntr; t++) if (F[OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t].exists) aux.push_back(OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t);
+        }
+        if (desc.has_hydrostatic_pressure) aux.push_back(OB_FIELD_PHY);
+        if (!aux.empty()) OB_TRY(fill_halos(aux, true));
+        return compute_tendencies();
+    }
+
+    // ---- time stepping ------------------------------------------------------------------------------------------------
+    int32_t flux_bc_tendencies() {
+        // compute_flux_bc_tendencies! (compute_nonhydrostatic_tendencies.jl:161-175): x, then y, then z, per field
+        for (int d = 0; d < 3; d++)
+            for (int n = 0; n < 3 + ntr; n++) {
+                const int fid = n < 3 ? n : OB_FIELD_TRACER0 + (n - 3);
+                const FieldInfo &f = F[fid];
+                for (int side = 0; side < 2; side++) {
+                    if (f.bc.kind[2 * d + side] != OB_BC_FLUX || f.bc.value[2 * d + side] == 0.0) continue;
+                    FluxBcTask<T> t;
+                    t.G = fld(OB_FIELD_GN0 + n);
+                    t.dir = d; t.side = side;
+                    for (int k = 0; k < 3; k++) t.loc[k] = f.loc[k];
+                    t.flux = (T)f.bc.value[2 * d + side];
+                    const int da = d == 0 ? 1 : 0, db = d == 2 ? 1 : 2;
+                    dim3 grid(nblk(g.N[da], 128), g.N[db]);
+                    flux_bc_kernel<T><<<grid, 128, 0, ctx->stream>>>(g, t);
+                    launches++;
+                }
+            }
+        return OB_OK;
+    }
+    int32_t launch_update(int mode, double dt, double gamma, double zeta, double chi, bool cache) {
+        PhaseScope ps(this, PH_UPDATE);
+        OB_TRY(flux_bc_tendencies());
+        UpdateP<T> P;
+        memset(&P, 0, sizeof(P));
+        P.nfields = 3 + ntr;
+        for (int n = 0; n < P.nfields; n++) {
+            const int fid = n < 3 ? n : OB_FIELD_TRACER0 + (n - 3);
+            P.U[n] = fld(fid); P.Gn[n] = fld(OB_FIELD_GN0 + n); P.Gm[n] = fld(OB_FIELD_GM0 + n);
+            for (int k = 0; k < 3; k++) P.lo[n][k] = 1;
+            if (n < 3 && g.topo[n] == BOUNDED) P.lo[n][n] = 2;  // exclude_periphery (kernel_launching.jl:160-173)
+        }
+        for (int k = 0; k < 3; k++) P.N[k] = g.N[k];
+        P.mode = mode; P.do_cache = cache ? 1 : 0;
+        P.dt = (T)dt; P.gamma = (T)gamma; P.zeta = (T)zeta; P.chi = (T)chi;
+        const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
+        dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], P.nfields);
+        update_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    int32_t rk3_substep(double dt, double gamma, double zeta, int has_zeta, bool cache) override {
+        OB_TRY(need_all());
+        OB_TRY(launch_update(has_zeta ? 1 : 0, dt, gamma, zeta, 0, cache));
+        // Δτ = convert(FT, Δt * (γ + ζ)) with γ, ζ of the grid float type (runge_kutta_3.jl:186-187)
+        T gz = has_zeta ? (T)((T)gamma + (T)zeta) : (T)gamma;
+        double dtau = (double)(T)(dt * (double)gz);
+        OB_TRY(compute_pressure_correction(dtau));
+        return make_pressure_correction(dtau);
+    }
+    int32_t ab2_step(double dt, double chi, bool cache) override {
+        OB_TRY(need_all());
+        OB_TRY(launch_update(2, dt, 0, 0, chi, cache));
+        double dtau = (double)(T)dt;
+        OB_TRY(compute_pressure_correction(dtau));
+        return make_pressure_correction(dtau);
+    }
+    int32_t cache_tendencies() override {
+        OB_TRY(need_all());
+        CopyP<T> P;
+        memset(&P, 0, sizeof(P));
+        P.nfields = 3 + ntr;
+        for (int n = 0; n < P.nfields; n++) { P.dst[n] = fld(OB_FIELD_GM0 + n); P.src[n] = fld(OB_FIELD_GN0 + n); }
+        for (int k = 0; k < 3; k++) P.N[k] = g.N[k];
+        const int bs = 128;
+        dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], P.nfields);
+        cache_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+
+    int32_t compute_pressure_correction(double dtau) override {
+        (void)dtau;
+        OB_TRY(need_all());
+        OB_TRY(fill_halos({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W}, true));
+        const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
+        dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], 1);
+        {
+            PhaseScope ps(this, PH_SOURCE);
+            SourceP<T> P;
+            memset(&P, 0, sizeof(P));
+            P.g = g; P.u = fld(OB_FIELD_U); P.v = fld(OB_FIELD_V); P.w = fld(OB_FIELD_W);
+            P.out = (T *)solver->storage();
+            P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
+            P.times_dz = solver->tridiag ? 1 : 0;
+            P.cplx = 1;
+            source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            launches++;
+        }
+        {
+            PhaseScope ps(this, PH_SOLVE);
+            int64_t before = solver->launches;
+            OB_TRY(solver->solve_in_storage());
+            launches += solver->launches - before;
+            CopyRealP<T> P;
+            memset(&P, 0, sizeof(P));
+            P.p = fld(OB_FIELD_PNHS);
+            P.in = (const T *)solver->storage();
+            P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
+            for (int k = 0; k < 3; k++) P.N[k] = g.N[k];
+            P.cplx = 1;
+            P.scale = (T)solver->scale();
+            copy_real_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            launches++;
+        }
+        OB_TRY(fill_halos({OB_FIELD_PNHS}, true));
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    int32_t make_pressure_correction(double dtau) override {
+        OB_TRY(need_all());
+        PhaseScope ps(this, PH_CORRECT);
+        CorrectP<T> P;
+        memset(&P, 0, sizeof(P));
+        P.g = g; P.u = fld(OB_FIELD_U); P.v = fld(OB_FIELD_V); P.w = fld(OB_FIELD_W); P.p = fld(OB_FIELD_PNHS);
+        const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
+        dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], 1);
+        pressure_correct_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+        const long n = F[OB_FIELD_PNHS].count();
+        T denom = std::max(std::numeric_limits<T>::epsilon(), (T)dtau);
+        scale_kernel<T><<<nblk(n, 256), 256, 0, ctx->stream>>>((T *)F[OB_FIELD_PNHS].ptr, n, denom);
+        launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+
+    int32_t time_step_rk3(double dt, int first) override {
+        // RK3 coefficients are stored in the grid float type (runge_kutta_3.jl:66-75)
+        const T g1 = (T)(8.0 / 15.0), g2 = (T)(5.0 / 12.0), g3 = (T)(3.0 / 4.0), z2 = (T)(-17.0 / 60.0), z3 = (T)(-5.0 / 12.0);
+        if (first) OB_TRY(update_state());
+        OB_TRY(rk3_substep(dt, g1, 0, 0, true));
+        OB_TRY(update_state());
+        OB_TRY(rk3_substep(dt, g2, z2, 1, true));
+        OB_TRY(update_state());
+        OB_TRY(rk3_substep(dt, g3, z3, 1, true));
+        OB_TRY(update_state());
+        if (timing) collect();
+        return OB_OK;
+    }
+    int32_t time_step_ab2(double dt, int euler, int first) override {
+        if (first) OB_TRY(update_state());
+        const double chi = euler ? -0.5 : desc.chi;
+        OB_TRY(ab2_step(dt, chi, true));
+        OB_TRY(update_state());
+        if (timing) collect();
+        return OB_OK;
+    }
+    int32_t advection_timescale(double *tau) override;
+};
+
+#include "diagnostics.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI: model
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int32_t ob_model_create(ob_ctx *ctx, const ob_model_desc *desc, ob_model **out) {
+    if (!ctx || !desc || !out) return fail(OB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ob_model *m = nullptr;
+    int32_t st;
+    if (desc->grid.float_type == OB_F64) { auto *p = new ModelT<double>(); st = p->init(ctx, desc); m = p; }
+    else if (desc->grid.float_type == OB_F32) { auto *p = new ModelT<float>(); st = p->init(ctx, desc); m = p; }
+    else return fail(OB_ERR_INVALID, "float_type");
+    if (st != OB_OK) { delete m; return st; }
+    *out = m;
+    return OB_OK;
+}
+extern "C" int32_t ob_model_destroy(ob_model *m) {
+    if (m) { cudaSetDevice(m->ctx->device); cudaStreamSynchronize(m->ctx->stream); delete m; }
+    return OB_OK;
+}
+#define MCALL(expr)                               \
+    if (!m) return fail(OB_ERR_INVALID, "null model"); \
+    CUDA_TRY(cudaSetDevice(m->ctx->device));      \
+    return (expr);
+extern "C" int32_t ob_model_bind_field(ob_model *m, int32_t id, void *p) { MCALL(m->bind(id, p)) }
+extern "C" int32_t ob_fill_halo(ob_model *m, int32_t id, int32_t fn) { MCALL(m->fill_halo(id, fn)) }
+extern "C" int32_t ob_update_state(ob_model *m) { MCALL(m->update_state()) }
+extern "C" int32_t ob_compute_tendencies(ob_model *m) { MCALL(m->compute_tendencies()) }
+extern "C" int32_t ob_compute_closure_fields(ob_model *m) { MCALL(m->compute_closure_fields()) }
+extern "C" int32_t ob_update_hydrostatic_pressure(ob_model *m) { MCALL(m->update_hydrostatic_pressure()) }
+extern "C" int32_t ob_rk3_substep(ob_model *m, double dt, double gamma, double zeta, int32_t has_zeta) { MCALL(m->rk3_substep(dt, gamma, zeta, has_zeta, false)) }
+extern "C" int32_t ob_ab2_step(ob_model *m, double dt, double chi) { MCALL(m->ab2_step(dt, chi, false)) }
+extern "C" int32_t ob_cache_tendencies(ob_model *m) { MCALL(m->cache_tendencies()) }
+extern "C" int32_t ob_compute_pressure_correction(ob_model *m, double dtau) { MCALL(m->compute_pressure_correction(dtau)) }
+extern "C" int32_t ob_make_pressure_correction(ob_model *m, double dtau) { MCALL(m->make_pressure_correction(dtau)) }
+extern "C" int32_t ob_time_step_rk3(ob_model *m, double dt, int32_t first) { MCALL(m->time_step_rk3(dt, first)) }
+extern "C" int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first) { MCALL(m->time_step_ab2(dt, euler, first)) }
+extern "C" int32_t ob_cell_advection_timescale(ob_model *m, double *tau) { MCALL(m->advection_timescale(tau)) }
+extern "C" int32_t ob_launch_count(ob_model *m, int64_t *n) { *n = m->launches; return OB_OK; }
+extern "C" int32_t ob_enable_timing(ob_model *m, int32_t e) { m->collect(); m->timing = e != 0; return OB_OK; }
+extern "C" int32_t ob_phase_count(int32_t *n) { *n = PH_COUNT; return OB_OK; }
+extern "C" const char *ob_phase_name(int32_t p) { return (p >= 0 && p < PH_COUNT) ? PHASE_NAMES[p] : ""; }
+extern "C" int32_t ob_phase_time_ms(ob_model *m, int32_t p, double *ms, int64_t *calls) {
+    if (p < 0 || p >= PH_COUNT) return fail(OB_ERR_INVALID, "phase");
+    m->collect();
+    *ms = m->phase_ms[p];
+    *calls = m->phase_calls[p];
+    return OB_OK;
+}
+extern "C" int32_t ob_reset_timing(ob_model *m) {
+    m->collect();
+    for (int p = 0; p < PH_COUNT; p++) { m->phase_ms[p] = 0; m->phase_calls[p] = 0; }
+    return OB_OK;
+}
+
+#include "dist.cuh"

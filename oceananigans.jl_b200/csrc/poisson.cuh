@@ -1,0 +1,142 @@
+// poisson.cuh -- pressure solvers: FFTBasedPoissonSolver (src/Solvers/fft_based_poisson_solver.jl:51-124) and
+// FourierTridiagonalPoissonSolver with the BatchedTridiagonalSolver Thomas sweep
+// (fourier_tridiagonal_poisson_solver.jl:87-260, batched_tridiagonal_solver.jl:211-243).
+//
+// cuFFT does only the batched 1-D / 2-D complex transforms.  Hand-written kernels do everything around them:
+// the Makhoul (1980) DCT index permutation fused with the load, the twiddle multiply fused with the store
+// (reference: 5-6 separate full-array passes per Bounded dimension, discrete_transforms.jl:114-183), the
+// eigenvalue division, and the complex Thomas sweep fused with the mean removal.
+#pragma once
+#include <cufft.h>
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+
+namespace ob {
+
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; };
+template <> struct Cx<float> { using type = float2; };
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// Makhoul permutation (index_permutations.jl:18-36), 0-based: even i -> i/2 ; odd i -> N-1-(i-1)/2
+__device__ __forceinline__ int makhoul(int i, int N) { return (i & 1) ? N - 1 - (i - 1) / 2 : i / 2; }
+
+// B[perm_d(idx)] = A[idx] along dimension d
+template <typename C>
+__global__ void __launch_bounds__(256) permute_kernel(const C *__restrict__ A, C *__restrict__ B, int Nx, int Ny, int Nz, int d) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
+    int ii = i, jj = j, kk = k;
+    if (d == 0) ii = makhoul(i, Nx); else if (d == 1) jj = makhoul(j, Ny); else kk = makhoul(k, Nz);
+    B[ii + (long)Nx * (jj + (long)Ny * kk)] = A[t];
+}
+// forward twiddle: A = 2 * real(ω_4N^k * B)   (discrete_transforms.jl:172-175; twiddles :48-78)
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) twiddle_fwd_kernel(const C *__restrict__ B, C *__restrict__ A, const C *__restrict__ w,
+                                                          int Nx, int Ny, int Nz, int d) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
+    int q = d == 0 ? i : d == 1 ? j : k;
+    C v = cmul(w[q], B[t]);
+    C o;
+    o.x = 2 * v.x;
+    o.y = 0;
+    A[t] = o;
+}
+// backward twiddle: B = A * ω_4N^{-k} (k = 0 halved)   (discrete_transforms.jl:177-183)
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) twiddle_bwd_kernel(const C *__restrict__ A, C *__restrict__ B, const C *__restrict__ w,
+                                                          int Nx, int Ny, int Nz, int d) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
+    int q = d == 0 ? i : d == 1 ? j : k;
+    B[t] = cmul(A[t], w[q]);
+}
+// unpermute + real: A[idx] = real(B[perm_d(idx)])
+template <typename C>
+__global__ void __launch_bounds__(256) unpermute_kernel(const C *__restrict__ B, C *__restrict__ A, int Nx, int Ny, int Nz, int d) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
+    int ii = i, jj = j, kk = k;
+    if (d == 0) ii = makhoul(i, Nx); else if (d == 1) jj = makhoul(j, Ny); else kk = makhoul(k, Nz);
+    C v = B[ii + (long)Nx * (jj + (long)Ny * kk)];
+    v.y = 0;
+    A[t] = v;
+}
+// ϕ̂ = -b̂ / (λx + λy + λz) ; ϕ̂[1,1,1] = 0   (fft_based_poisson_solver.jl:109-114)
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) eigen_divide_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
+                                                           const T *__restrict__ lz, int Nx, int Ny, int Nz) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
+    C v = A[t];
+    T lam = lx[i] + ly[j] + lz[k];
+    C o;
+    if (t == 0) { o.x = 0; o.y = 0; }
+    else { o.x = -v.x / lam; o.y = -v.y / lam; }
+    A[t] = o;
+}
+
+// Complex Thomas sweep along z, one thread per (i,j) column, coalesced along x
+// (batched_tridiagonal_solver.jl:217-243).  a = c = lower diagonal (Nz-1), D = main diagonal (Nx,Ny,Nz),
+// tscr = real scratch (Nx,Ny,Nz).  In place on the complex array A (f and ϕ alias).
+// Column (1,1) additionally removes its k-mean, which equals `ϕ .-= mean(ϕ)` of
+// fourier_tridiagonal_poisson_solver.jl:252-254 (only the horizontal-mean mode has a non-zero mean).
+template <typename T, typename C>
+__global__ void __launch_bounds__(128) thomas_kernel(C *__restrict__ A, const T *__restrict__ lower, const T *__restrict__ D,
+                                                     T *__restrict__ tscr, int Nx, int Ny, int Nz, T eps10, int remove_mean) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= Nx) return;
+    const long s = (long)Nx * Ny;
+    const long o = i + (long)Nx * j;
+    T beta = D[o];
+    C f = A[o];
+    C phi;
+    phi.x = f.x / beta;
+    phi.y = f.y / beta;
+    A[o] = phi;
+    for (int k = 1; k < Nz; k++) {
+        const T cm = lower[k - 1], am = lower[k - 1];
+        const T tk = cm / beta;
+        tscr[o + k * s] = tk;
+        beta = D[o + k * s] - am * tk;
+        f = A[o + k * s];
+        const bool ok = fabs(beta) > eps10;
+        C star;
+        star.x = (f.x - am * phi.x) / beta;
+        star.y = (f.y - am * phi.y) / beta;
+        if (!ok) { star.x = 0; star.y = 0; }  // singular (λ = 0) column: value is arbitrary, removed by the mean
+        phi = star;
+        A[o + k * s] = phi;
+    }
+    for (int k = Nz - 2; k >= 0; k--) {
+        const T tk = tscr[o + (k + 1) * s];
+        C cur = A[o + k * s];
+        cur.x -= tk * phi.x;
+        cur.y -= tk * phi.y;
+        phi = cur;
+        A[o + k * s] = phi;
+    }
+    if (remove_mean && o == 0) {
+        T mx = 0, my = 0;
+        for (int k = 0; k < Nz; k++) { C v = A[k * s]; mx += v.x; my += v.y; }
+        mx /= Nz; my /= Nz;
+        for (int k = 0; k < Nz; k++) { C v = A[k * s]; v.x -= mx; v.y -= my; A[k * s] = v; }
+    }
+}
+
+}  // namespace ob

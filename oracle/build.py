@@ -18,7 +18,7 @@ def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
-    flags = ["-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=gnu11", "-Wall", "-Wno-unused-function"]
+    flags = ["-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=gnu11", "-Wall", "-Wno-unused-function", "-Wno-maybe-uninitialized"]
     o64 = os.path.join(OUT_DIR, "oracle_f64.o")
     o32 = os.path.join(OUT_DIR, "oracle_f32.o")
     subprocess.check_call(["gcc", *flags, "-DFT=double", "-c", SRC, "-o", o64])

@@ -676,3 +676,105 @@ void SUF(orc_smagorinsky_viscosity)(const oparams *g, int m) {
                 *ref(&g->nue[m], i, j, k) = cs2 * (Df * Df) * SQRT(2 * SS);
             }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * AnisotropicMinimumDissipation (turbulence_closure_implementations/anisotropic_minimum_dissipation.jl:161-358;
+ * normalised gradients velocity_tracer_gradients.jl:126-260).  Filter widths are 2Δ at ccc, evaluated at the
+ * index of the stencil point whatever its location (:231-243).
+ * ------------------------------------------------------------------------------------------ */
+#define DFX(i) ((FT)2 * dxc(i))
+#define DFY(j) ((FT)2 * dyc(j))
+#define DFZ(k) ((FT)2 * dzc(k))
+static FT n_dx_u(P g, const void *a, int i, int j, int k) { (void)a; return dx_u(g, i, j, k); }
+static FT n_dy_v(P g, const void *a, int i, int j, int k) { (void)a; return dy_v(g, i, j, k); }
+static FT n_dz_w(P g, const void *a, int i, int j, int k) { (void)a; return dz_w(g, i, j, k); }
+static FT n_dx_v(P g, const void *a, int i, int j, int k) { (void)a; return DFX(i) / DFY(j) * dx_v(g, i, j, k); }
+static FT n_dy_u(P g, const void *a, int i, int j, int k) { (void)a; return DFY(j) / DFX(i) * dy_u(g, i, j, k); }
+static FT n_dx_w(P g, const void *a, int i, int j, int k) { (void)a; return DFX(i) / DFZ(k) * dx_w(g, i, j, k); }
+static FT n_dz_u(P g, const void *a, int i, int j, int k) { (void)a; return DFZ(k) / DFX(i) * dz_u(g, i, j, k); }
+static FT n_dy_w(P g, const void *a, int i, int j, int k) { (void)a; return DFY(j) / DFZ(k) * dy_w(g, i, j, k); }
+static FT n_dz_v(P g, const void *a, int i, int j, int k) { (void)a; return DFZ(k) / DFY(j) * dz_v(g, i, j, k); }
+static FT n_S12(P g, const void *a, int i, int j, int k) { return (FT)0.5 * (n_dy_u(g, a, i, j, k) + n_dx_v(g, a, i, j, k)); }
+static FT n_S13(P g, const void *a, int i, int j, int k) { return (FT)0.5 * (n_dz_u(g, a, i, j, k) + n_dx_w(g, a, i, j, k)); }
+static FT n_S23(P g, const void *a, int i, int j, int k) { return (FT)0.5 * (n_dz_v(g, a, i, j, k) + n_dy_w(g, a, i, j, k)); }
+#define SQFN(name, base) static FT name(P g, const void *a, int i, int j, int k) { FT x = base(g, a, i, j, k); return x * x; }
+SQFN(n_dx_v2, n_dx_v) SQFN(n_dy_u2, n_dy_u) SQFN(n_dx_w2, n_dx_w) SQFN(n_dz_u2, n_dz_u) SQFN(n_dy_w2, n_dy_w) SQFN(n_dz_v2, n_dz_v)
+#define PRFN(name, f1, f2) static FT name(P g, const void *a, int i, int j, int k) { return f1(g, a, i, j, k) * f2(g, a, i, j, k); }
+PRFN(n_dx_v_S12, n_dx_v, n_S12) PRFN(n_dy_u_S12, n_dy_u, n_S12) PRFN(n_dx_w_S13, n_dx_w, n_S13) PRFN(n_dz_u_S13, n_dz_u, n_S13)
+PRFN(n_dz_v_S23, n_dz_v, n_S23) PRFN(n_dy_w_S23, n_dy_w, n_S23)
+/* ℑxyᶜᶜᵃ = ℑyᵃᶜᵃ(ℑxᶜᵃᵃ), ℑxzᶜᵃᶜ = ℑzᵃᵃᶜ(ℑxᶜᵃᵃ), ℑyzᵃᶜᶜ = ℑzᵃᵃᶜ(ℑyᵃᶜᵃ)  (interpolation_operators.jl:45-53) */
+#define IXY(f) I2(g, 1, 0, 0, 0, f, NULL, i, j, k)
+#define IXZ(f) I2(g, 2, 0, 0, 0, f, NULL, i, j, k)
+#define IYZ(f) I2(g, 2, 0, 1, 0, f, NULL, i, j, k)
+
+/* tracer gradients: norm_∂x_c = Δᶠx * ∂xᶠᶜᶜ c, ... */
+static FT n_dx_c(P g, const void *a, int i, int j, int k) { const ofield *c = a; return DFX(i) * ((FLATX ? 0 : at(c, i, j, k) - at(c, i - 1, j, k)) * (1 / dxf(i))); }
+static FT n_dy_c(P g, const void *a, int i, int j, int k) { const ofield *c = a; return DFY(j) * ((FLATY ? 0 : at(c, i, j, k) - at(c, i, j - 1, k)) * (1 / dyf(j))); }
+static FT n_dz_c(P g, const void *a, int i, int j, int k) { const ofield *c = a; return DFZ(k) * ((FLATZ ? 0 : at(c, i, j, k) - at(c, i, j, k - 1)) * (1 / dzf(k))); }
+SQFN(n_dx_c2, n_dx_c) SQFN(n_dy_c2, n_dy_c) SQFN(n_dz_c2, n_dz_c)
+/* ∂x b at fcc etc. of the buoyancy perturbation */
+static FT pt_dx_b(P g, const void *a, int i, int j, int k) { (void)a; return (FLATX ? 0 : bpert(g, NULL, i, j, k) - bpert(g, NULL, i - 1, j, k)) * (1 / dxf(i)); }
+static FT pt_dy_b(P g, const void *a, int i, int j, int k) { (void)a; return (FLATY ? 0 : bpert(g, NULL, i, j, k) - bpert(g, NULL, i, j - 1, k)) * (1 / dyf(j)); }
+
+static FT amd_delta2(P g, int i, int j, int k) {
+    FT fx = DFX(i), fy = DFY(j), fz = DFZ(k);
+    return 3 / (1 / (fx * fx) + 1 / (fy * fy) + 1 / (fz * fz));
+}
+
+void SUF(orc_amd_viscosity)(const oparams *g, int m) {
+    const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 1; k <= Nz; k++)
+        for (int j = 1; j <= Ny; j++)
+            for (int i = 1; i <= Nx; i++) {
+                const FT ux = dx_u(g, i, j, k), vy = dy_v(g, i, j, k), wz = dz_w(g, i, j, k);
+                /* norm_tr_∇uᶜᶜᶜ (:295-316) */
+                FT q = ux * ux + vy * vy + wz * wz + IXY(n_dx_v2) + IXY(n_dy_u2) + IXZ(n_dx_w2) + IXZ(n_dz_u2) + IYZ(n_dy_w2) + IYZ(n_dz_v2);
+                FT nu = 0;
+                if (q != 0) {
+                    /* norm_uᵢₐ_uⱼₐ_Σᵢⱼᶜᶜᶜ (:251-289) */
+                    FT r1 = ux * (ux * ux) + vy * IXY(n_dx_v2) + wz * IXZ(n_dx_w2) + 2 * ux * IXY(n_dx_v_S12) + 2 * ux * IXZ(n_dx_w_S13) +
+                            2 * IXY(n_dx_v) * IXZ(n_dx_w) * IYZ(n_S23);
+                    FT r2 = ux * IXY(n_dy_u2) + vy * (vy * vy) + wz * IYZ(n_dy_w2) + 2 * vy * IXY(n_dy_u_S12) +
+                            2 * IXY(n_dy_u) * IYZ(n_dy_w) * IXZ(n_S13) + 2 * vy * IYZ(n_dy_w_S23);
+                    FT r3 = ux * IXZ(n_dz_u2) + vy * IYZ(n_dz_v2) + wz * (wz * wz) + 2 * IXZ(n_dz_u) * IYZ(n_dz_v) * IXY(n_S12) +
+                            2 * wz * IXZ(n_dz_u_S13) + 2 * wz * IYZ(n_dz_v_S23);
+                    FT r = r1 + r2 + r3;
+                    FT cbz = 0;
+                    if (g->amd_has_cb[m]) { /* Cb_norm_wᵢ_bᵢᶜᶜᶜ (:320-333) */
+                        FT wxbx = IXZ(n_dx_w) * DFX(i) * Ic(g, 0, pt_dx_b, NULL, i, j, k);
+                        FT wyby = IYZ(n_dy_w) * DFY(j) * Ic(g, 1, pt_dy_b, NULL, i, j, k);
+                        FT wzbz = wz * DFZ(k) * Ic(g, 2, pt_dz_b, NULL, i, j, k);
+                        cbz = g->cb[m] * (wxbx + wyby + wzbz);
+                    }
+                    cbz = cbz / DFZ(k);
+                    nu = -g->Cnu[m] * amd_delta2(g, i, j, k) * (r - cbz) / q;
+                }
+                *ref(&g->nue[m], i, j, k) = FMAX((FT)0, nu);
+            }
+}
+
+void SUF(orc_amd_diffusivity)(const oparams *g, int m, int t) {
+    const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];
+    const ofield *c = &g->c[t];
+#define ICX(f) Ic(g, 0, f, c, i, j, k)
+#define ICY(f) Ic(g, 1, f, c, i, j, k)
+#define ICZ(f) Ic(g, 2, f, c, i, j, k)
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 1; k <= Nz; k++)
+        for (int j = 1; j <= Ny; j++)
+            for (int i = 1; i <= Nx; i++) {
+                FT sigma = ICX(n_dx_c2) + ICY(n_dy_c2) + ICZ(n_dz_c2); /* norm_θᵢ²ᶜᶜᶜ (:355-357) */
+                FT kap_ = 0;
+                if (sigma != 0) {
+                    const FT ux = dx_u(g, i, j, k), vy = dy_v(g, i, j, k), wz = dz_w(g, i, j, k);
+                    /* norm_uᵢⱼ_cⱼ_cᵢᶜᶜᶜ (:335-353); the ℑxz of norm_∂y_w in cy_uy is the reference's own */
+                    FT cx = ux * ICX(n_dx_c2) + IXY(n_dx_v) * ICX(n_dx_c) * ICY(n_dy_c) + IXZ(n_dx_w) * ICX(n_dx_c) * ICZ(n_dz_c);
+                    FT cy = IXY(n_dy_u) * ICY(n_dy_c) * ICX(n_dx_c) + vy * ICY(n_dy_c2) + IXZ(n_dy_w) * ICY(n_dy_c) * ICZ(n_dz_c);
+                    FT cz = IXZ(n_dz_u) * ICZ(n_dz_c) * ICX(n_dx_c) + IYZ(n_dz_v) * ICZ(n_dz_c) * ICY(n_dy_c) + wz * ICZ(n_dz_c2);
+                    FT theta = cx + cy + cz;
+                    kap_ = -g->Ckappa[m][t] * amd_delta2(g, i, j, k) * theta / sigma;
+                }
+                *ref(&g->kappae[m][t], i, j, k) = FMAX((FT)0, kap_);
+            }
+}
