@@ -140,6 +140,9 @@ int32_t ob_shutdown(ob_ctx *ctx);
 const char *ob_last_error(void);
 int32_t ob_device_count(int32_t *n);
 int32_t ob_sync(ob_ctx *ctx);                                         /* Architectures.synchronize / sync_device! */
+/* CUDA-event timer on the context's stream: start records, stop records + synchronises and returns milliseconds */
+int32_t ob_timer_start(ob_ctx *ctx);
+int32_t ob_timer_stop(ob_ctx *ctx, double *ms);
 int32_t ob_malloc(ob_ctx *ctx, size_t bytes, void **ptr);             /* Base.zeros(::B200, FT, dims...) */
 int32_t ob_free(ob_ctx *ctx, void *ptr);                              /* finalizer / unsafe_free! */
 int32_t ob_malloc_host(ob_ctx *ctx, size_t bytes, void **ptr);        /* pinned staging buffers */

@@ -15,7 +15,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libocean_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH + os.environ.get("OB_NVCC_EXTRA", "").split()
 
 INSTANCES = [("double", "f64", 0, 0), ("float", "f32", 0, 0)]
 INSTANCES += [(t, tn, 1, nb) for t, tn in (("double", "f64"), ("float", "f32")) for nb in (1, 2, 3)]

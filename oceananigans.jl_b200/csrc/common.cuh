@@ -63,6 +63,15 @@ struct BcD {
     T value[6];
 };
 
+// un-contracted arithmetic for the places where the reference CPU code has no @muladd and the result must be
+// bit-identical (halo extrapolation) or is a pure rounding residue (Thomas sweep of the singular column)
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
 // Flattened launch geometry: blockIdx.x enumerates (x-block, j, k); returns false for the x tail.
 __device__ __forceinline__ bool cell_from_block(int Nx, int Ny, int &i, int &j, int &k) {
     const int nbx = (Nx + blockDim.x - 1) / blockDim.x;

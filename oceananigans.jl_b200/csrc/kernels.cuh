@@ -61,15 +61,15 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloB
     switch (t.bc_lo) {
         case BC_FLUX: AT(0) = AT(1); break;
         case BC_IMPENETRABLE: if (B.fill_normal) AT(1) = T(0); break;
-        case BC_GRADIENT: { T c = AT(1); AT(0) = c + t.v_lo * (-t.d_lo); } break;
-        case BC_VALUE: { T c = AT(1); T g = (c - t.v_lo) / (t.d_lo / 2); AT(0) = c + g * (-t.d_lo); } break;
+        case BC_GRADIENT: { T c = AT(1); AT(0) = add_rn(c, mul_rn(t.v_lo, -t.d_lo)); } break;
+        case BC_VALUE: { T c = AT(1); T g = (c - t.v_lo) / (t.d_lo / 2); AT(0) = add_rn(c, mul_rn(g, -t.d_lo)); } break;
         default: break;
     }
     switch (t.bc_hi) {
         case BC_FLUX: AT(N + 1) = AT(N); break;
         case BC_IMPENETRABLE: if (B.fill_normal) AT(N + 1) = T(0); break;
-        case BC_GRADIENT: { T c = AT(N); AT(N + 1) = c + t.v_hi * t.d_hi; } break;
-        case BC_VALUE: { T c = AT(N); T g = (t.v_hi - c) / (t.d_hi / 2); AT(N + 1) = c + g * t.d_hi; } break;
+        case BC_GRADIENT: { T c = AT(N); AT(N + 1) = add_rn(c, mul_rn(t.v_hi, t.d_hi)); } break;
+        case BC_VALUE: { T c = AT(N); T g = (t.v_hi - c) / (t.d_hi / 2); AT(N + 1) = add_rn(c, mul_rn(g, t.d_hi)); } break;
         default: break;
     }
 #undef AT

@@ -69,6 +69,7 @@ struct ob_ctx {
     int *d_flag = nullptr;
     int rank = 0, world = 1;
     void *comm = nullptr;  // ncclComm_t (dist.cuh)
+    cudaEvent_t tA = nullptr, tB = nullptr;
 };
 
 extern "C" int32_t ob_device_count(int32_t *n) {
@@ -103,6 +104,22 @@ extern "C" int32_t ob_shutdown(ob_ctx *ctx) {
     cudaFree(ctx->d_flag);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return OB_OK;
+}
+// device-side timer on the context's stream (bench.py: CUDA events on the stream the kernels are launched on)
+extern "C" int32_t ob_timer_start(ob_ctx *ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->tA) { CUDA_TRY(cudaEventCreate(&ctx->tA)); CUDA_TRY(cudaEventCreate(&ctx->tB)); }
+    CUDA_TRY(cudaEventRecord(ctx->tA, ctx->stream));
+    return OB_OK;
+}
+extern "C" int32_t ob_timer_stop(ob_ctx *ctx, double *ms) {
+    if (!ctx->tA) return fail(OB_ERR_INVALID, "ob_timer_stop without ob_timer_start");
+    CUDA_TRY(cudaEventRecord(ctx->tB, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->tB));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->tA, ctx->tB));
+    *ms = f;
     return OB_OK;
 }
 extern "C" int32_t ob_sync(ob_ctx *ctx) {
@@ -339,7 +356,7 @@ struct SolverT : ob_solver {
         if (transformed(2) && topo[2] == OB_PERIODIC) OB_TRY(fft_dim(S, 2, CUFFT_FORWARD));
         if (tridiag) {
             dim3 grid(nblk(N[0], 128), N[1]);
-            thomas_kernel<T, C><<<grid, 128, 0, st>>>(S, lower, diag, tscr, N[0], N[1], N[2], (T)(10 * std::numeric_limits<T>::epsilon()), 1);
+            thomas_kernel<T, C><<<grid, 128, 0, st>>>(S, lower, lower, diag, tscr, N[0], N[1], N[2], (T)(10 * std::numeric_limits<T>::epsilon()), 1);
         } else {
             eigen_divide_kernel<T, C><<<nb, 256, 0, st>>>(S, lam[0], lam[1], lam[2], N[0], N[1], N[2]);
         }
@@ -400,19 +417,16 @@ extern "C" int32_t ob_poisson_solve(ob_solver *s, const void *rhs, void *phi) {
 
 extern "C" int32_t ob_batched_tridiagonal_solve(ob_ctx *ctx, int32_t ft, int32_t is_complex, int32_t Nx, int32_t Ny, int32_t Nz,
                                                 const void *a, const void *b, const void *c, const void *f, void *phi, void *scratch) {
-    // BatchedTridiagonalSolver with a == c (symmetric off-diagonals as built by the Poisson solver); general a != c is
-    // outside the hot path.
-    if (a != c) return fail(OB_ERR_UNSUPPORTED, "ob_batched_tridiagonal_solve: only symmetric off-diagonals (a == c) are supported");
     if (!is_complex) return fail(OB_ERR_UNSUPPORTED, "ob_batched_tridiagonal_solve: real right-hand sides: pass complex with zero imaginary part");
     const long n = (long)Nx * Ny * Nz;
     dim3 grid(nblk(Nx, 128), Ny);
     if (ft == OB_F64) {
         if (phi != f) CUDA_TRY(cudaMemcpyAsync(phi, f, sizeof(double2) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-        thomas_kernel<double, double2><<<grid, 128, 0, ctx->stream>>>((double2 *)phi, (const double *)a, (const double *)b, (double *)scratch, Nx, Ny, Nz,
+        thomas_kernel<double, double2><<<grid, 128, 0, ctx->stream>>>((double2 *)phi, (const double *)a, (const double *)c, (const double *)b, (double *)scratch, Nx, Ny, Nz,
                                                                       10 * std::numeric_limits<double>::epsilon(), 0);
     } else {
         if (phi != f) CUDA_TRY(cudaMemcpyAsync(phi, f, sizeof(float2) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-        thomas_kernel<float, float2><<<grid, 128, 0, ctx->stream>>>((float2 *)phi, (const float *)a, (const float *)b, (float *)scratch, Nx, Ny, Nz,
+        thomas_kernel<float, float2><<<grid, 128, 0, ctx->stream>>>((float2 *)phi, (const float *)a, (const float *)c, (const float *)b, (float *)scratch, Nx, Ny, Nz,
                                                                     10 * std::numeric_limits<float>::epsilon(), 0);
     }
     CUDA_TRY(cudaGetLastError());

@@ -95,9 +95,12 @@ __global__ void __launch_bounds__(256) eigen_divide_kernel(C *__restrict__ A, co
 // tscr = real scratch (Nx,Ny,Nz).  In place on the complex array A (f and ϕ alias).
 // Column (1,1) additionally removes its k-mean, which equals `ϕ .-= mean(ϕ)` of
 // fourier_tridiagonal_poisson_solver.jl:252-254 (only the horizontal-mean mode has a non-zero mean).
+// un-contracted arithmetic (the reference CPU code has no @muladd in the Thomas sweep; β of the singular
+// column is a pure rounding residue, so contraction would change it at O(1))
 template <typename T, typename C>
-__global__ void __launch_bounds__(128) thomas_kernel(C *__restrict__ A, const T *__restrict__ lower, const T *__restrict__ D,
-                                                     T *__restrict__ tscr, int Nx, int Ny, int Nz, T eps10, int remove_mean) {
+__global__ void __launch_bounds__(128) thomas_kernel(C *__restrict__ A, const T *__restrict__ lower, const T *__restrict__ upper,
+                                                     const T *__restrict__ D, T *__restrict__ tscr, int Nx, int Ny, int Nz, T eps10,
+                                                     int remove_mean) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= Nx) return;
@@ -110,24 +113,26 @@ __global__ void __launch_bounds__(128) thomas_kernel(C *__restrict__ A, const T 
     phi.y = f.y / beta;
     A[o] = phi;
     for (int k = 1; k < Nz; k++) {
-        const T cm = lower[k - 1], am = lower[k - 1];
+        const T cm = upper[k - 1], am = lower[k - 1];
         const T tk = cm / beta;
         tscr[o + k * s] = tk;
-        beta = D[o + k * s] - am * tk;
+        beta = sub_rn(D[o + k * s], mul_rn(am, tk));
         f = A[o + k * s];
         const bool ok = fabs(beta) > eps10;
         C star;
-        star.x = (f.x - am * phi.x) / beta;
-        star.y = (f.y - am * phi.y) / beta;
-        if (!ok) { star.x = 0; star.y = 0; }  // singular (λ = 0) column: value is arbitrary, removed by the mean
+        star.x = sub_rn(f.x, mul_rn(am, phi.x)) / beta;
+        star.y = sub_rn(f.y, mul_rn(am, phi.y)) / beta;
+        // not definitely diagonally dominant (the singular λ = 0 column): the reference leaves ϕ[k] untouched, i.e.
+        // an arbitrary stale value that only shifts the null-space constant removed by the mean subtraction; 0 here.
+        if (!ok) { star.x = 0; star.y = 0; }
         phi = star;
         A[o + k * s] = phi;
     }
     for (int k = Nz - 2; k >= 0; k--) {
         const T tk = tscr[o + (k + 1) * s];
         C cur = A[o + k * s];
-        cur.x -= tk * phi.x;
-        cur.y -= tk * phi.y;
+        cur.x = sub_rn(cur.x, mul_rn(tk, phi.x));
+        cur.y = sub_rn(cur.y, mul_rn(tk, phi.y));
         phi = cur;
         A[o + k * s] = phi;
     }
