@@ -20,6 +20,7 @@ OB_CLOSURE_SCALAR_DIFFUSIVITY, OB_CLOSURE_SMAGORINSKY, OB_CLOSURE_AMD = 1, 2, 3
 OB_BUOYANCY_NONE, OB_BUOYANCY_TRACER, OB_BUOYANCY_LINEAR_SEAWATER = 0, 1, 2
 OB_RK3, OB_AB2 = 0, 1
 OB_DIV_EXACT, OB_DIV_RCP_NEWTON = 0, 1
+OB_OPT_TENDENCY_KERNEL = 1
 OB_FIELD_U, OB_FIELD_V, OB_FIELD_W, OB_FIELD_PNHS, OB_FIELD_PHY = 0, 1, 2, 3, 4
 OB_FIELD_TRACER0, OB_FIELD_GN0, OB_FIELD_GM0, OB_FIELD_NUE0, OB_FIELD_KAPPAE0 = 16, 32, 48, 64, 80
 
@@ -86,6 +87,7 @@ PROTOTYPES = {
     "ob_rk3_substep": [_P, _dbl, _dbl, _dbl, _i32], "ob_ab2_step": [_P, _dbl, _dbl], "ob_cache_tendencies": [_P],
     "ob_compute_pressure_correction": [_P, _dbl], "ob_make_pressure_correction": [_P, _dbl],
     "ob_time_step_rk3": [_P, _dbl, _i32], "ob_time_step_ab2": [_P, _dbl, _i32, _i32],
+    "ob_model_set_option": [_P, _i32, _i32],
     "ob_launch_count": [_P, C.POINTER(_i64)], "ob_enable_timing": [_P, _i32], "ob_phase_count": [C.POINTER(_i32)],
     "ob_phase_time_ms": [_P, _i32, C.POINTER(_dbl), C.POINTER(_i64)], "ob_reset_timing": [_P],
     "ob_solver_create": [_P, C.POINTER(GridDesc), _PP], "ob_solver_destroy": [_P],

@@ -453,6 +453,7 @@ struct ob_model {
     ob_model_desc desc;
     int64_t launches = 0;
     bool timing = false;
+    int opt_tendency_kernel = 0;  // OB_OPT_TENDENCY_KERNEL: 0 auto, 1 generic (one thread per cell), 2 marching
     double phase_ms[PH_COUNT] = {0};
     int64_t phase_calls[PH_COUNT] = {0};
     struct Ev { int phase; cudaEvent_t a, b; };
@@ -710,7 +711,7 @@ struct ModelT : ob_model {
         const int kind = desc.advection_kind;
         const int nb = kind == OB_ADV_WENO ? (desc.advection_order + 1) / 2 : kind == OB_ADV_CENTERED ? desc.advection_order / 2 : 0;
         int nl = 0;
-        cudaError_t e = launch_tendency(P, kind, nb, desc.weno_division == OB_DIV_RCP_NEWTON, ctx->stream, ctx->sm_count, &nl);
+        cudaError_t e = launch_tendency(P, kind, nb, desc.weno_division == OB_DIV_RCP_NEWTON, opt_tendency_kernel, ctx->stream, ctx->sm_count, &nl);
         if (e == cudaErrorNotSupported) return fail(OB_ERR_UNSUPPORTED, "advection scheme kind %d buffer %d has no tendency kernel", kind, nb);
         if (e != cudaSuccess) return fail(OB_ERR_CUDA, "tendency launch: %s", cudaGetErrorString(e));
         launches += nl;
@@ -972,6 +973,13 @@ extern "C" int32_t ob_make_pressure_correction(ob_model *m, double dtau) { MCALL
 extern "C" int32_t ob_time_step_rk3(ob_model *m, double dt, int32_t first) { MCALL(m->time_step_rk3(dt, first)) }
 extern "C" int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first) { MCALL(m->time_step_ab2(dt, euler, first)) }
 extern "C" int32_t ob_cell_advection_timescale(ob_model *m, double *tau) { MCALL(m->advection_timescale(tau)) }
+extern "C" int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t value) {
+    if (!m) return fail(OB_ERR_INVALID, "null model");
+    switch (option) {
+        case OB_OPT_TENDENCY_KERNEL: m->opt_tendency_kernel = value; return OB_OK;
+    }
+    return fail(OB_ERR_INVALID, "unknown option %d", option);
+}
 extern "C" int32_t ob_launch_count(ob_model *m, int64_t *n) { *n = m->launches; return OB_OK; }
 extern "C" int32_t ob_enable_timing(ob_model *m, int32_t e) { m->collect(); m->timing = e != 0; return OB_OK; }
 extern "C" int32_t ob_phase_count(int32_t *n) { *n = PH_COUNT; return OB_OK; }

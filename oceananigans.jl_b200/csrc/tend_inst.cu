@@ -9,13 +9,13 @@ namespace ob {
 #define OB_CAT_(a, b, c, d) launch_tend_##a##_k##b##_n##c
 #define OB_CAT(a, b, c) OB_CAT_(a, b, c, 0)
 
-cudaError_t OB_CAT(OB_TI_TN, OB_TI_KIND, OB_TI_NB)(const TendP<OB_TI_T> &P, int fast, cudaStream_t st, int sm_count, int *nlaunch) {
+cudaError_t OB_CAT(OB_TI_TN, OB_TI_KIND, OB_TI_NB)(const TendP<OB_TI_T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch) {
     using T = OB_TI_T;
     using S = Scheme<OB_TI_KIND, OB_TI_NB>;
     cudaError_t e = upload_tables();
     if (e != cudaSuccess) return e;
     bool done = false;
-    e = try_tiled_tendency<T, S>(P, fast, st, sm_count, nlaunch, done);
+    e = try_tiled_tendency<T, S>(P, fast, mode, st, sm_count, nlaunch, done);
     if (e != cudaSuccess) return e;
     if (!done) {
         const int Nx = P.g.N[0];

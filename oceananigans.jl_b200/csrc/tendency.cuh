@@ -192,11 +192,15 @@ template <typename T> __device__ __forceinline__ T bpert(const TendP<T> &P, int 
 }
 
 // ---- pointwise tendencies (nonhydrostatic_tendency_kernel_functions.jl:71-302) -----------------------------------
-template <typename T, class S, bool FAST> __device__ __forceinline__ T Gu_point(const TendP<T> &P, int i, int j, int k) {
+// Every tendency = finish(advective flux divergence); the generic kernel evaluates each face flux through the
+// difference operator as the reference does, the marching kernel (tendency_tiled.cuh) shares face fluxes between cells.
+template <typename T, class S, bool FAST> __device__ __forceinline__ T Gu_adv(const TendP<T> &P, int i, int j, int k) {
     T Vi = 1 / ((DXF * DYC) * DZC(k));
-    T adv = Vi * (DELTA_((mom_flux<T, S, FAST, 0, 0>(P, i, j, k)), (mom_flux<T, S, FAST, 0, 0>(P, i - 1, j, k)), 0) +
-                  DELTA_((mom_flux<T, S, FAST, 1, 0>(P, i, j + 1, k)), (mom_flux<T, S, FAST, 1, 0>(P, i, j, k)), 1) +
-                  DELTA_((mom_flux<T, S, FAST, 2, 0>(P, i, j, k + 1)), (mom_flux<T, S, FAST, 2, 0>(P, i, j, k)), 2));
+    return Vi * (DELTA_((mom_flux<T, S, FAST, 0, 0>(P, i, j, k)), (mom_flux<T, S, FAST, 0, 0>(P, i - 1, j, k)), 0) +
+                 DELTA_((mom_flux<T, S, FAST, 1, 0>(P, i, j + 1, k)), (mom_flux<T, S, FAST, 1, 0>(P, i, j, k)), 1) +
+                 DELTA_((mom_flux<T, S, FAST, 2, 0>(P, i, j, k + 1)), (mom_flux<T, S, FAST, 2, 0>(P, i, j, k)), 2));
+}
+template <typename T> __device__ __forceinline__ T Gu_finish(const TendP<T> &P, T adv, int i, int j, int k) {
     T r = -adv;
     if (P.has_cor) {  // coriolis_schemes.jl:67 : -ℑy(f) * ℑxyᶠᶜᵃ(Ay_q v) * Ay⁻¹ᶠᶜᶜ
         const bool fy = P.g.topo[1] == FLAT, fx = P.g.topo[0] == FLAT;
@@ -214,11 +218,13 @@ template <typename T, class S, bool FAST> __device__ __forceinline__ T Gu_point(
     }
     return r;
 }
-template <typename T, class S, bool FAST> __device__ __forceinline__ T Gv_point(const TendP<T> &P, int i, int j, int k) {
+template <typename T, class S, bool FAST> __device__ __forceinline__ T Gv_adv(const TendP<T> &P, int i, int j, int k) {
     T Vi = 1 / ((DXC * DYF) * DZC(k));
-    T adv = Vi * (DELTA_((mom_flux<T, S, FAST, 0, 1>(P, i + 1, j, k)), (mom_flux<T, S, FAST, 0, 1>(P, i, j, k)), 0) +
-                  DELTA_((mom_flux<T, S, FAST, 1, 1>(P, i, j, k)), (mom_flux<T, S, FAST, 1, 1>(P, i, j - 1, k)), 1) +
-                  DELTA_((mom_flux<T, S, FAST, 2, 1>(P, i, j, k + 1)), (mom_flux<T, S, FAST, 2, 1>(P, i, j, k)), 2));
+    return Vi * (DELTA_((mom_flux<T, S, FAST, 0, 1>(P, i + 1, j, k)), (mom_flux<T, S, FAST, 0, 1>(P, i, j, k)), 0) +
+                 DELTA_((mom_flux<T, S, FAST, 1, 1>(P, i, j, k)), (mom_flux<T, S, FAST, 1, 1>(P, i, j - 1, k)), 1) +
+                 DELTA_((mom_flux<T, S, FAST, 2, 1>(P, i, j, k + 1)), (mom_flux<T, S, FAST, 2, 1>(P, i, j, k)), 2));
+}
+template <typename T> __device__ __forceinline__ T Gv_finish(const TendP<T> &P, T adv, int i, int j, int k) {
     T r = -adv;
     if (P.has_cor) {  // coriolis_schemes.jl:68 : +ℑx(f) * ℑxyᶜᶠᵃ(Ax_q u) * Ax⁻¹ᶜᶠᶜ
         const bool fy = P.g.topo[1] == FLAT, fx = P.g.topo[0] == FLAT;
@@ -236,11 +242,13 @@ template <typename T, class S, bool FAST> __device__ __forceinline__ T Gv_point(
     }
     return r;
 }
-template <typename T, class S, bool FAST> __device__ __forceinline__ T Gw_point(const TendP<T> &P, int i, int j, int k) {
+template <typename T, class S, bool FAST> __device__ __forceinline__ T Gw_adv(const TendP<T> &P, int i, int j, int k) {
     T Vi = 1 / ((DXC * DYC) * DZF(k));
-    T adv = Vi * (DELTA_((mom_flux<T, S, FAST, 0, 2>(P, i + 1, j, k)), (mom_flux<T, S, FAST, 0, 2>(P, i, j, k)), 0) +
-                  DELTA_((mom_flux<T, S, FAST, 1, 2>(P, i, j + 1, k)), (mom_flux<T, S, FAST, 1, 2>(P, i, j, k)), 1) +
-                  DELTA_((mom_flux<T, S, FAST, 2, 2>(P, i, j, k)), (mom_flux<T, S, FAST, 2, 2>(P, i, j, k - 1)), 2));
+    return Vi * (DELTA_((mom_flux<T, S, FAST, 0, 2>(P, i + 1, j, k)), (mom_flux<T, S, FAST, 0, 2>(P, i, j, k)), 0) +
+                 DELTA_((mom_flux<T, S, FAST, 1, 2>(P, i, j + 1, k)), (mom_flux<T, S, FAST, 1, 2>(P, i, j, k)), 1) +
+                 DELTA_((mom_flux<T, S, FAST, 2, 2>(P, i, j, k)), (mom_flux<T, S, FAST, 2, 2>(P, i, j, k - 1)), 2));
+}
+template <typename T> __device__ __forceinline__ T Gw_finish(const TendP<T> &P, T adv, int i, int j, int k) {
     T r = -adv;
     if (!P.has_pHY && P.buoy != BUOY_NONE) {  // maybe_z_dot_g_bᶜᶜᶠ = ℑzᵃᵃᶠ(b)
         r = r + (P.g.topo[2] == FLAT ? bpert(P, i, j, k) : T(0.5) * (bpert(P, i, j, k - 1) + bpert(P, i, j, k)));
@@ -252,12 +260,14 @@ template <typename T, class S, bool FAST> __device__ __forceinline__ T Gw_point(
     }
     return r;
 }
-template <typename T, class S, bool FAST> __device__ __forceinline__ T Gc_point(const TendP<T> &P, int t, int i, int j, int k) {
+template <typename T, class S, bool FAST> __device__ __forceinline__ T Gc_adv(const TendP<T> &P, int t, int i, int j, int k) {
     const Fld<T> &c = P.c[t];
     T Vi = 1 / ((DXC * DYC) * DZC(k));
-    T adv = Vi * (DELTA_((tracer_flux<T, S, FAST, 0>(P, c, i + 1, j, k)), (tracer_flux<T, S, FAST, 0>(P, c, i, j, k)), 0) +
-                  DELTA_((tracer_flux<T, S, FAST, 1>(P, c, i, j + 1, k)), (tracer_flux<T, S, FAST, 1>(P, c, i, j, k)), 1) +
-                  DELTA_((tracer_flux<T, S, FAST, 2>(P, c, i, j, k + 1)), (tracer_flux<T, S, FAST, 2>(P, c, i, j, k)), 2));
+    return Vi * (DELTA_((tracer_flux<T, S, FAST, 0>(P, c, i + 1, j, k)), (tracer_flux<T, S, FAST, 0>(P, c, i, j, k)), 0) +
+                 DELTA_((tracer_flux<T, S, FAST, 1>(P, c, i, j + 1, k)), (tracer_flux<T, S, FAST, 1>(P, c, i, j, k)), 1) +
+                 DELTA_((tracer_flux<T, S, FAST, 2>(P, c, i, j, k + 1)), (tracer_flux<T, S, FAST, 2>(P, c, i, j, k)), 2));
+}
+template <typename T> __device__ __forceinline__ T Gc_finish(const TendP<T> &P, T adv, int t, int i, int j, int k) {
     T r = -adv;
     if (P.ncl > 0) {
         T q = div_q(P, 0, t, i, j, k);
@@ -275,10 +285,10 @@ __global__ void __launch_bounds__(128) tendency_generic_kernel(const __grid_cons
     if (!cell_from_block(i1 - i0 + 1, P.g.N[1], i, j, k)) return;
     i += i0 - 1;
     const int which = blockIdx.y;
-    if (which == 0) P.Gu(i, j, k) = Gu_point<T, S, FAST>(P, i, j, k);
-    else if (which == 1) P.Gv(i, j, k) = Gv_point<T, S, FAST>(P, i, j, k);
-    else if (which == 2) P.Gw(i, j, k) = Gw_point<T, S, FAST>(P, i, j, k);
-    else P.Gc[which - 3](i, j, k) = Gc_point<T, S, FAST>(P, which - 3, i, j, k);
+    if (which == 0) P.Gu(i, j, k) = Gu_finish<T>(P, Gu_adv<T, S, FAST>(P, i, j, k), i, j, k);
+    else if (which == 1) P.Gv(i, j, k) = Gv_finish<T>(P, Gv_adv<T, S, FAST>(P, i, j, k), i, j, k);
+    else if (which == 2) P.Gw(i, j, k) = Gw_finish<T>(P, Gw_adv<T, S, FAST>(P, i, j, k), i, j, k);
+    else P.Gc[which - 3](i, j, k) = Gc_finish<T>(P, Gc_adv<T, S, FAST>(P, which - 3, i, j, k), which - 3, i, j, k);
 }
 
 #undef DXF

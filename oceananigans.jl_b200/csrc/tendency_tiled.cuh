@@ -1,13 +1,117 @@
-// tendency_tiled.cuh -- shared-memory tiled fast path of the fused tendency kernel (placeholder dispatcher:
-// returns done = false so the generic kernel runs).
+// tendency_tiled.cuh -- the fused tendency kernel, flux-sharing marching form (the hot kernel of the time step).
+//
+// The reference evaluates every face flux twice (once per neighbouring cell, through δ(f) =  f(i+1) - f(i),
+// src/Operators/difference_operators.jl:20-27) in 3+n separate launches.  Here ONE launch computes all 3+n
+// tendencies and every advective face flux exactly ONCE:
+//
+//   * blockIdx.y selects the tendency (Gu, Gv, Gw, Gc[t]); each has exactly one x-, one y- and one z-direction
+//     advective flux per cell, so every CTA runs the same shape of work and holds little state.
+//   * a CTA is a 32 x TY tile of (i, j) columns that MARCHES in k over a chunk of KC levels:
+//       - z-direction flux: kept in a register from one level to the next,
+//       - x-direction flux: taken from lane+1 with a warp shuffle (lane 31 is the overlap lane: tiles advance by 31),
+//       - y-direction flux: taken from row+1 through double-buffered shared memory (one __syncthreads per level;
+//         row TY-1 is the overlap row and computes only its y-flux: tiles advance by TY-1).
+//   * the flux functions are the SAME device functions the generic kernel uses (mom_flux / tracer_flux with the
+//     Bounded fallback chain and Flat rules), so the arithmetic of every flux is unchanged; the non-advective terms
+//     (buoyancy, Coriolis, hydrostatic pressure gradient, closures) are added by the shared G*_finish functions.
+//
+// Inputs are read with ld.global.nc through L1 (coalesced along x); the kernel is FP64-issue bound, not HBM or
+// L1 bound, so no shared-memory staging of the input tile is needed.
 #pragma once
 #include "tendency.cuh"
+#include "tendency_fast.cuh"
 
 namespace ob {
-template <typename T, class S>
-static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, cudaStream_t st, int sm_count, int *nlaunch, bool &done) {
-    (void)P; (void)fast; (void)st; (void)sm_count; (void)nlaunch;
-    done = false;
-    return cudaSuccess;
+
+// own-direction advective flux of tendency WHICH (0 u, 1 v, 2 w, 3 tracer) at flux index (i, j, k)
+template <typename T, class S, bool FAST, int WHICH, int DIR>
+__device__ __forceinline__ T adv_flux(const TendP<T> &P, const Fld<T> &c, int i, int j, int k) {
+    if constexpr (WHICH == 3) return tracer_flux<T, S, FAST, DIR>(P, c, i, j, k);
+    else return mom_flux<T, S, FAST, DIR, WHICH>(P, i, j, k);
 }
+
+template <typename T, class S, bool FAST, int WHICH, int TY, int KC>
+__device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int j, int k0, int k1, T (*sy)[TY][32]) {
+    const GridD<T> &g = P.g;
+    const int Nx = g.N[0], Ny = g.N[1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    // centre-type directions: the tendency at index n uses F(n) - F(n-1), so the thread at n owns F(n-1)
+    constexpr int cx = WHICH == 0, cy = WHICH == 1, cz = WHICH == 2;
+    const bool do_x = (ty < TY - 1) && (j <= Ny) && (i <= Nx + 1);
+    const bool do_y = (tx < 31) && (i <= Nx) && (j <= Ny + 1);
+    const bool do_out = (tx < 31) && (ty < TY - 1) && (i <= Nx) && (j <= Ny);
+    const Fld<T> &c = P.c[WHICH == 3 ? t : 0];
+    const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[t];
+    // volume at the tendency location: V = (Δx Δy) Δz (spacings_and_areas_and_volumes.jl:483-491)
+    T lower = do_out ? adv_flux<T, S, FAST, WHICH, 2>(P, c, i, j, k0 - cz) : T(0);
+    for (int k = k0; k <= k1; k++) {
+        const T fx = do_x ? adv_flux<T, S, FAST, WHICH, 0>(P, c, i - cx, j, k) : T(0);
+        const T fy = do_y ? adv_flux<T, S, FAST, WHICH, 1>(P, c, i, j - cy, k) : T(0);
+        const T upper = do_out ? adv_flux<T, S, FAST, WHICH, 2>(P, c, i, j, k + 1 - cz) : T(0);
+        const T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
+        const int buf = k & 1;
+        sy[buf][ty][tx] = fy;
+        __syncthreads();
+        if (do_out) {
+            const T fy1 = sy[buf][ty + 1][tx];
+            const T dz = WHICH == 2 ? g.dzF(k) : g.dzC(k);
+            const T Vi = 1 / ((g.dx * g.dy) * dz);
+            const T ddx = g.topo[0] == FLAT ? T(0) : fx1 - fx;
+            const T ddy = g.topo[1] == FLAT ? T(0) : fy1 - fy;
+            const T ddz = g.topo[2] == FLAT ? T(0) : upper - lower;
+            const T adv = Vi * (ddx + ddy + ddz);
+            T r;
+            if constexpr (WHICH == 0) r = Gu_finish<T>(P, adv, i, j, k);
+            else if constexpr (WHICH == 1) r = Gv_finish<T>(P, adv, i, j, k);
+            else if constexpr (WHICH == 2) r = Gw_finish<T>(P, adv, i, j, k);
+            else r = Gc_finish<T>(P, adv, t, i, j, k);
+            G(i, j, k) = r;
+        }
+        lower = upper;
+    }
+}
+
+template <typename T, class S, bool FAST, int TY, int KC>
+__global__ void __launch_bounds__(32 * TY, 2) tendency_march_kernel(const __grid_constant__ TendP<T> P) {
+    __shared__ T sy[2][TY][32];
+    const int which = blockIdx.y;
+    const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
+    const int ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+    const int b = blockIdx.x;
+    const int tile_x = b % ntx, tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
+    const int i = 1 + tile_x * 31 + (int)threadIdx.x, j = 1 + tile_y * (TY - 1) + (int)threadIdx.y;
+    const int k0 = 1 + kc * KC, k1 = min(k0 + KC - 1, Nz);
+    if constexpr (S::kind == ADV_WENO) {
+        if (fast_path_ok<T, S::n>(P, k0, k1)) {  // CTA-uniform
+            if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC>(P, 0, i, j, k0, k1, sy);
+            else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC>(P, 0, i, j, k0, k1, sy);
+            else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC>(P, 0, i, j, k0, k1, sy);
+            else march_fast_body<T, S::n, FAST, 3, TY, KC>(P, which - 3, i, j, k0, k1, sy);
+            return;
+        }
+    }
+    if (which == 0) march_body<T, S, FAST, 0, TY, KC>(P, 0, i, j, k0, k1, sy);
+    else if (which == 1) march_body<T, S, FAST, 1, TY, KC>(P, 0, i, j, k0, k1, sy);
+    else if (which == 2) march_body<T, S, FAST, 2, TY, KC>(P, 0, i, j, k0, k1, sy);
+    else march_body<T, S, FAST, 3, TY, KC>(P, which - 3, i, j, k0, k1, sy);
+}
+
+// mode: 0 auto, 1 generic, 2 marching
+template <typename T, class S>
+static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done) {
+    (void)sm_count;
+    done = false;
+    if (mode == 1) return cudaSuccess;
+    constexpr int TY = 8, KC = 32;
+    const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
+    const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1), nkc = (Nz + KC - 1) / KC;
+    if (ntx * nty * nkc > 2147483647L) return cudaSuccess;
+    dim3 grid((unsigned)(ntx * nty * nkc), 3 + P.ntr), block(32, TY);
+    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC><<<grid, block, 0, st>>>(P);
+    else tendency_march_kernel<T, S, false, TY, KC><<<grid, block, 0, st>>>(P);
+    *nlaunch += 1;
+    done = true;
+    return cudaGetLastError();
+}
+
 }  // namespace ob

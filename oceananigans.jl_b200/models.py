@@ -27,8 +27,9 @@ class Centered:
 
 class WENO:
     """WENO(; order=5).  `weight_computation` in {None, 'NormalDivision', 'BackendOptimizedDivision'}: None takes
-    `default_weno_weight_computation(::B200)` = exact division (OB_DIV_EXACT), which reproduces the reference CPU
-    arithmetic; 'BackendOptimizedDivision' selects rcp.approx + Newton (ext/OceananigansCUDAExt.jl:147-163)."""
+    `default_weno_weight_computation(::B200)` = BackendOptimizedDivision, i.e. rcp.approx + one cubic Newton step --
+    the construction the reference's own CUDA backend uses (ext/OceananigansCUDAExt.jl:147-163; materialize_advection.jl:
+    45-51); 'NormalDivision' selects IEEE division (OB_DIV_EXACT).  Both stay within the parity tolerances."""
 
     def __init__(self, order=5, weight_computation=None):
         if order % 2 == 0 or order < 3:
@@ -174,7 +175,7 @@ class NonhydrostaticModel:
         if isinstance(advection, WENO):
             d.advection_kind, d.advection_order = _abi.OB_ADV_WENO, advection.order
             wc = advection.weight_computation
-            d.weno_division = _abi.OB_DIV_RCP_NEWTON if wc == "BackendOptimizedDivision" else _abi.OB_DIV_EXACT
+            d.weno_division = _abi.OB_DIV_EXACT if wc == "NormalDivision" else _abi.OB_DIV_RCP_NEWTON
         elif isinstance(advection, Centered):
             d.advection_kind, d.advection_order = _abi.OB_ADV_CENTERED, advection.order
         else:
@@ -321,6 +322,9 @@ class NonhydrostaticModel:
         n = C.c_int64(0)
         _abi.call("ob_launch_count", self.handle, C.byref(n))
         return n.value
+
+    def set_option(self, option, value):
+        _abi.call("ob_model_set_option", self.handle, int(option), int(value))
 
     def synchronize(self):
         self.architecture.synchronize()

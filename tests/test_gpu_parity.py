@@ -83,19 +83,34 @@ def _sync_state_from_oracle(om, bm):
         bm.tracers[n].set_parent(f.data)
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["generic", "marching"])
+@pytest.mark.parametrize("division", ["NormalDivision", "BackendOptimizedDivision"])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_tendencies_match_oracle(arch, name):
+def test_tendencies_match_oracle(arch, name, division, kernel):
     """one evaluation of update_state! (halo fills, closure fields, pHY', fused tendency kernel) on bit-identical
-    inputs: every Gⁿ and closure field <= 1e-13 of its own scale"""
-    om, bm = pair(CONFIGS[name], arch, seed=11)
+    inputs: every Gⁿ and closure field <= 1e-13 of its own scale -- for both tendency kernels (one thread per cell /
+    flux-sharing marching) and both WENO division modes"""
+    from ocean_b200 import _abi
+    d = dict(CONFIGS[name].__dict__)
+    d["weno_division"] = division
+    om, bm = pair(Config(**d), arch, seed=11)
+    bm.set_option(_abi.OB_OPT_TENDENCY_KERNEL, kernel)
     _sync_state_from_oracle(om, bm)
     om.update_state()
     bm.update_state()
     N, H = om.grid.N, om.grid.H
     sl = (slice(H[2], H[2] + N[2]), slice(H[1], H[1] + N[1]), slice(H[0], H[0] + N[0]))
+    umax = max(np.abs(f.data).max() for f in (om.u, om.v, om.w))
+    dmin = min(float(np.min(om.grid.dc[d])) for d in range(3) if om.grid.topo[d] != 2)
     for n, (og, bg) in enumerate(zip(om.Gn, bm.Gn)):
         a, b = bg.parent()[sl], og.data[sl]
-        assert rel_l2(a, b) <= 1e-13, (name, n, rel_l2(a, b))
+        # a tracer tendency is a cancelling sum of fluxes of size |u||c|/Δ: the attainable accuracy is relative to that
+        # scale, not to |G| (T = 20, S = 35 in the LES configurations)
+        tol = 1e-13
+        if n >= 3:
+            cmax = np.abs(om.tracers[n - 3].data).max()
+            tol *= max(1.0, umax * cmax / dmin / max(np.abs(b).max(), 1e-300))
+        assert rel_l2(a, b) <= tol, (name, n, rel_l2(a, b), tol)
     for m, cf in enumerate(bm.closure_fields):
         if "nue" in cf:
             assert rel_l2(cf["nue"].parent(), om.nue[m].data) <= 1e-13, (name, "nue")
@@ -163,12 +178,12 @@ def test_closure_fields_match_oracle(arch):
                 assert rel_l2(a, b) <= 1e-12, (name, "kappae", t, rel_l2(a, b))
 
 
-def test_fast_division_mode_within_tolerance(arch):
-    """WENO(weight_computation=BackendOptimizedDivision): rcp.approx + Newton (the reference's CUDA newton_div) stays
-    within the 1-step tolerance of the exact-division CPU arithmetic."""
+def test_exact_division_mode_within_tolerance(arch):
+    """WENO(weight_computation=NormalDivision): IEEE division instead of the default rcp.approx + Newton (the
+    reference's CUDA newton_div); both stay within the 1-step tolerance of the CPU arithmetic."""
     import ocean_b200 as ob
     d = dict(CONFIGS["ppp_weno5"].__dict__)
-    d["weno_division"] = "BackendOptimizedDivision"
+    d["weno_division"] = "NormalDivision"
     om, bm = pair(Config(**d), arch, seed=8)
     om.time_step(1e-3)
     ob.time_step(bm, 1e-3)
