@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) smagorinsky_kernel(const __grid_constant_
     T cs2;
     if (c.lilly) {
         auto dzb = [&](int a, int b, int cc) {
-            return (g.topo[2] == FLAT ? T(0) : bpert(P, a, b, cc) - bpert(P, a, b, cc - 1)) * (1 / g.dzF(cc));
+            return (g.topo[2] == FLAT ? T(0) : bpert(P, a, b, cc) - bpert(P, a, b, cc - 1)) * g.rdzF(cc);
         };
         const T N2 = Ic1<T, 2>(g, dzb, i, j, k);
         const T N2p = fmax(T(0), N2);
@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<
             const T r = r1 + r2 + r3;
             T cbz = 0;
             if (cl.amd_has_cb) {
-                auto dxb = [&](int a, int b, int c) { return (g.topo[0] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a - 1, b, c)) * (1 / g.dx); };
-                auto dyb = [&](int a, int b, int c) { return (g.topo[1] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a, b - 1, c)) * (1 / g.dy); };
-                auto dzb = [&](int a, int b, int c) { return (g.topo[2] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a, b, c - 1)) * (1 / g.dzF(c)); };
+                auto dxb = [&](int a, int b, int c) { return (g.topo[0] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a - 1, b, c)) * g.rdx; };
+                auto dyb = [&](int a, int b, int c) { return (g.topo[1] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a, b - 1, c)) * g.rdy; };
+                auto dzb = [&](int a, int b, int c) { return (g.topo[2] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a, b, c - 1)) * g.rdzF(c); };
                 const T wxbx = IXZ(n_dx_w) * fx * Ic1<T, 0>(g, dxb, i, j, k);
                 const T wyby = IYZ(n_dy_w) * fy * Ic1<T, 1>(g, dyb, i, j, k);
                 const T wzbz = wz * fz * Ic1<T, 2>(g, dzb, i, j, k);
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<
     } else {
         const int t = blockIdx.y - 1;
         const Fld<T> &c = P.c[t];
-        auto n_dx_c = [&](int a, int b, int cc) { return dfx(a) * ((g.topo[0] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a - 1, b, cc)) * (1 / g.dx)); };
-        auto n_dy_c = [&](int a, int b, int cc) { return dfy(b) * ((g.topo[1] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a, b - 1, cc)) * (1 / g.dy)); };
-        auto n_dz_c = [&](int a, int b, int cc) { return dfz(cc) * ((g.topo[2] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a, b, cc - 1)) * (1 / g.dzF(cc))); };
+        auto n_dx_c = [&](int a, int b, int cc) { return dfx(a) * ((g.topo[0] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a - 1, b, cc)) * g.rdx); };
+        auto n_dy_c = [&](int a, int b, int cc) { return dfy(b) * ((g.topo[1] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a, b - 1, cc)) * g.rdy); };
+        auto n_dz_c = [&](int a, int b, int cc) { return dfz(cc) * ((g.topo[2] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a, b, cc - 1)) * g.rdzF(cc)); };
         auto n_dx_c2 = [&](int a, int b, int cc) { T x = n_dx_c(a, b, cc); return x * x; };
         auto n_dy_c2 = [&](int a, int b, int cc) { T x = n_dy_c(a, b, cc); return x * x; };
         auto n_dz_c2 = [&](int a, int b, int cc) { T x = n_dz_c(a, b, cc); return x * x; };

@@ -40,8 +40,18 @@ struct GridD {
     T dx, dy, dz;        // regular spacings (1 for Flat: spacings_and_areas_and_volumes.jl:138)
     const T *dzf;        // stretched z: Δzᵃᵃᶠ, pre-offset so dzf[k] is logical k; nullptr when regular
     const T *dzc;        // stretched z: Δzᵃᵃᶜ
+    // reciprocals, precomputed on the host with the same IEEE division the reference evaluates per call
+    // (Δ⁻¹ = 1/Δ, reciprocal_metric_operators.jl:13-26; V⁻¹ = 1/((Δx Δy) Δz), spacings_and_areas_and_volumes.jl:483-491)
+    T rdx, rdy, rdz;     // 1/Δx, 1/Δy, 1/Δz (regular)
+    T rvol;              // 1/((Δx Δy) Δz) (regular z)
+    const T *rdzf, *rdzc;  // stretched z: 1/Δzᶠ(k), 1/Δzᶜ(k) (pre-offset, logical k)
+    const T *rvf, *rvc;    // stretched z: 1/((Δx Δy) Δzᶠ(k)), 1/((Δx Δy) Δzᶜ(k))
     __device__ __forceinline__ T dzF(int k) const { return dzf ? __ldg(dzf + k) : dz; }
     __device__ __forceinline__ T dzC(int k) const { return dzc ? __ldg(dzc + k) : dz; }
+    __device__ __forceinline__ T rdzF(int k) const { return dzf ? __ldg(rdzf + k) : rdz; }
+    __device__ __forceinline__ T rdzC(int k) const { return dzc ? __ldg(rdzc + k) : rdz; }
+    __device__ __forceinline__ T rVf(int k) const { return dzf ? __ldg(rvf + k) : rvol; }
+    __device__ __forceinline__ T rVc(int k) const { return dzc ? __ldg(rvc + k) : rvol; }
 };
 
 template <typename T>

@@ -19,9 +19,9 @@ __global__ void __launch_bounds__(256) advection_timescale_kernel(const __grid_c
     double best = INFINITY;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
         const int i = 1 + (int)(t % g.N[0]), j = 1 + (int)((t / g.N[0]) % g.N[1]), k = 1 + (int)(t / ((long)g.N[0] * g.N[1]));
-        const T ix = g.topo[0] == FLAT ? T(0) : fabs(P.u.ld(i, j, k)) * (1 / g.dx);
-        const T iy = g.topo[1] == FLAT ? T(0) : fabs(P.v.ld(i, j, k)) * (1 / g.dy);
-        const T iz = g.topo[2] == FLAT ? T(0) : fabs(P.w.ld(i, j, k)) * (1 / g.dzF(k));
+        const T ix = g.topo[0] == FLAT ? T(0) : fabs(P.u.ld(i, j, k)) * g.rdx;
+        const T iy = g.topo[1] == FLAT ? T(0) : fabs(P.v.ld(i, j, k)) * g.rdy;
+        const T iz = g.topo[2] == FLAT ? T(0) : fabs(P.w.ld(i, j, k)) * g.rdzF(k);
         const T inv = ix + iy + iz;
         best = fmin(best, (double)(1 / inv));
     }

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) source_term_kernel(const __grid_constant_
     const T ddx = P.g.topo[0] == FLAT ? T(0) : Ax * P.u.ld(i + 1, j, k) - Ax * P.u.ld(i, j, k);
     const T ddy = P.g.topo[1] == FLAT ? T(0) : Ay * P.v.ld(i, j + 1, k) - Ay * P.v.ld(i, j, k);
     const T ddz = P.g.topo[2] == FLAT ? T(0) : Az * P.w.ld(i, j, k + 1) - Az * P.w.ld(i, j, k);
-    const T Vi = 1 / ((P.g.dx * P.g.dy) * dzc);
+    const T Vi = P.g.rVc(k);
     T div = Vi * (ddx + ddy + ddz);
     if (P.times_dz) div = dzc * div;
     const long o = (i - 1) + (j - 1) * P.ldx + (long)(k - 1) * P.ldxy;
@@ -258,9 +258,9 @@ __global__ void __launch_bounds__(256) pressure_correct_kernel(const __grid_cons
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const T pc = P.p.ld(i, j, k);
-    if (P.g.topo[0] != FLAT) P.u(i, j, k) -= (pc - P.p.ld(i - 1, j, k)) * (1 / P.g.dx);
-    if (P.g.topo[1] != FLAT) P.v(i, j, k) -= (pc - P.p.ld(i, j - 1, k)) * (1 / P.g.dy);
-    if (P.g.topo[2] != FLAT) P.w(i, j, k) -= (pc - P.p.ld(i, j, k - 1)) * (1 / P.g.dzF(k));
+    if (P.g.topo[0] != FLAT) P.u(i, j, k) -= (pc - P.p.ld(i - 1, j, k)) * P.g.rdx;
+    if (P.g.topo[1] != FLAT) P.v(i, j, k) -= (pc - P.p.ld(i, j - 1, k)) * P.g.rdy;
+    if (P.g.topo[2] != FLAT) P.w(i, j, k) -= (pc - P.p.ld(i, j, k - 1)) * P.g.rdzF(k);
 }
 
 // pNHS ./= Δt over the whole parent array (pressure_correction.jl:101-103)

@@ -508,7 +508,7 @@ struct PhaseScope {
 template <typename T>
 struct ModelT : ob_model {
     GridD<T> g;
-    T *d_dzf = nullptr, *d_dzc = nullptr;
+    T *d_dzf = nullptr, *d_dzc = nullptr, *d_rdzf = nullptr, *d_rdzc = nullptr, *d_rvf = nullptr, *d_rvc = nullptr;
     std::vector<T> h_dzf, h_dzc;
     int Hz_ = 0;
     FieldInfo F[128];
@@ -518,6 +518,7 @@ struct ModelT : ob_model {
 
     ~ModelT() override {
         cudaFree(d_dzf); cudaFree(d_dzc); cudaFree(d_partial);
+        cudaFree(d_rdzf); cudaFree(d_rdzc); cudaFree(d_rvf); cudaFree(d_rvc);
         delete solver;
         for (auto e : pool) cudaEventDestroy(e);
     }
@@ -559,6 +560,7 @@ struct ModelT : ob_model {
         g.dy = g.topo[1] == FLAT ? (T)1 : (T)gd.d[1];
         g.dz = g.topo[2] == FLAT ? (T)1 : (T)gd.d[2];
         g.dzf = g.dzc = nullptr;
+        g.rdzf = g.rdzc = g.rvf = g.rvc = nullptr;
         Hz_ = g.H[2];
         if (gd.dzf_host) {
             if (!gd.dzc_host) return fail(OB_ERR_INVALID, "dzf given without dzc");
@@ -570,7 +572,21 @@ struct ModelT : ob_model {
             CUDA_TRY(cudaMemcpy(d_dzc, h_dzc.data(), sizeof(T) * gd.n_dzc, cudaMemcpyHostToDevice));
             g.dzf = d_dzf + Hz_;       // logical k -> dzf[k + Hz]
             g.dzc = d_dzc + Hz_ - 1;   // logical k -> dzc[k + Hz - 1]
+            // reciprocal metrics, same IEEE divisions as the reference evaluates per call
+            std::vector<T> rf(gd.n_dzf), rc(gd.n_dzc), vf(gd.n_dzf), vc(gd.n_dzc);
+            for (int q = 0; q < gd.n_dzf; q++) { rf[q] = (T)1 / h_dzf[q]; vf[q] = (T)1 / ((g.dx * g.dy) * h_dzf[q]); }
+            for (int q = 0; q < gd.n_dzc; q++) { rc[q] = (T)1 / h_dzc[q]; vc[q] = (T)1 / ((g.dx * g.dy) * h_dzc[q]); }
+            CUDA_TRY(cudaMalloc(&d_rdzf, sizeof(T) * gd.n_dzf)); CUDA_TRY(cudaMalloc(&d_rvf, sizeof(T) * gd.n_dzf));
+            CUDA_TRY(cudaMalloc(&d_rdzc, sizeof(T) * gd.n_dzc)); CUDA_TRY(cudaMalloc(&d_rvc, sizeof(T) * gd.n_dzc));
+            CUDA_TRY(cudaMemcpy(d_rdzf, rf.data(), sizeof(T) * gd.n_dzf, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(d_rvf, vf.data(), sizeof(T) * gd.n_dzf, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(d_rdzc, rc.data(), sizeof(T) * gd.n_dzc, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(d_rvc, vc.data(), sizeof(T) * gd.n_dzc, cudaMemcpyHostToDevice));
+            g.rdzf = d_rdzf + Hz_; g.rvf = d_rvf + Hz_;
+            g.rdzc = d_rdzc + Hz_ - 1; g.rvc = d_rvc + Hz_ - 1;
         }
+        g.rdx = (T)1 / g.dx; g.rdy = (T)1 / g.dy; g.rdz = (T)1 / g.dz;
+        g.rvol = (T)1 / ((g.dx * g.dy) * g.dz);
         ntr = d->n_tracers;
         ncl = d->n_closures;
         if (ntr > OB_MAXTR || ncl > OB_MAXCL) return fail(OB_ERR_INVALID, "too many tracers/closures");

@@ -81,15 +81,15 @@ template <typename T> struct Grad {
     __device__ __forceinline__ bool fx() const { return P.g.topo[0] == FLAT; }
     __device__ __forceinline__ bool fy() const { return P.g.topo[1] == FLAT; }
     __device__ __forceinline__ bool fz() const { return P.g.topo[2] == FLAT; }
-    __device__ __forceinline__ T dx_u(int i, int j, int k) const { return (fx() ? T(0) : P.u.ld(i + 1, j, k) - P.u.ld(i, j, k)) * (1 / DXC); }
-    __device__ __forceinline__ T dy_v(int i, int j, int k) const { return (fy() ? T(0) : P.v.ld(i, j + 1, k) - P.v.ld(i, j, k)) * (1 / DYC); }
-    __device__ __forceinline__ T dz_w(int i, int j, int k) const { return (fz() ? T(0) : P.w.ld(i, j, k + 1) - P.w.ld(i, j, k)) * (1 / DZC(k)); }
-    __device__ __forceinline__ T dx_v(int i, int j, int k) const { return (fx() ? T(0) : P.v.ld(i, j, k) - P.v.ld(i - 1, j, k)) * (1 / DXF); }
-    __device__ __forceinline__ T dy_u(int i, int j, int k) const { return (fy() ? T(0) : P.u.ld(i, j, k) - P.u.ld(i, j - 1, k)) * (1 / DYF); }
-    __device__ __forceinline__ T dx_w(int i, int j, int k) const { return (fx() ? T(0) : P.w.ld(i, j, k) - P.w.ld(i - 1, j, k)) * (1 / DXF); }
-    __device__ __forceinline__ T dz_u(int i, int j, int k) const { return (fz() ? T(0) : P.u.ld(i, j, k) - P.u.ld(i, j, k - 1)) * (1 / DZF(k)); }
-    __device__ __forceinline__ T dy_w(int i, int j, int k) const { return (fy() ? T(0) : P.w.ld(i, j, k) - P.w.ld(i, j - 1, k)) * (1 / DYF); }
-    __device__ __forceinline__ T dz_v(int i, int j, int k) const { return (fz() ? T(0) : P.v.ld(i, j, k) - P.v.ld(i, j, k - 1)) * (1 / DZF(k)); }
+    __device__ __forceinline__ T dx_u(int i, int j, int k) const { return (fx() ? T(0) : P.u.ld(i + 1, j, k) - P.u.ld(i, j, k)) * P.g.rdx; }
+    __device__ __forceinline__ T dy_v(int i, int j, int k) const { return (fy() ? T(0) : P.v.ld(i, j + 1, k) - P.v.ld(i, j, k)) * P.g.rdy; }
+    __device__ __forceinline__ T dz_w(int i, int j, int k) const { return (fz() ? T(0) : P.w.ld(i, j, k + 1) - P.w.ld(i, j, k)) * P.g.rdzC(k); }
+    __device__ __forceinline__ T dx_v(int i, int j, int k) const { return (fx() ? T(0) : P.v.ld(i, j, k) - P.v.ld(i - 1, j, k)) * P.g.rdx; }
+    __device__ __forceinline__ T dy_u(int i, int j, int k) const { return (fy() ? T(0) : P.u.ld(i, j, k) - P.u.ld(i, j - 1, k)) * P.g.rdy; }
+    __device__ __forceinline__ T dx_w(int i, int j, int k) const { return (fx() ? T(0) : P.w.ld(i, j, k) - P.w.ld(i - 1, j, k)) * P.g.rdx; }
+    __device__ __forceinline__ T dz_u(int i, int j, int k) const { return (fz() ? T(0) : P.u.ld(i, j, k) - P.u.ld(i, j, k - 1)) * P.g.rdzF(k); }
+    __device__ __forceinline__ T dy_w(int i, int j, int k) const { return (fy() ? T(0) : P.w.ld(i, j, k) - P.w.ld(i, j - 1, k)) * P.g.rdy; }
+    __device__ __forceinline__ T dz_v(int i, int j, int k) const { return (fz() ? T(0) : P.v.ld(i, j, k) - P.v.ld(i, j, k - 1)) * P.g.rdzF(k); }
     __device__ __forceinline__ T S11(int i, int j, int k) const { return dx_u(i, j, k); }
     __device__ __forceinline__ T S22(int i, int j, int k) const { return dy_v(i, j, k); }
     __device__ __forceinline__ T S33(int i, int j, int k) const { return dz_w(i, j, k); }
@@ -144,19 +144,19 @@ template <typename T> struct VFlux {
 
 template <typename T> __device__ __forceinline__ T div_tau1(const TendP<T> &P, int m, int i, int j, int k) {
     VFlux<T> F(P, m);
-    T Vi = 1 / ((DXF * DYC) * DZC(k));
+    T Vi = P.g.rVc(k);
     return Vi * (DELTA_(F.ux(i, j, k), F.ux(i - 1, j, k), 0) + DELTA_(F.uy(i, j + 1, k), F.uy(i, j, k), 1) +
                  DELTA_(F.uz(i, j, k + 1), F.uz(i, j, k), 2));
 }
 template <typename T> __device__ __forceinline__ T div_tau2(const TendP<T> &P, int m, int i, int j, int k) {
     VFlux<T> F(P, m);
-    T Vi = 1 / ((DXC * DYF) * DZC(k));
+    T Vi = P.g.rVc(k);
     return Vi * (DELTA_(F.vx(i + 1, j, k), F.vx(i, j, k), 0) + DELTA_(F.vy(i, j, k), F.vy(i, j - 1, k), 1) +
                  DELTA_(F.vz(i, j, k + 1), F.vz(i, j, k), 2));
 }
 template <typename T> __device__ __forceinline__ T div_tau3(const TendP<T> &P, int m, int i, int j, int k) {
     VFlux<T> F(P, m);
-    T Vi = 1 / ((DXC * DYC) * DZF(k));
+    T Vi = P.g.rVf(k);
     return Vi * (DELTA_(F.wx(i + 1, j, k), F.wx(i, j, k), 0) + DELTA_(F.wy(i, j + 1, k), F.wy(i, j, k), 1) +
                  DELTA_(F.wz(i, j, k), F.wz(i, j, k - 1), 2));
 }
@@ -172,13 +172,13 @@ template <typename T, int D> __device__ __forceinline__ T qflux(const TendP<T> &
     const Fld<T> &c = P.c[t];
     int a = i, b = j, cc = k;
     shift<D>(a, b, cc, -1);
-    T rd = D == 0 ? 1 / DXF : D == 1 ? 1 / DYF : 1 / DZF(k);
+    T rd = D == 0 ? P.g.rdx : D == 1 ? P.g.rdy : P.g.rdzF(k);
     T A = D == 0 ? DYC * DZC(k) : D == 1 ? DXC * DZC(k) : DXC * DYC;
     T dc = (P.g.topo[D] == FLAT ? T(0) : c.ld(i, j, k) - c.ld(a, b, cc)) * rd;
     return A * (-kap<T, D>(P, m, t, i, j, k) * dc);
 }
 template <typename T> __device__ __forceinline__ T div_q(const TendP<T> &P, int m, int t, int i, int j, int k) {
-    T Vi = 1 / ((DXC * DYC) * DZC(k));
+    T Vi = P.g.rVc(k);
     return Vi * (DELTA_((qflux<T, 0>(P, m, t, i + 1, j, k)), (qflux<T, 0>(P, m, t, i, j, k)), 0) +
                  DELTA_((qflux<T, 1>(P, m, t, i, j + 1, k)), (qflux<T, 1>(P, m, t, i, j, k)), 1) +
                  DELTA_((qflux<T, 2>(P, m, t, i, j, k + 1)), (qflux<T, 2>(P, m, t, i, j, k)), 2));
@@ -195,7 +195,7 @@ template <typename T> __device__ __forceinline__ T bpert(const TendP<T> &P, int 
 // Every tendency = finish(advective flux divergence); the generic kernel evaluates each face flux through the
 // difference operator as the reference does, the marching kernel (tendency_tiled.cuh) shares face fluxes between cells.
 template <typename T, class S, bool FAST> __device__ __forceinline__ T Gu_adv(const TendP<T> &P, int i, int j, int k) {
-    T Vi = 1 / ((DXF * DYC) * DZC(k));
+    T Vi = P.g.rVc(k);
     return Vi * (DELTA_((mom_flux<T, S, FAST, 0, 0>(P, i, j, k)), (mom_flux<T, S, FAST, 0, 0>(P, i - 1, j, k)), 0) +
                  DELTA_((mom_flux<T, S, FAST, 1, 0>(P, i, j + 1, k)), (mom_flux<T, S, FAST, 1, 0>(P, i, j, k)), 1) +
                  DELTA_((mom_flux<T, S, FAST, 2, 0>(P, i, j, k + 1)), (mom_flux<T, S, FAST, 2, 0>(P, i, j, k)), 2));
@@ -210,7 +210,7 @@ template <typename T> __device__ __forceinline__ T Gu_finish(const TendP<T> &P, 
         T I = fy ? Ix(j) : T(0.5) * (Ix(j) + Ix(j + 1));
         r = r - (-fbar * I * (1 / (DXF * DZC(k))));
     }
-    if (P.has_pHY) r = r - (P.g.topo[0] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i - 1, j, k)) * (1 / DXF);
+    if (P.has_pHY) r = r - (P.g.topo[0] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i - 1, j, k)) * P.g.rdx;
     if (P.ncl > 0) {
         T t = div_tau1(P, 0, i, j, k);
         for (int m = 1; m < P.ncl; m++) t = t + div_tau1(P, m, i, j, k);
@@ -219,7 +219,7 @@ template <typename T> __device__ __forceinline__ T Gu_finish(const TendP<T> &P, 
     return r;
 }
 template <typename T, class S, bool FAST> __device__ __forceinline__ T Gv_adv(const TendP<T> &P, int i, int j, int k) {
-    T Vi = 1 / ((DXC * DYF) * DZC(k));
+    T Vi = P.g.rVc(k);
     return Vi * (DELTA_((mom_flux<T, S, FAST, 0, 1>(P, i + 1, j, k)), (mom_flux<T, S, FAST, 0, 1>(P, i, j, k)), 0) +
                  DELTA_((mom_flux<T, S, FAST, 1, 1>(P, i, j, k)), (mom_flux<T, S, FAST, 1, 1>(P, i, j - 1, k)), 1) +
                  DELTA_((mom_flux<T, S, FAST, 2, 1>(P, i, j, k + 1)), (mom_flux<T, S, FAST, 2, 1>(P, i, j, k)), 2));
@@ -234,7 +234,7 @@ template <typename T> __device__ __forceinline__ T Gv_finish(const TendP<T> &P, 
         T I = fy ? Ix(j) : T(0.5) * (Ix(j - 1) + Ix(j));
         r = r - (fbar * I * (1 / (DYF * DZC(k))));
     }
-    if (P.has_pHY) r = r - (P.g.topo[1] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i, j - 1, k)) * (1 / DYF);
+    if (P.has_pHY) r = r - (P.g.topo[1] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i, j - 1, k)) * P.g.rdy;
     if (P.ncl > 0) {
         T t = div_tau2(P, 0, i, j, k);
         for (int m = 1; m < P.ncl; m++) t = t + div_tau2(P, m, i, j, k);
@@ -243,7 +243,7 @@ template <typename T> __device__ __forceinline__ T Gv_finish(const TendP<T> &P, 
     return r;
 }
 template <typename T, class S, bool FAST> __device__ __forceinline__ T Gw_adv(const TendP<T> &P, int i, int j, int k) {
-    T Vi = 1 / ((DXC * DYC) * DZF(k));
+    T Vi = P.g.rVf(k);
     return Vi * (DELTA_((mom_flux<T, S, FAST, 0, 2>(P, i + 1, j, k)), (mom_flux<T, S, FAST, 0, 2>(P, i, j, k)), 0) +
                  DELTA_((mom_flux<T, S, FAST, 1, 2>(P, i, j + 1, k)), (mom_flux<T, S, FAST, 1, 2>(P, i, j, k)), 1) +
                  DELTA_((mom_flux<T, S, FAST, 2, 2>(P, i, j, k)), (mom_flux<T, S, FAST, 2, 2>(P, i, j, k - 1)), 2));
@@ -262,7 +262,7 @@ template <typename T> __device__ __forceinline__ T Gw_finish(const TendP<T> &P, 
 }
 template <typename T, class S, bool FAST> __device__ __forceinline__ T Gc_adv(const TendP<T> &P, int t, int i, int j, int k) {
     const Fld<T> &c = P.c[t];
-    T Vi = 1 / ((DXC * DYC) * DZC(k));
+    T Vi = P.g.rVc(k);
     return Vi * (DELTA_((tracer_flux<T, S, FAST, 0>(P, c, i + 1, j, k)), (tracer_flux<T, S, FAST, 0>(P, c, i, j, k)), 0) +
                  DELTA_((tracer_flux<T, S, FAST, 1>(P, c, i, j + 1, k)), (tracer_flux<T, S, FAST, 1>(P, c, i, j, k)), 1) +
                  DELTA_((tracer_flux<T, S, FAST, 2>(P, c, i, j, k + 1)), (tracer_flux<T, S, FAST, 2>(P, c, i, j, k)), 2));

@@ -81,6 +81,124 @@ __device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Non-advective terms on the fast path: the arithmetic of Gu/Gv/Gw/Gc_finish (tendency.cuh) restated with offsets
+// from the thread's own point (a, b, c are compile-time after inlining) so that every load is base + constant.
+// Valid where x, y, z are not Flat and every field shares the strides (sy, sz).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct FastTerms {
+    const TendP<T> &P;
+    const T *u, *v, *w;   // at the thread's (i, j, k)
+    long eo;              // element offset of (i, j, k) relative to logical (0, 0, 0): i + j*sy + k*sz
+    long sy, sz;
+    int k;
+    __device__ __forceinline__ T ld(const T *p, int a, int b, int c) const { return __ldg(p + (a + b * sy + c * sz)); }
+    __device__ __forceinline__ const T *at(const Fld<T> &f) const { return f.p + f.off + eo; }
+    __device__ __forceinline__ T dzC(int c) const { return P.g.dzC(k + c); }
+    __device__ __forceinline__ T dzF(int c) const { return P.g.dzF(k + c); }
+    // velocity gradients (velocity_tracer_gradients.jl:6-19)
+    __device__ __forceinline__ T dx_u(int a, int b, int c) const { return (ld(u, a + 1, b, c) - ld(u, a, b, c)) * P.g.rdx; }
+    __device__ __forceinline__ T dy_v(int a, int b, int c) const { return (ld(v, a, b + 1, c) - ld(v, a, b, c)) * P.g.rdy; }
+    __device__ __forceinline__ T dz_w(int a, int b, int c) const { return (ld(w, a, b, c + 1) - ld(w, a, b, c)) * P.g.rdzC(k + c); }
+    __device__ __forceinline__ T dx_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a - 1, b, c)) * P.g.rdx; }
+    __device__ __forceinline__ T dy_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b - 1, c)) * P.g.rdy; }
+    __device__ __forceinline__ T dx_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a - 1, b, c)) * P.g.rdx; }
+    __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b, c - 1)) * P.g.rdzF(k + c); }
+    __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a, b - 1, c)) * P.g.rdy; }
+    __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a, b, c - 1)) * P.g.rdzF(k + c); }
+    __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * (dy_u(a, b, c) + dx_v(a, b, c)); }
+    __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * (dz_u(a, b, c) + dx_w(a, b, c)); }
+    __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * (dz_v(a, b, c) + dy_w(a, b, c)); }
+    // ℑ of a ccc array to faces (interpolation_operators.jl:8-71): D = direction of the -1 shift
+    __device__ __forceinline__ T If1(const T *f, int D, int a, int b, int c) const {
+        return T(0.5) * (ld(f, a - (D == 0), b - (D == 1), c - (D == 2)) + ld(f, a, b, c));
+    }
+    __device__ __forceinline__ T If2(const T *f, int D2, int D1, int a, int b, int c) const {
+        return T(0.5) * (If1(f, D1, a - (D2 == 0), b - (D2 == 1), c - (D2 == 2)) + If1(f, D1, a, b, c));
+    }
+    // viscosity of closure m at ccc / ffc / fcf / cff (abstract_scalar_diffusivity_closure.jl:330-351)
+    __device__ __forceinline__ T nu_ccc(int m, const T *ne, int a, int b, int c) const { return ne ? ld(ne, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_ffc(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 1, 0, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_fcf(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 0, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_cff(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 1, a, b, c) : P.cl[m].nu; }
+    // Ax_q(viscous flux) = area * (-2 ν Σ) (closure_kernel_operators.jl:20-40)
+    __device__ __forceinline__ T ux(int m, const T *ne, int a, int b, int c) const { return (P.g.dy * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dx_u(a, b, c))); }
+    __device__ __forceinline__ T uy(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T uz(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * P.g.dy) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T vx(int m, const T *ne, int a, int b, int c) const { return (P.g.dy * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T vy(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dy_v(a, b, c))); }
+    __device__ __forceinline__ T vz(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * P.g.dy) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wx(int m, const T *ne, int a, int b, int c) const { return (P.g.dy * dzF(c)) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T wy(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * dzF(c)) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wz(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * P.g.dy) * (-2 * (nu_ccc(m, ne, a, b, c) * dz_w(a, b, c))); }
+    __device__ __forceinline__ const T *nue_ptr(int m) const { return P.cl[m].kind == CL_SCALAR ? nullptr : at(P.nue[m]); }
+    template <int WHICH> __device__ __forceinline__ T div_tau(int m) const {
+        const T *ne = nue_ptr(m);
+        if constexpr (WHICH == 0)
+            return P.g.rVc(k) * ((ux(m, ne, 0, 0, 0) - ux(m, ne, -1, 0, 0)) + (uy(m, ne, 0, 1, 0) - uy(m, ne, 0, 0, 0)) + (uz(m, ne, 0, 0, 1) - uz(m, ne, 0, 0, 0)));
+        else if constexpr (WHICH == 1)
+            return P.g.rVc(k) * ((vx(m, ne, 1, 0, 0) - vx(m, ne, 0, 0, 0)) + (vy(m, ne, 0, 0, 0) - vy(m, ne, 0, -1, 0)) + (vz(m, ne, 0, 0, 1) - vz(m, ne, 0, 0, 0)));
+        else
+            return P.g.rVf(k) * ((wx(m, ne, 1, 0, 0) - wx(m, ne, 0, 0, 0)) + (wy(m, ne, 0, 1, 0) - wy(m, ne, 0, 0, 0)) + (wz(m, ne, 0, 0, 0) - wz(m, ne, 0, 0, -1)));
+    }
+    // diffusive flux of tracer t along D at the face (a, b, c) (abstract_scalar_diffusivity_closure.jl:260-262)
+    __device__ __forceinline__ T qflux(int m, int t, const T *cp, const T *kf, int D, int a, int b, int c) const {
+        const int kind = P.cl[m].kind;
+        const T kap = kind == CL_SCALAR ? P.cl[m].kappa[t] : kind == CL_SMAG ? If1(kf, D, a, b, c) / P.cl[m].Pr[t] : If1(kf, D, a, b, c);
+        const T rd = D == 0 ? P.g.rdx : D == 1 ? P.g.rdy : P.g.rdzF(k + c);
+        const T A = D == 0 ? P.g.dy * dzC(c) : D == 1 ? P.g.dx * dzC(c) : P.g.dx * P.g.dy;
+        const T dc = (ld(cp, a, b, c) - ld(cp, a - (D == 0), b - (D == 1), c - (D == 2))) * rd;
+        return A * (-kap * dc);
+    }
+    __device__ __forceinline__ T div_q(int m, int t, const T *cp) const {
+        const int kind = P.cl[m].kind;
+        const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][t]);
+        return P.g.rVc(k) * ((qflux(m, t, cp, kf, 0, 1, 0, 0) - qflux(m, t, cp, kf, 0, 0, 0, 0)) + (qflux(m, t, cp, kf, 1, 0, 1, 0) - qflux(m, t, cp, kf, 1, 0, 0, 0)) +
+                             (qflux(m, t, cp, kf, 2, 0, 0, 1) - qflux(m, t, cp, kf, 2, 0, 0, 0)));
+    }
+    __device__ __forceinline__ T bpert(int c) const {
+        if (P.buoy == BUOY_TRACER) return ld(at(P.c[P.ib]), 0, 0, c);
+        if (P.buoy == BUOY_SEAWATER) return P.grav * (P.alpha * ld(at(P.c[P.iT]), 0, 0, c) - P.beta * ld(at(P.c[P.iS]), 0, 0, c));
+        return 0;
+    }
+    // the tendency assemblers (nonhydrostatic_tendency_kernel_functions.jl:71-302), same term order as G*_finish
+    template <int WHICH> __device__ __forceinline__ T finish(T adv, int t, const T *cp) const {
+        T r = -adv;
+        if constexpr (WHICH == 0) {
+            if (P.has_cor) {
+                const T fbar = T(0.5) * (P.f + P.f);
+                const T A = P.g.dx * dzC(0);
+                const T I = T(0.5) * (T(0.5) * (A * ld(v, -1, 0, 0) + A * ld(v, 0, 0, 0)) + T(0.5) * (A * ld(v, -1, 1, 0) + A * ld(v, 0, 1, 0)));
+                r = r - (-fbar * I * (1 / (P.g.dx * dzC(0))));
+            }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, -1, 0, 0)) * P.g.rdx; }
+        } else if constexpr (WHICH == 1) {
+            if (P.has_cor) {
+                const T fbar = T(0.5) * (P.f + P.f);
+                const T A = P.g.dy * dzC(0);
+                const T I = T(0.5) * (T(0.5) * (A * ld(u, 0, -1, 0) + A * ld(u, 1, -1, 0)) + T(0.5) * (A * ld(u, 0, 0, 0) + A * ld(u, 1, 0, 0)));
+                r = r - (fbar * I * (1 / (P.g.dy * dzC(0))));
+            }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, 0, -1, 0)) * P.g.rdy; }
+        } else if constexpr (WHICH == 2) {
+            if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
+        }
+        if (P.ncl > 0) {
+            if constexpr (WHICH == 3) {
+                T q = div_q(0, t, cp);
+                for (int m = 1; m < P.ncl; m++) q = q + div_q(m, t, cp);
+                r = r - q;
+            } else {
+                T tt = div_tau<WHICH>(0);
+                for (int m = 1; m < P.ncl; m++) tt = tt + div_tau<WHICH>(m);
+                r = r - tt;
+            }
+        }
+        return r;
+    }
+};
+
 template <typename T, int N, bool FAST, int WHICH, int TY, int KC>
 __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i, int j, int k0, int k1, T (*sy_buf)[TY][32]) {
     const GridD<T> &gg = P.g;
@@ -110,15 +228,11 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
         __syncthreads();
         if (do_out) {
             const T fy1 = sy_buf[buf][ty + 1][tx];
-            const T dzk = WHICH == 2 ? g.dzF(k) : g.dzC(k);
-            const T Vi = 1 / ((g.dx * g.dy) * dzk);
+            const T Vi = WHICH == 2 ? gg.rVf(k) : gg.rVc(k);
             const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower));
-            T r;
-            if constexpr (WHICH == 0) r = Gu_finish<T>(P, adv, i, j, k);
-            else if constexpr (WHICH == 1) r = Gv_finish<T>(P, adv, i, j, k);
-            else if constexpr (WHICH == 2) r = Gw_finish<T>(P, adv, i, j, k);
-            else r = Gc_finish<T>(P, adv, t, i, j, k);
-            G(i, j, k) = r;
+            const long eo = (long)i + (long)j * g.sy + (long)k * g.sz;
+            FastTerms<T> F{P, pu, pv, pw, eo, g.sy, g.sz, k};
+            G.p[G.off + eo] = F.template finish<WHICH>(adv, t, pq);
         }
         lower = upper;
         pq += g.sz; pu += g.sz; pv += g.sz; pw += g.sz;

@@ -54,8 +54,7 @@ __device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int 
         __syncthreads();
         if (do_out) {
             const T fy1 = sy[buf][ty + 1][tx];
-            const T dz = WHICH == 2 ? g.dzF(k) : g.dzC(k);
-            const T Vi = 1 / ((g.dx * g.dy) * dz);
+            const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
             const T ddx = g.topo[0] == FLAT ? T(0) : fx1 - fx;
             const T ddy = g.topo[1] == FLAT ? T(0) : fy1 - fy;
             const T ddz = g.topo[2] == FLAT ? T(0) : upper - lower;
@@ -72,7 +71,7 @@ __device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int 
 }
 
 template <typename T, class S, bool FAST, int TY, int KC>
-__global__ void __launch_bounds__(32 * TY, 2) tendency_march_kernel(const __grid_constant__ TendP<T> P) {
+__global__ void __launch_bounds__(32 * TY, 3) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc) {
     __shared__ T sy[2][TY][32];
     const int which = blockIdx.y;
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
@@ -80,7 +79,13 @@ __global__ void __launch_bounds__(32 * TY, 2) tendency_march_kernel(const __grid
     const int b = blockIdx.x;
     const int tile_x = b % ntx, tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
     const int i = 1 + tile_x * 31 + (int)threadIdx.x, j = 1 + tile_y * (TY - 1) + (int)threadIdx.y;
-    const int k0 = 1 + kc * KC, k1 = min(k0 + KC - 1, Nz);
+    // k-chunks: with a Bounded z and a WENO scheme of buffer nb the first and last chunk are the nb wall-adjacent
+    // levels (general path with the fallback chain); every other chunk is interior and takes the fast path
+    int k0, k1;
+    if (nb == 0) { k0 = 1 + kc * KC; k1 = min(k0 + KC - 1, Nz); }
+    else if (kc == 0) { k0 = 1; k1 = nb; }
+    else if (kc == nkc - 1) { k0 = Nz - nb + 1; k1 = Nz; }
+    else { k0 = nb + 1 + (kc - 1) * KC; k1 = min(k0 + KC - 1, Nz - nb); }
     if constexpr (S::kind == ADV_WENO) {
         if (fast_path_ok<T, S::n>(P, k0, k1)) {  // CTA-uniform
             if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC>(P, 0, i, j, k0, k1, sy);
@@ -104,11 +109,17 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     if (mode == 1) return cudaSuccess;
     constexpr int TY = 8, KC = 32;
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
-    const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1), nkc = (Nz + KC - 1) / KC;
+    int nb = 0;
+    long nkc = (Nz + KC - 1) / KC;
+    if (S::kind == ADV_WENO && P.g.topo[2] == BOUNDED && P.g.topo[0] == PERIODIC && P.g.topo[1] == PERIODIC && Nz > 2 * S::n) {
+        nb = S::n;
+        nkc = 2 + (Nz - 2 * nb + KC - 1) / KC;
+    }
+    const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
     if (ntx * nty * nkc > 2147483647L) return cudaSuccess;
     dim3 grid((unsigned)(ntx * nty * nkc), 3 + P.ntr), block(32, TY);
-    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC><<<grid, block, 0, st>>>(P);
-    else tendency_march_kernel<T, S, false, TY, KC><<<grid, block, 0, st>>>(P);
+    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC><<<grid, block, 0, st>>>(P, nb, (int)nkc);
+    else tendency_march_kernel<T, S, false, TY, KC><<<grid, block, 0, st>>>(P, nb, (int)nkc);
     *nlaunch += 1;
     done = true;
     return cudaGetLastError();
