@@ -204,24 +204,26 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
     const GridD<T> &gg = P.g;
     const int Nx = gg.N[0], Ny = gg.N[1];
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const bool do_x = (ty < TY - 1) && (j <= Ny) && (i <= Nx + 1);
-    const bool do_y = (tx < 31) && (i <= Nx) && (j <= Ny + 1);
     const bool do_out = (tx < 31) && (ty < TY - 1) && (i <= Nx) && (j <= Ny);
-    const bool in_range = (i <= Nx + 1) && (j <= Ny + 1);
+    const bool full_row = ty < TY - 1;  // warp-uniform: the overlap row only supplies its y-direction flux
     const Fld<T> &qf = WHICH == 0 ? P.u : WHICH == 1 ? P.v : WHICH == 2 ? P.w : P.c[t];
     const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[t];
     FastGeom<T> g;
     g.sy = P.u.sy; g.sz = P.u.sz; g.dx = gg.dx; g.dy = gg.dy; g.dz = gg.dz; g.dzc = gg.dzc; g.dzf = gg.dzf;
-    // clamp out-of-range threads onto a valid column so that their (unused) pointers stay inside the arrays
-    const int ii = in_range ? i : 1, jj = in_range ? j : 1;
+    // Lanes outside the flux region (i > Nx+1, j > Ny+1) are clamped onto its edge: they compute valid-but-unused
+    // fluxes, which keeps each level ONE branch-free block in which the three independent WENO chains interleave.
+    const int ii = min(i, Nx + 1), jj = min(j, Ny + 1);
     const long base = (long)ii + (long)jj * g.sy + (long)k0 * g.sz;  // every field has the same offsets on this path
     const T *pq = qf.p + qf.off + base;
     const T *pu = P.u.p + P.u.off + base, *pv = P.v.p + P.v.off + base, *pw = P.w.p + P.w.off + base;
-    T lower = do_out ? fast_flux<T, N, FAST, WHICH, 2>(pq, pw, g, k0) : T(0);
+    T lower = full_row ? fast_flux<T, N, FAST, WHICH, 2>(pq, pw, g, k0) : T(0);
     for (int k = k0; k <= k1; k++) {
-        const T fx = do_x ? fast_flux<T, N, FAST, WHICH, 0>(pq, pu, g, k) : T(0);
-        const T fy = do_y ? fast_flux<T, N, FAST, WHICH, 1>(pq, pv, g, k) : T(0);
-        const T upper = do_out ? fast_flux<T, N, FAST, WHICH, 2>(pq + g.sz, pw + g.sz, g, k + 1) : T(0);
+        T fx = T(0), upper = T(0);
+        const T fy = fast_flux<T, N, FAST, WHICH, 1>(pq, pv, g, k);
+        if (full_row) {
+            fx = fast_flux<T, N, FAST, WHICH, 0>(pq, pu, g, k);
+            upper = fast_flux<T, N, FAST, WHICH, 2>(pq + g.sz, pw + g.sz, g, k + 1);
+        }
         const T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
         const int buf = k & 1;
         sy_buf[buf][ty][tx] = fy;

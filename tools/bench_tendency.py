@@ -1,0 +1,33 @@
+"""Time the fused tendency kernel alone (CUDA events on the library stream): python tools/bench_tendency.py [N] [reps]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ocean_b200 as ob  # noqa: E402
+from ocean_b200 import _abi  # noqa: E402
+from bench import workload_config  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+arch = ob.B200(0)
+for ft in (np.float64, np.float32):
+    cfg = workload_config(n, ft=ft)
+    m = cfg.b200_model(arch)
+    ob.set(m, **cfg.initial_conditions(2))
+    for mode, name in ((2, "marching"), (1, "generic")):
+        m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, mode)
+        for _ in range(3):
+            m.compute_tendencies()
+        arch.synchronize()
+        _abi.call("ob_timer_start", arch.ctx)
+        for _ in range(reps):
+            m.compute_tendencies()
+        ms = C.c_double(0)
+        _abi.call("ob_timer_stop", arch.ctx, C.byref(ms))
+        t = ms.value / reps
+        print("%s %s %d^3: %.3f ms/launch, %.1f GB/s algorithmic (%d B/cell)" % (ft.__name__, name, n, t, 8 * np.dtype(ft).itemsize * n ** 3 / t / 1e6, 8 * np.dtype(ft).itemsize))
+    del m
