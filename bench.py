@@ -160,7 +160,7 @@ def main():
     ft = np.float32 if args.f32 else np.float64
     n = args.size
     cfg = workload_config(n, ft=ft, nx=n * world)
-    model = ob.distributed_model(cfg, arch) if world > 1 else cfg.b200_model(arch)
+    model = cfg.b200_model(arch)
     ic = cfg.initial_conditions(2)
     if world > 1:
         ic = {k: v[:, :, rank * n:(rank + 1) * n] for k, v in ic.items()}

@@ -19,3 +19,4 @@ from .models import (NonhydrostaticModel, Centered, WENO, ScalarDiffusivity, Sma
 from .simulations import (Simulation, run, Callback, IterationInterval, TimeInterval, TimeStepWizard,  # noqa: F401
                           conjure_time_step_wizard, NaNChecker)
 from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver, solve  # noqa: F401
+from .distributed import Distributed, partition_x, neighbors, gather_x, all_reduce_scalar  # noqa: F401

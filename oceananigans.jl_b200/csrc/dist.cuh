@@ -4,12 +4,6 @@
 #pragma once
 #include <nccl.h>
 
-#define NCCL_TRY(x)                                                                                       \
-    do {                                                                                                  \
-        ncclResult_t r_ = (x);                                                                            \
-        if (r_ != ncclSuccess) return fail(OB_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #x, ncclGetErrorString(r_)); \
-    } while (0)
-
 extern "C" int32_t ob_dist_unique_id(void *out128) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;

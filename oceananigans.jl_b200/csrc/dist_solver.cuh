@@ -1,0 +1,258 @@
+// dist_solver.cuh -- slab-x distributed pressure solvers (one process per GPU, NCCL over NVLink/NVSwitch).
+//
+// Reference: src/DistributedComputations/distributed_fft_based_poisson_solver.jl:141-183 (z-FFT, [z->y no-op for
+// slabs], y-FFT, y->x all-to-all, x-FFT, eigenvalue division, and back), distributed_fft_tridiagonal_solver.jl:292-316
+// (stretched z: the Thomas sweep runs in the x-local layout), transposable_field.jl:49-110 and
+// distributed_transpose.jl:39-109 (pack / unpack index maps), ext/OceananigansNCCLExt/nccl_transpose.jl:47-75 (grouped
+// ncclSend/ncclRecv all-to-all).  Included by ocean_b200.cu after SolverT.
+//
+// Layouts (x fastest everywhere): S  = y-local "slab" layout   (nx, Ny, Nz),  nx = Nx/R
+//                                 Tt = x-local transposed layout (Nx, ny, Nz), ny = Ny/R
+// Peer chunk r of a transpose buffer holds (nx, ny, Nz) elements: [xl + nx*(yl + ny*z)].
+#pragma once
+#include <nccl.h>
+
+#define NCCL_TRY(x)                                                                                       \
+    do {                                                                                                  \
+        ncclResult_t r_ = (x);                                                                            \
+        if (r_ != ncclSuccess) return fail(OB_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #x, ncclGetErrorString(r_)); \
+    } while (0)
+
+namespace ob {
+
+// slab -> per-peer chunks (integer index work: bit-exact)
+template <typename C>
+__global__ void __launch_bounds__(256) pack_y_to_x_kernel(const C *__restrict__ S, C *__restrict__ buf, int nx, int ny, int Ny, int Nz) {
+    const long n = (long)nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int xl = (int)(t % nx), y = (int)((t / nx) % Ny), z = (int)(t / ((long)nx * Ny));
+    const int r = y / ny, yl = y - r * ny;
+    buf[(long)r * nx * ny * Nz + xl + (long)nx * (yl + (long)ny * z)] = S[t];
+}
+// received chunks -> transposed layout
+template <typename C>
+__global__ void __launch_bounds__(256) unpack_y_to_x_kernel(const C *__restrict__ buf, C *__restrict__ Tt, int nx, int ny, int NxG, int Nz) {
+    const long n = (long)NxG * ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int x = (int)(t % NxG), yl = (int)((t / NxG) % ny), z = (int)(t / ((long)NxG * ny));
+    const int r = x / nx, xl = x - r * nx;
+    Tt[t] = buf[(long)r * nx * ny * Nz + xl + (long)nx * (yl + (long)ny * z)];
+}
+template <typename C>
+__global__ void __launch_bounds__(256) pack_x_to_y_kernel(const C *__restrict__ Tt, C *__restrict__ buf, int nx, int ny, int NxG, int Nz) {
+    const long n = (long)NxG * ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int x = (int)(t % NxG), yl = (int)((t / NxG) % ny), z = (int)(t / ((long)NxG * ny));
+    const int r = x / nx, xl = x - r * nx;
+    buf[(long)r * nx * ny * Nz + xl + (long)nx * (yl + (long)ny * z)] = Tt[t];
+}
+template <typename C>
+__global__ void __launch_bounds__(256) unpack_x_to_y_kernel(const C *__restrict__ buf, C *__restrict__ S, int nx, int ny, int Ny, int Nz) {
+    const long n = (long)nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int xl = (int)(t % nx), y = (int)((t / nx) % Ny), z = (int)(t / ((long)nx * Ny));
+    const int r = y / ny, yl = y - r * ny;
+    S[t] = buf[(long)r * nx * ny * Nz + xl + (long)nx * (yl + (long)ny * z)];
+}
+// ϕ̂ = -b̂ / (λx + λy + λz) in the transposed layout; global mode (0,0,0) lives on rank 0
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) eigen_divide_dist_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
+                                                                const T *__restrict__ lz, int NxG, int ny, int Nz, int y0, int zero_mode) {
+    const long n = (long)NxG * ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = (int)(t % NxG), j = (int)((t / NxG) % ny), k = (int)(t / ((long)NxG * ny));
+    C v = A[t];
+    const T lam = lx[i] + ly[y0 + j] + lz[k];
+    C o;
+    if (t == 0 && zero_mode) { o.x = 0; o.y = 0; }
+    else { o.x = -v.x / lam; o.y = -v.y / lam; }
+    A[t] = o;
+}
+
+}  // namespace ob
+
+template <typename T>
+struct DistSolverT : ob_solver {
+    using C = typename Cx<T>::type;
+    int R = 1, rank = 0, nx = 0, ny = 0, NxG = 0;
+    C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
+    T *lam[3] = {nullptr, nullptr, nullptr};
+    C *tw_f = nullptr, *tw_b = nullptr;          // z DCT twiddles (Bounded regular z)
+    T *diag = nullptr, *lower = nullptr, *tscr = nullptr;
+    cufftHandle plan_yz = 0, plan_y = 0, plan_z = 0, plan_x = 0;
+    bool has_yz = false, has_y = false, has_z = false, has_x = false;
+    double scale_ = 1.0;
+    static constexpr cufftType CT = std::is_same<T, double>::value ? CUFFT_Z2Z : CUFFT_C2C;
+
+    int32_t exec(cufftHandle p, C *data, int dir) {
+        launches++;
+        if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2Z(p, data, data, dir));
+        else CUFFT_TRY(cufftExecC2C(p, data, data, dir));
+        return OB_OK;
+    }
+    int32_t init(ob_ctx *c, const ob_grid_desc *g) {
+        ctx = c;
+        ft = g->float_type;
+        R = c->world; rank = c->rank;
+        for (int d = 0; d < 3; d++) { N[d] = g->N[d]; topo[d] = g->topology[d]; L[d] = g->L[d]; }
+        nx = N[0]; NxG = nx * R;
+        if (topo[0] != OB_PERIODIC || topo[1] != OB_PERIODIC) return fail(OB_ERR_UNSUPPORTED, "distributed solver: x and y must be Periodic");
+        if (N[1] % R) return fail(OB_ERR_INVALID, "distributed solver: Ny = %d must be divisible by the number of ranks %d", N[1], R);
+        if (topo[2] == OB_FLAT) return fail(OB_ERR_UNSUPPORTED, "distributed solver: Flat z");
+        ny = N[1] / R;
+        tridiag = g->dzf_host != nullptr;
+        const long n = (long)nx * N[1] * N[2];
+        for (C **p : {&S, &Tt, &buf_a, &buf_b}) { CUDA_TRY(cudaMalloc(p, sizeof(C) * n)); CUDA_TRY(cudaMemsetAsync(*p, 0, sizeof(C) * n, ctx->stream)); }
+        // eigenvalues with the GLOBAL x extent (poisson_eigenvalues.jl:8-32)
+        const int Ng[3] = {NxG, N[1], N[2]};
+        const double Lg[3] = {L[0] * R, L[1], L[2]};
+        for (int d = 0; d < 3; d++) {
+            std::vector<T> h(Ng[d]);
+            for (int i = 0; i < Ng[d]; i++) {
+                double v = 0;
+                if (topo[d] == OB_PERIODIC) { double s = 2 * sin(i * M_PI / Ng[d]) / (Lg[d] / Ng[d]); v = s * s; }
+                else if (topo[d] == OB_BOUNDED) { double s = 2 * sin(i * M_PI / (2.0 * Ng[d])) / (Lg[d] / Ng[d]); v = s * s; }
+                h[i] = (T)v;
+            }
+            CUDA_TRY(cudaMalloc(&lam[d], sizeof(T) * Ng[d]));
+            CUDA_TRY(cudaMemcpy(lam[d], h.data(), sizeof(T) * Ng[d], cudaMemcpyHostToDevice));
+        }
+        scale_ = 1.0 / ((double)NxG * N[1]);
+        const bool z_fft = !tridiag;
+        if (z_fft) scale_ /= N[2];
+        if (z_fft && topo[2] == OB_PERIODIC) {   // one strided rank-2 (z, y) transform per x column
+            int nn[2] = {N[2], N[1]};
+            CUFFT_TRY(cufftPlanMany(&plan_yz, 2, nn, nn, nx, 1, nn, nx, 1, CT, nx));
+            CUFFT_TRY(cufftSetStream(plan_yz, ctx->stream));
+            has_yz = true;
+        } else {
+            int nn[1] = {N[1]};  // y: one z-plane per call (stride nx, batch nx)
+            CUFFT_TRY(cufftPlanMany(&plan_y, 1, nn, nn, nx, 1, nn, nx, 1, CT, nx));
+            CUFFT_TRY(cufftSetStream(plan_y, ctx->stream));
+            has_y = true;
+            if (z_fft) {  // Bounded regular z: Makhoul DCT through a z-FFT
+                int nz[1] = {N[2]};
+                CUFFT_TRY(cufftPlanMany(&plan_z, 1, nz, nz, nx * N[1], 1, nz, nx * N[1], 1, CT, nx * N[1]));
+                CUFFT_TRY(cufftSetStream(plan_z, ctx->stream));
+                has_z = true;
+                std::vector<C> f(N[2]), b(N[2]);
+                for (int k = 0; k < N[2]; k++) {
+                    double a = -2 * M_PI * k / (4.0 * N[2]);
+                    f[k].x = (T)cos(a); f[k].y = (T)sin(a); b[k].x = (T)cos(-a); b[k].y = (T)sin(-a);
+                }
+                b[0].x *= (T)0.5; b[0].y *= (T)0.5;
+                CUDA_TRY(cudaMalloc(&tw_f, sizeof(C) * N[2])); CUDA_TRY(cudaMalloc(&tw_b, sizeof(C) * N[2]));
+                CUDA_TRY(cudaMemcpy(tw_f, f.data(), sizeof(C) * N[2], cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(tw_b, b.data(), sizeof(C) * N[2], cudaMemcpyHostToDevice));
+            }
+        }
+        {
+            int nn[1] = {NxG};
+            CUFFT_TRY(cufftPlanMany(&plan_x, 1, nn, nn, 1, NxG, nn, 1, NxG, CT, ny * N[2]));
+            CUFFT_TRY(cufftSetStream(plan_x, ctx->stream));
+            has_x = true;
+        }
+        if (tridiag) {  // diagonal in the transposed layout (fourier_tridiagonal_poisson_solver.jl:199-229)
+            const int Nz = N[2], Hz = g->H[2];
+            const T *dzf = (const T *)g->dzf_host, *dzc = (const T *)g->dzc_host;
+            auto DZF = [&](int k) { return dzf[k + Hz]; };
+            auto DZC = [&](int k) { return dzc[k + Hz - 1]; };
+            std::vector<T> lx(NxG), ly(N[1]);
+            CUDA_TRY(cudaMemcpy(lx.data(), lam[0], sizeof(T) * NxG, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(ly.data(), lam[1], sizeof(T) * N[1], cudaMemcpyDeviceToHost));
+            std::vector<T> D((size_t)n), low(std::max(1, Nz - 1));
+            for (int k = 1; k <= Nz; k++)
+                for (int j = 0; j < ny; j++)
+                    for (int i = 0; i < NxG; i++) {
+                        T l = lx[i] + ly[rank * ny + j];
+                        T v;
+                        if (k == 1) v = (T)-1 / DZF(2) - DZC(1) * l;
+                        else if (k == Nz) v = (T)-1 / DZF(Nz) - DZC(Nz) * l;
+                        else v = -((T)1 / DZF(k + 1) + (T)1 / DZF(k)) - DZC(k) * l;
+                        D[i + (size_t)NxG * (j + (size_t)ny * (k - 1))] = v;
+                    }
+            for (int q = 1; q <= Nz - 1; q++) low[q - 1] = (T)1 / DZF(q + 1);
+            CUDA_TRY(cudaMalloc(&diag, sizeof(T) * n)); CUDA_TRY(cudaMalloc(&tscr, sizeof(T) * n));
+            CUDA_TRY(cudaMalloc(&lower, sizeof(T) * low.size()));
+            CUDA_TRY(cudaMemcpy(diag, D.data(), sizeof(T) * n, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(lower, low.data(), sizeof(T) * low.size(), cudaMemcpyHostToDevice));
+        }
+        return OB_OK;
+    }
+    ~DistSolverT() override {
+        cudaFree(S); cudaFree(Tt); cudaFree(buf_a); cudaFree(buf_b);
+        for (int d = 0; d < 3; d++) cudaFree(lam[d]);
+        cudaFree(tw_f); cudaFree(tw_b); cudaFree(diag); cudaFree(lower); cudaFree(tscr);
+        if (has_yz) cufftDestroy(plan_yz);
+        if (has_y) cufftDestroy(plan_y);
+        if (has_z) cufftDestroy(plan_z);
+        if (has_x) cufftDestroy(plan_x);
+    }
+    void *storage() override { return S; }
+    double scale() override { return scale_; }
+
+    // all-to-all of per-peer chunks (nccl_transpose.jl:47-75: grouped Send/Recv, complex as 2 x real)
+    int32_t alltoall(const C *send, C *recv) {
+        const size_t chunk = (size_t)nx * ny * N[2];
+        ncclComm_t comm = (ncclComm_t)ctx->comm;
+        const ncclDataType_t dt = std::is_same<T, double>::value ? ncclDouble : ncclFloat;
+        NCCL_TRY(ncclGroupStart());
+        for (int r = 0; r < R; r++) {
+            NCCL_TRY(ncclSend(send + r * chunk, 2 * chunk, dt, r, comm, ctx->stream));
+            NCCL_TRY(ncclRecv(recv + r * chunk, 2 * chunk, dt, r, comm, ctx->stream));
+        }
+        NCCL_TRY(ncclGroupEnd());
+        launches++;
+        return OB_OK;
+    }
+    int32_t y_fft(int dir) {
+        for (int k = 0; k < N[2]; k++) OB_TRY(exec(plan_y, S + (long)k * nx * N[1], dir));
+        return OB_OK;
+    }
+    int32_t solve_in_storage() override {
+        const long n = (long)nx * N[1] * N[2];
+        const unsigned nb = nblk(n, 256);
+        cudaStream_t st = ctx->stream;
+        const bool z_dct = !tridiag && topo[2] == OB_BOUNDED;
+        // forward: z (Bounded first), y in the slab layout
+        if (z_dct) {
+            permute_kernel<C><<<nb, 256, 0, st>>>(S, buf_a, nx, N[1], N[2], 2);
+            OB_TRY(exec(plan_z, buf_a, CUFFT_FORWARD));
+            twiddle_fwd_kernel<T, C><<<nb, 256, 0, st>>>(buf_a, S, tw_f, nx, N[1], N[2], 2);
+            launches += 2;
+        }
+        if (has_yz) OB_TRY(exec(plan_yz, S, CUFFT_FORWARD));
+        else OB_TRY(y_fft(CUFFT_FORWARD));
+        // y -> x transpose, x transform
+        pack_y_to_x_kernel<C><<<nb, 256, 0, st>>>(S, buf_a, nx, ny, N[1], N[2]);
+        OB_TRY(alltoall(buf_a, buf_b));
+        unpack_y_to_x_kernel<C><<<nb, 256, 0, st>>>(buf_b, Tt, nx, ny, NxG, N[2]);
+        OB_TRY(exec(plan_x, Tt, CUFFT_FORWARD));
+        if (tridiag) {
+            dim3 grid(nblk(NxG, 128), ny);
+            thomas_kernel<T, C><<<grid, 128, 0, st>>>(Tt, lower, lower, diag, tscr, NxG, ny, N[2], (T)(10 * std::numeric_limits<T>::epsilon()), rank == 0 ? 1 : 0);
+        } else {
+            eigen_divide_dist_kernel<T, C><<<nb, 256, 0, st>>>(Tt, lam[0], lam[1], lam[2], NxG, ny, N[2], rank * ny, rank == 0 ? 1 : 0);
+        }
+        OB_TRY(exec(plan_x, Tt, CUFFT_INVERSE));
+        pack_x_to_y_kernel<C><<<nb, 256, 0, st>>>(Tt, buf_a, nx, ny, NxG, N[2]);
+        OB_TRY(alltoall(buf_a, buf_b));
+        unpack_x_to_y_kernel<C><<<nb, 256, 0, st>>>(buf_b, S, nx, ny, N[1], N[2]);
+        launches += 5;
+        if (has_yz) OB_TRY(exec(plan_yz, S, CUFFT_INVERSE));
+        else OB_TRY(y_fft(CUFFT_INVERSE));
+        if (z_dct) {
+            twiddle_bwd_kernel<T, C><<<nb, 256, 0, st>>>(S, buf_a, tw_b, nx, N[1], N[2], 2);
+            OB_TRY(exec(plan_z, buf_a, CUFFT_INVERSE));
+            unpermute_kernel<C><<<nb, 256, 0, st>>>(buf_a, S, nx, N[1], N[2], 2);
+            launches += 2;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+};

@@ -75,6 +75,43 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloB
 #undef AT
 }
 
+// Distributed west/east halo slabs: pack the H interior columns next to each x boundary of every field of the batch
+// into contiguous buffers, and unpack the neighbours' slabs into the halos.  Integer index work: bit-exact.
+template <typename T>
+struct XHaloTask {
+    T *p;
+    int Px;       // parent x size
+    long rows;    // Py * Pz
+    long offset;  // element offset of this field inside the slab buffers
+};
+template <typename T>
+struct XHaloBatch {
+    XHaloTask<T> t[OB_MAX_HALO_TASKS];
+    int count, H, N;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) xhalo_pack_kernel(const __grid_constant__ XHaloBatch<T> B, T *__restrict__ send_w, T *__restrict__ send_e) {
+    const XHaloTask<T> &t = B.t[blockIdx.y];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= t.rows * B.H) return;
+    const int h = (int)(tid % B.H);
+    const long row = tid / B.H;
+    const T *q = t.p + row * t.Px;
+    send_w[t.offset + tid] = q[B.H + h];   // logical i = 1 .. H
+    send_e[t.offset + tid] = q[B.N + h];   // logical i = N-H+1 .. N
+}
+template <typename T>
+__global__ void __launch_bounds__(256) xhalo_unpack_kernel(const __grid_constant__ XHaloBatch<T> B, const T *__restrict__ recv_w, const T *__restrict__ recv_e) {
+    const XHaloTask<T> &t = B.t[blockIdx.y];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= t.rows * B.H) return;
+    const int h = (int)(tid % B.H);
+    const long row = tid / B.H;
+    T *q = t.p + row * t.Px;
+    q[h] = recv_w[t.offset + tid];               // west halo <- west neighbour's east interior slab
+    q[B.N + B.H + h] = recv_e[t.offset + tid];   // east halo <- east neighbour's west interior slab
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K7: constant-flux boundary contributions (compute_flux_bcs.jl:113-162): Gc[1] += flux*A/V ; Gc[N] -= flux*A/V
 // ------------------------------------------------------------------------------------------------------------

@@ -380,13 +380,26 @@ struct SolverT : ob_solver {
     }
 };
 
+#include "dist_solver.cuh"
+
+template <typename T>
+static int32_t make_solver(ob_ctx *ctx, const ob_grid_desc *grid, ob_solver **out) {
+    int32_t st;
+    ob_solver *s;
+    if (ctx->world > 1) { auto *p = new DistSolverT<T>(); st = p->init(ctx, grid); s = p; }
+    else { auto *p = new SolverT<T>(); st = p->init(ctx, grid); s = p; }
+    if (st != OB_OK) { delete s; return st; }
+    *out = s;
+    return OB_OK;
+}
+
 extern "C" int32_t ob_solver_create(ob_ctx *ctx, const ob_grid_desc *grid, ob_solver **out) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     ob_solver *s = nullptr;
     int32_t st;
-    if (grid->float_type == OB_F64) { auto *p = new SolverT<double>(); st = p->init(ctx, grid); s = p; }
-    else { auto *p = new SolverT<float>(); st = p->init(ctx, grid); s = p; }
-    if (st != OB_OK) { delete s; return st; }
+    if (grid->float_type == OB_F64) st = make_solver<double>(ctx, grid, &s);
+    else st = make_solver<float>(ctx, grid, &s);
+    if (st != OB_OK) return st;
     *out = s;
     return OB_OK;
 }
@@ -512,13 +525,16 @@ struct ModelT : ob_model {
     std::vector<T> h_dzf, h_dzc;
     int Hz_ = 0;
     FieldInfo F[128];
-    SolverT<T> *solver = nullptr;
+    ob_solver *solver = nullptr;
     int ntr = 0, ncl = 0;
     double *d_partial = nullptr;
+    bool dist = false;
+    T *d_halo_buf = nullptr;
+    size_t halo_buf_elems = 0;
 
     ~ModelT() override {
         cudaFree(d_dzf); cudaFree(d_dzc); cudaFree(d_partial);
-        cudaFree(d_rdzf); cudaFree(d_rdzc); cudaFree(d_rvf); cudaFree(d_rvc);
+        cudaFree(d_rdzf); cudaFree(d_rdzc); cudaFree(d_rvf); cudaFree(d_rvc); cudaFree(d_halo_buf);
         delete solver;
         for (auto e : pool) cudaEventDestroy(e);
     }
@@ -620,8 +636,9 @@ struct ModelT : ob_model {
             if (d->closures[m].kind == OB_CLOSURE_AMD)
                 for (int t = 0; t < ntr; t++) setup_field(OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t, 0, 0, 0, d->bcs_kappae[m][t]);
         }
-        solver = new SolverT<T>();
-        OB_TRY(solver->init(ctx, &d->grid));
+        OB_TRY(make_solver<T>(ctx, &d->grid, &solver));
+        dist = ctx->world > 1;
+        if (dist && g.topo[0] != PERIODIC) return fail(OB_ERR_UNSUPPORTED, "slab-x distributed models need a Periodic x");
         return OB_OK;
     }
 
@@ -650,6 +667,7 @@ struct ModelT : ob_model {
                 if (g.topo[d] == FLAT) continue;
                 const bool per = g.topo[d] == PERIODIC;
                 if ((pass == 0) == per) continue;
+                if (dist && d == 0) { OB_TRY(exchange_x_halos(ids)); continue; }
                 size_t pos = 0;
                 while (pos < ids.size()) {
                     HaloBatch<T> B;
@@ -687,6 +705,48 @@ struct ModelT : ob_model {
                     launches++;
                 }
             }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    // Distributed west/east halos (halo_communication.jl:96-203; nccl_distributed.jl:209-246): ONE pack launch, one
+    // grouped Send/Recv pair per side carrying every field of the batch, ONE unpack launch.  Slabs span the full
+    // parent extent in y and z (OneDBuffer, communication_buffers.jl:96-114), so corners stay consistent exactly as
+    // with the local periodic copy.
+    int32_t exchange_x_halos(const std::vector<int> &ids) {
+        XHaloBatch<T> B;
+        B.count = 0; B.H = g.H[0]; B.N = g.N[0];
+        size_t total = 0;
+        for (int id : ids) {
+            const FieldInfo &f = F[id];
+            OB_TRY(need(id));
+            if (f.bc.kind[0] == OB_BC_NONE && f.bc.kind[1] == OB_BC_NONE) continue;
+            if (B.count >= OB_MAX_HALO_TASKS) return fail(OB_ERR_INVALID, "too many fields in one halo exchange");
+            XHaloTask<T> &t = B.t[B.count++];
+            t.p = (T *)f.ptr; t.Px = f.P[0]; t.rows = (long)f.P[1] * f.P[2]; t.offset = (long)total;
+            total += (size_t)g.H[0] * t.rows;
+        }
+        if (B.count == 0) return OB_OK;
+        if (4 * total > halo_buf_elems) {
+            cudaFree(d_halo_buf);
+            CUDA_TRY(cudaMalloc(&d_halo_buf, sizeof(T) * 4 * total));
+            halo_buf_elems = 4 * total;
+        }
+        T *send_w = d_halo_buf, *send_e = d_halo_buf + total, *recv_w = d_halo_buf + 2 * total, *recv_e = d_halo_buf + 3 * total;
+        long maxrows = 0;
+        for (int q = 0; q < B.count; q++) maxrows = std::max(maxrows, B.t[q].rows);
+        dim3 grid(nblk(maxrows * g.H[0], 256), B.count);
+        xhalo_pack_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, send_w, send_e);
+        ncclComm_t comm = (ncclComm_t)ctx->comm;
+        const int R = ctx->world, west = (ctx->rank + R - 1) % R, east = (ctx->rank + 1) % R;
+        const size_t bytes = sizeof(T) * total;
+        NCCL_TRY(ncclGroupStart());
+        NCCL_TRY(ncclSend(send_w, bytes, ncclChar, west, comm, ctx->stream));   // my west interior slab -> west neighbour's east halo
+        NCCL_TRY(ncclSend(send_e, bytes, ncclChar, east, comm, ctx->stream));
+        NCCL_TRY(ncclRecv(recv_e, bytes, ncclChar, east, comm, ctx->stream));   // east first: matches the send order when R == 2
+        NCCL_TRY(ncclRecv(recv_w, bytes, ncclChar, west, comm, ctx->stream));
+        NCCL_TRY(ncclGroupEnd());
+        xhalo_unpack_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, recv_w, recv_e);
+        launches += 3;
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }

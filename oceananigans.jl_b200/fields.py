@@ -170,7 +170,8 @@ class Field:
         flag = C.c_int32(0)
         ft = _abi.OB_F64 if self.grid.FT == np.float64 else _abi.OB_F32
         _abi.call("ob_any_nan", self.arch.ctx, self.data, self.count, ft, C.byref(flag))
-        return bool(flag.value)
+        from .distributed import all_reduce_scalar
+        return bool(all_reduce_scalar(self.arch, flag.value, "max"))  # all-reduced across ranks (run.jl:191-197)
 
     def __repr__(self):
         return "%dx%dx%d Field{%s} %s" % (*self.n, self.loc, self.name)

@@ -86,6 +86,17 @@ class RectilinearGrid:
         self.topology = tuple(topology)
         topo = self.topo = tuple(_TOPO[t] for t in topology)
         self.N = tuple(int(n) for n in _inflate(size, topo, 1))
+        # Distributed(B200()): `size` and the x interval are GLOBAL; this rank owns an equal slab in x
+        # (DistributedComputations/distributed_grids.jl: local size = global size / partition)
+        self.world, self.rank = getattr(architecture, "world", 1), getattr(architecture, "rank", 0)
+        self.N_global = self.N
+        self._x0 = 0
+        if self.world > 1:
+            from .distributed import partition_x
+            if topo[0] != _abi.OB_PERIODIC:
+                raise _abi.OceanB200Error(-3, "slab-x distributed grids need a Periodic x")
+            nx, self._x0 = partition_x(self.N[0], self.world, self.rank)
+            self.N = (nx,) + self.N[1:]
         if halo is None:
             halo = tuple(min(3, n) for n in self.N)  # validate_halo(::Nothing)
             halo = tuple(h for h, t in zip(halo, topo) if t != _abi.OB_FLAT)
@@ -117,6 +128,9 @@ class RectilinearGrid:
     # grid_generation.jl:34-156 ------------------------------------------------------------------------------
     def _generate(self, d, c):
         ft, N, H, topo = self.FT, self.N[d], self.H[d], self.topo[d]
+        split = d == 0 and self.world > 1
+        if split:
+            N = self.N_global[0]   # generate the global coordinate, then keep this rank's window (same Δx on every rank)
         if topo == _abi.OB_FLAT:
             self.L.append(ft(1)); self.faces.append(np.zeros(1, ft)); self.centers.append(np.zeros(1, ft))
             self.dF.append(ft(1)); self.dC.append(ft(1)); self.regular.append(True)
@@ -139,10 +153,15 @@ class RectilinearGrid:
             Cm = Fm + D / 2
             Cp = Cm + L + D * (2 * H - 1)
             rnd = (lambda q: ft(float(q))) if ft == np.float64 else (lambda q: np.float32(float(q)))
-            self.faces.append(np.linspace(rnd(Fm), rnd(Fp), TF).astype(ft))
-            self.centers.append(np.linspace(rnd(Cm), rnd(Cp), TC).astype(ft))
+            F, Cc = np.linspace(rnd(Fm), rnd(Fp), TF).astype(ft), np.linspace(rnd(Cm), rnd(Cp), TC).astype(ft)
+            if split:
+                n = self.N[0]
+                F, Cc, L = F[self._x0:self._x0 + n + 2 * H], Cc[self._x0:self._x0 + n + 2 * H], L / self.world
+            self.faces.append(F); self.centers.append(Cc)
             self.L.append(rnd(L)); self.dF.append(rnd(D)); self.dC.append(rnd(D)); self.regular.append(True)
             return
+        if split:
+            raise _abi.OceanB200Error(-3, "a partitioned x must be regularly spaced")
         # variably spaced: explicit interior faces
         Fi = np.asarray(c, dtype=ft)
         if Fi.shape != (N + 1,):
@@ -171,7 +190,7 @@ class RectilinearGrid:
     # ---------------------------------------------------------------------------------------------------------
     def with_halo(self, halo):
         """with_halo(new_halo, grid) (rectilinear_grid.jl:440-455)"""
-        kw = dict(size=tuple(n for n, t in zip(self.N, self.topo) if t != _abi.OB_FLAT),
+        kw = dict(size=tuple(n for n, t in zip(self.N_global, self.topo) if t != _abi.OB_FLAT),
                   halo=tuple(h for h, t in zip(halo, self.topo) if t != _abi.OB_FLAT), topology=self.topology)
         xyz = {}
         for d, name in enumerate("xyz"):

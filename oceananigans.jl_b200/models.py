@@ -316,7 +316,8 @@ class NonhydrostaticModel:
     def cell_advection_timescale(self):
         tau = C.c_double(0)
         _abi.call("ob_cell_advection_timescale", self.handle, C.byref(tau))
-        return tau.value
+        from .distributed import all_reduce_scalar
+        return all_reduce_scalar(self.architecture, tau.value, "min")
 
     def launch_count(self):
         n = C.c_int64(0)
