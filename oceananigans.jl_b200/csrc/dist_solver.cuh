@@ -58,6 +58,43 @@ __global__ void __launch_bounds__(256) unpack_x_to_y_kernel(const C *__restrict_
     const int r = y / ny, yl = y - r * ny;
     S[t] = buf[(long)r * nx * ny * Nz + xl + (long)nx * (yl + (long)ny * z)];
 }
+// x <-> z transposition (used when Nz % R == 0 and the solver is FFT-based): the slab layout (nx, Ny, Nz) is z-slowest,
+// so the chunk for peer r -- levels r*nz .. (r+1)*nz-1 -- is CONTIGUOUS and is sent straight from S without packing;
+// the receiver scatters rows of nx into the z-local layout Tz = (Nx, Ny, nz), where the (x, y) transform is one
+// contiguous batched 2-D cuFFT exactly as on a single GPU.
+template <typename C>
+__global__ void __launch_bounds__(256) unpack_z_to_x_kernel(const C *__restrict__ buf, C *__restrict__ Tz, int nx, int NxG, int Ny, int nz) {
+    const long n = (long)NxG * Ny * nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int x = (int)(t % NxG), y = (int)((t / NxG) % Ny), zl = (int)(t / ((long)NxG * Ny));
+    const int r = x / nx, xl = x - r * nx;
+    Tz[t] = buf[(long)r * nx * Ny * nz + xl + (long)nx * (y + (long)Ny * zl)];
+}
+template <typename C>
+__global__ void __launch_bounds__(256) pack_x_to_z_kernel(const C *__restrict__ Tz, C *__restrict__ buf, int nx, int NxG, int Ny, int nz) {
+    const long n = (long)NxG * Ny * nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int x = (int)(t % NxG), y = (int)((t / NxG) % Ny), zl = (int)(t / ((long)NxG * Ny));
+    const int r = x / nx, xl = x - r * nx;
+    buf[(long)r * nx * Ny * nz + xl + (long)nx * (y + (long)Ny * zl)] = Tz[t];
+}
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) eigen_divide_zslab_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
+                                                                 const T *__restrict__ lz, int NxG, int Ny, int nz, int z0, int zero_mode) {
+    const long n = (long)NxG * Ny * nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = (int)(t % NxG), j = (int)((t / NxG) % Ny), k = (int)(t / ((long)NxG * Ny));
+    C v = A[t];
+    const T lam = lx[i] + ly[j] + lz[z0 + k];
+    C o;
+    if (t == 0 && zero_mode) { o.x = 0; o.y = 0; }
+    else { o.x = -v.x / lam; o.y = -v.y / lam; }
+    A[t] = o;
+}
+
 // ϕ̂ = -b̂ / (λx + λy + λz) in the transposed layout; global mode (0,0,0) lives on rank 0
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) eigen_divide_dist_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
@@ -79,7 +116,10 @@ __global__ void __launch_bounds__(256) eigen_divide_dist_kernel(C *__restrict__ 
 template <typename T>
 struct DistSolverT : ob_solver {
     using C = typename Cx<T>::type;
-    int R = 1, rank = 0, nx = 0, ny = 0, NxG = 0;
+    int R = 1, rank = 0, nx = 0, ny = 0, nz = 0, NxG = 0;
+    bool zx = false;   // x<->z transposition (FFT-based solvers with Nz % R == 0), else y<->x
+    cufftHandle plan_xy = 0;
+    bool has_xy = false;
     C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
     T *lam[3] = {nullptr, nullptr, nullptr};
     C *tw_f = nullptr, *tw_b = nullptr;          // z DCT twiddles (Bounded regular z)
@@ -102,10 +142,12 @@ struct DistSolverT : ob_solver {
         for (int d = 0; d < 3; d++) { N[d] = g->N[d]; topo[d] = g->topology[d]; L[d] = g->L[d]; }
         nx = N[0]; NxG = nx * R;
         if (topo[0] != OB_PERIODIC || topo[1] != OB_PERIODIC) return fail(OB_ERR_UNSUPPORTED, "distributed solver: x and y must be Periodic");
-        if (N[1] % R) return fail(OB_ERR_INVALID, "distributed solver: Ny = %d must be divisible by the number of ranks %d", N[1], R);
         if (topo[2] == OB_FLAT) return fail(OB_ERR_UNSUPPORTED, "distributed solver: Flat z");
-        ny = N[1] / R;
         tridiag = g->dzf_host != nullptr;
+        zx = !tridiag && (N[2] % R == 0) && !getenv("OB_DIST_FORCE_YX");
+        if (!zx && N[1] % R) return fail(OB_ERR_INVALID, "distributed solver: Ny = %d (or Nz = %d) must be divisible by the number of ranks %d", N[1], N[2], R);
+        ny = zx ? N[1] : N[1] / R;
+        nz = zx ? N[2] / R : N[2];
         const long n = (long)nx * N[1] * N[2];
         for (C **p : {&S, &Tt, &buf_a, &buf_b}) { CUDA_TRY(cudaMalloc(p, sizeof(C) * n)); CUDA_TRY(cudaMemsetAsync(*p, 0, sizeof(C) * n, ctx->stream)); }
         // eigenvalues with the GLOBAL x extent (poisson_eigenvalues.jl:8-32)
@@ -125,7 +167,27 @@ struct DistSolverT : ob_solver {
         scale_ = 1.0 / ((double)NxG * N[1]);
         const bool z_fft = !tridiag;
         if (z_fft) scale_ /= N[2];
-        if (z_fft && topo[2] == OB_PERIODIC) {   // one strided rank-2 (z, y) transform per x column
+        if (zx) {
+            int nzz[1] = {N[2]};   // z in the slab layout: stride nx*Ny, contiguous batch nx*Ny
+            CUFFT_TRY(cufftPlanMany(&plan_z, 1, nzz, nzz, nx * N[1], 1, nzz, nx * N[1], 1, CT, nx * N[1]));
+            CUFFT_TRY(cufftSetStream(plan_z, ctx->stream));
+            has_z = true;
+            int nn[2] = {N[1], NxG};   // (x, y) in the z-local layout: contiguous, batched over the local levels
+            CUFFT_TRY(cufftPlanMany(&plan_xy, 2, nn, nullptr, 1, NxG * N[1], nullptr, 1, NxG * N[1], CT, nz));
+            CUFFT_TRY(cufftSetStream(plan_xy, ctx->stream));
+            has_xy = true;
+            if (topo[2] == OB_BOUNDED) {
+                std::vector<C> f(N[2]), b(N[2]);
+                for (int k = 0; k < N[2]; k++) {
+                    double a = -2 * M_PI * k / (4.0 * N[2]);
+                    f[k].x = (T)cos(a); f[k].y = (T)sin(a); b[k].x = (T)cos(-a); b[k].y = (T)sin(-a);
+                }
+                b[0].x *= (T)0.5; b[0].y *= (T)0.5;
+                CUDA_TRY(cudaMalloc(&tw_f, sizeof(C) * N[2])); CUDA_TRY(cudaMalloc(&tw_b, sizeof(C) * N[2]));
+                CUDA_TRY(cudaMemcpy(tw_f, f.data(), sizeof(C) * N[2], cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(tw_b, b.data(), sizeof(C) * N[2], cudaMemcpyHostToDevice));
+            }
+        } else if (z_fft && topo[2] == OB_PERIODIC) {   // one strided rank-2 (z, y) transform per x column
             int nn[2] = {N[2], N[1]};
             CUFFT_TRY(cufftPlanMany(&plan_yz, 2, nn, nn, nx, 1, nn, nx, 1, CT, nx));
             CUFFT_TRY(cufftSetStream(plan_yz, ctx->stream));
@@ -151,7 +213,7 @@ struct DistSolverT : ob_solver {
                 CUDA_TRY(cudaMemcpy(tw_b, b.data(), sizeof(C) * N[2], cudaMemcpyHostToDevice));
             }
         }
-        {
+        if (!zx) {
             int nn[1] = {NxG};
             CUFFT_TRY(cufftPlanMany(&plan_x, 1, nn, nn, 1, NxG, nn, 1, NxG, CT, ny * N[2]));
             CUFFT_TRY(cufftSetStream(plan_x, ctx->stream));
@@ -192,17 +254,21 @@ struct DistSolverT : ob_solver {
         if (has_y) cufftDestroy(plan_y);
         if (has_z) cufftDestroy(plan_z);
         if (has_x) cufftDestroy(plan_x);
+        if (has_xy) cufftDestroy(plan_xy);
     }
     void *storage() override { return S; }
     double scale() override { return scale_; }
 
     // all-to-all of per-peer chunks (nccl_transpose.jl:47-75: grouped Send/Recv, complex as 2 x real)
     int32_t alltoall(const C *send, C *recv) {
-        const size_t chunk = (size_t)nx * ny * N[2];
+        const size_t chunk = (size_t)nx * ny * nz;
         ncclComm_t comm = (ncclComm_t)ctx->comm;
         const ncclDataType_t dt = std::is_same<T, double>::value ? ncclDouble : ncclFloat;
+        // the self chunk is a local copy (nccl_transpose.jl:47-75)
+        CUDA_TRY(cudaMemcpyAsync(recv + rank * chunk, send + rank * chunk, sizeof(C) * chunk, cudaMemcpyDeviceToDevice, ctx->stream));
         NCCL_TRY(ncclGroupStart());
         for (int r = 0; r < R; r++) {
+            if (r == rank) continue;
             NCCL_TRY(ncclSend(send + r * chunk, 2 * chunk, dt, r, comm, ctx->stream));
             NCCL_TRY(ncclRecv(recv + r * chunk, 2 * chunk, dt, r, comm, ctx->stream));
         }
@@ -219,6 +285,35 @@ struct DistSolverT : ob_solver {
         const unsigned nb = nblk(n, 256);
         cudaStream_t st = ctx->stream;
         const bool z_dct = !tridiag && topo[2] == OB_BOUNDED;
+        if (zx) {
+            // z transform in the slab layout (DCT through permute / FFT / twiddle when Bounded)
+            if (z_dct) {
+                permute_kernel<C><<<nb, 256, 0, st>>>(S, buf_a, nx, N[1], N[2], 2);
+                OB_TRY(exec(plan_z, buf_a, CUFFT_FORWARD));
+                twiddle_fwd_kernel<T, C><<<nb, 256, 0, st>>>(buf_a, S, tw_f, nx, N[1], N[2], 2);
+                launches += 2;
+            } else {
+                OB_TRY(exec(plan_z, S, CUFFT_FORWARD));
+            }
+            OB_TRY(alltoall(S, buf_b));   // chunks are contiguous in S: no pack
+            unpack_z_to_x_kernel<C><<<nb, 256, 0, st>>>(buf_b, Tt, nx, NxG, N[1], nz);
+            OB_TRY(exec(plan_xy, Tt, CUFFT_FORWARD));
+            eigen_divide_zslab_kernel<T, C><<<nb, 256, 0, st>>>(Tt, lam[0], lam[1], lam[2], NxG, N[1], nz, rank * nz, rank == 0 ? 1 : 0);
+            OB_TRY(exec(plan_xy, Tt, CUFFT_INVERSE));
+            pack_x_to_z_kernel<C><<<nb, 256, 0, st>>>(Tt, buf_a, nx, NxG, N[1], nz);
+            OB_TRY(alltoall(buf_a, S));   // received chunks land contiguously in S: no unpack
+            launches += 3;
+            if (z_dct) {
+                twiddle_bwd_kernel<T, C><<<nb, 256, 0, st>>>(S, buf_a, tw_b, nx, N[1], N[2], 2);
+                OB_TRY(exec(plan_z, buf_a, CUFFT_INVERSE));
+                unpermute_kernel<C><<<nb, 256, 0, st>>>(buf_a, S, nx, N[1], N[2], 2);
+                launches += 2;
+            } else {
+                OB_TRY(exec(plan_z, S, CUFFT_INVERSE));
+            }
+            CUDA_TRY(cudaGetLastError());
+            return OB_OK;
+        }
         // forward: z (Bounded first), y in the slab layout
         if (z_dct) {
             permute_kernel<C><<<nb, 256, 0, st>>>(S, buf_a, nx, N[1], N[2], 2);
