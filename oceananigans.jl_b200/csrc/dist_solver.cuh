@@ -80,6 +80,33 @@ __global__ void __launch_bounds__(256) pack_x_to_z_kernel(const C *__restrict__ 
     const int r = x / nx, xl = x - r * nx;
     buf[(long)r * nx * Ny * nz + xl + (long)nx * (y + (long)Ny * zl)] = Tz[t];
 }
+// Fused transposition over NVLink peer memory: every rank PULLS its part of the transposed array straight out of the
+// peers' storage (CUDA IPC mappings; rows of nx contiguous complex numbers), so the all-to-all and the unpack are ONE
+// kernel and no staging buffer is touched.  Ordering across GPUs is provided by a stream-ordered barrier before each pull.
+#define OB_MAX_PEERS 16
+template <typename C> struct PeerPtrs { const C *p[OB_MAX_PEERS]; };
+template <typename C>
+__global__ void __launch_bounds__(256) pull_z_to_x_kernel(const __grid_constant__ PeerPtrs<C> peers, C *__restrict__ Tz, int nx, int NxG, int Ny,
+                                                          int nz, int Nz, int rank) {
+    const long n = (long)NxG * Ny * nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int x = (int)(t % NxG), y = (int)((t / NxG) % Ny), zl = (int)(t / ((long)NxG * Ny));
+    const int r = x / nx, xl = x - r * nx;
+    (void)Nz;
+    Tz[t] = peers.p[r][xl + (long)nx * (y + (long)Ny * (rank * nz + zl))];   // peer r's slab layout (nx, Ny, Nz)
+}
+template <typename C>
+__global__ void __launch_bounds__(256) pull_x_to_z_kernel(const __grid_constant__ PeerPtrs<C> peers, C *__restrict__ S, int nx, int NxG, int Ny,
+                                                          int nz, int Nz, int rank) {
+    const long n = (long)nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int xl = (int)(t % nx), y = (int)((t / nx) % Ny), z = (int)(t / ((long)nx * Ny));
+    const int r = z / nz, zl = z - r * nz;
+    S[t] = peers.p[r][(rank * nx + xl) + (long)NxG * (y + (long)Ny * zl)];     // peer r's z-local layout (Nx, Ny, nz)
+}
+
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) eigen_divide_zslab_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
                                                                  const T *__restrict__ lz, int NxG, int Ny, int nz, int z0, int zero_mode) {
@@ -120,6 +147,9 @@ struct DistSolverT : ob_solver {
     bool zx = false;   // x<->z transposition (FFT-based solvers with Nz % R == 0), else y<->x
     cufftHandle plan_xy = 0;
     bool has_xy = false;
+    bool use_ipc = false;           // pull transposes through CUDA-IPC peer mappings instead of NCCL send/recv
+    ob::PeerPtrs<C> peerS, peerT;
+    int *d_bar = nullptr;
     C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
     T *lam[3] = {nullptr, nullptr, nullptr};
     C *tw_f = nullptr, *tw_b = nullptr;          // z DCT twiddles (Bounded regular z)
@@ -219,6 +249,7 @@ struct DistSolverT : ob_solver {
             CUFFT_TRY(cufftSetStream(plan_x, ctx->stream));
             has_x = true;
         }
+        if (zx && !getenv("OB_DIST_NO_IPC")) OB_TRY(setup_ipc());
         if (tridiag) {  // diagonal in the transposed layout (fourier_tridiagonal_poisson_solver.jl:199-229)
             const int Nz = N[2], Hz = g->H[2];
             const T *dzf = (const T *)g->dzf_host, *dzc = (const T *)g->dzc_host;
@@ -246,7 +277,49 @@ struct DistSolverT : ob_solver {
         }
         return OB_OK;
     }
+    // exchange cudaIpcMemHandle_t of S and Tt between the ranks (all-gather over NCCL) and map the peers' arrays
+    int32_t setup_ipc() {
+        if (R > OB_MAX_PEERS) return OB_OK;
+        struct Pair { cudaIpcMemHandle_t s, t; };
+        Pair mine;
+        if (cudaIpcGetMemHandle(&mine.s, S) != cudaSuccess || cudaIpcGetMemHandle(&mine.t, Tt) != cudaSuccess) { cudaGetLastError(); return OB_OK; }
+        Pair *d_all = nullptr;
+        CUDA_TRY(cudaMalloc(&d_all, sizeof(Pair) * R));
+        CUDA_TRY(cudaMemcpyAsync(d_all + rank, &mine, sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ncclAllGather(d_all + rank, d_all, sizeof(Pair), ncclChar, (ncclComm_t)ctx->comm, ctx->stream));
+        std::vector<Pair> all(R);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(Pair) * R, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_all);
+        int ok = 1;
+        for (int r = 0; r < R; r++) {
+            if (r == rank) { peerS.p[r] = S; peerT.p[r] = Tt; continue; }
+            void *ps = nullptr, *pt = nullptr;
+            if (cudaIpcOpenMemHandle(&ps, all[r].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&pt, all[r].t, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            peerS.p[r] = (const C *)ps; peerT.p[r] = (const C *)pt;
+        }
+        // every rank must take the same path: agree through an all-reduce (min)
+        CUDA_TRY(cudaMalloc(&d_bar, sizeof(int)));
+        CUDA_TRY(cudaMemcpyAsync(d_bar, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&ok, d_bar, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        use_ipc = ok != 0;
+        return OB_OK;
+    }
+    // stream-ordered barrier across the ranks
+    int32_t barrier() {
+        NCCL_TRY(ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+        launches++;
+        return OB_OK;
+    }
     ~DistSolverT() override {
+        if (use_ipc) {
+            cudaStreamSynchronize(ctx->stream);
+            for (int r = 0; r < R; r++) if (r != rank) { cudaIpcCloseMemHandle((void *)peerS.p[r]); cudaIpcCloseMemHandle((void *)peerT.p[r]); }
+        }
+        cudaFree(d_bar);
         cudaFree(S); cudaFree(Tt); cudaFree(buf_a); cudaFree(buf_b);
         for (int d = 0; d < 3; d++) cudaFree(lam[d]);
         cudaFree(tw_f); cudaFree(tw_b); cudaFree(diag); cudaFree(lower); cudaFree(tscr);
@@ -295,13 +368,23 @@ struct DistSolverT : ob_solver {
             } else {
                 OB_TRY(exec(plan_z, S, CUFFT_FORWARD));
             }
-            OB_TRY(alltoall(S, buf_b));   // chunks are contiguous in S: no pack
-            unpack_z_to_x_kernel<C><<<nb, 256, 0, st>>>(buf_b, Tt, nx, NxG, N[1], nz);
+            if (use_ipc) {
+                OB_TRY(barrier());        // every peer's z transform is complete
+                pull_z_to_x_kernel<C><<<nb, 256, 0, st>>>(peerS, Tt, nx, NxG, N[1], nz, N[2], rank);
+            } else {
+                OB_TRY(alltoall(S, buf_b));   // chunks are contiguous in S: no pack
+                unpack_z_to_x_kernel<C><<<nb, 256, 0, st>>>(buf_b, Tt, nx, NxG, N[1], nz);
+            }
             OB_TRY(exec(plan_xy, Tt, CUFFT_FORWARD));
             eigen_divide_zslab_kernel<T, C><<<nb, 256, 0, st>>>(Tt, lam[0], lam[1], lam[2], NxG, N[1], nz, rank * nz, rank == 0 ? 1 : 0);
             OB_TRY(exec(plan_xy, Tt, CUFFT_INVERSE));
-            pack_x_to_z_kernel<C><<<nb, 256, 0, st>>>(Tt, buf_a, nx, NxG, N[1], nz);
-            OB_TRY(alltoall(buf_a, S));   // received chunks land contiguously in S: no unpack
+            if (use_ipc) {
+                OB_TRY(barrier());        // every peer's inverse (x, y) transform is complete (and its forward pull long done)
+                pull_x_to_z_kernel<C><<<nb, 256, 0, st>>>(peerT, S, nx, NxG, N[1], nz, N[2], rank);
+            } else {
+                pack_x_to_z_kernel<C><<<nb, 256, 0, st>>>(Tt, buf_a, nx, NxG, N[1], nz);
+                OB_TRY(alltoall(buf_a, S));   // received chunks land contiguously in S: no unpack
+            }
             launches += 3;
             if (z_dct) {
                 twiddle_bwd_kernel<T, C><<<nb, 256, 0, st>>>(S, buf_a, tw_b, nx, N[1], N[2], 2);
