@@ -198,6 +198,8 @@ struct ob_solver {
     virtual int32_t solve_in_storage() = 0;
     virtual void *storage() = 0;
     virtual double scale() = 0;
+    // true: storage() holds REAL numbers (Nx,Ny,Nz) on input and output (real-to-complex transforms inside)
+    virtual bool real_storage() const { return false; }
 };
 
 template <typename T>
@@ -207,8 +209,11 @@ struct SolverT : ob_solver {
     T *lam[3] = {nullptr, nullptr, nullptr};
     C *tw_f[3] = {nullptr, nullptr, nullptr}, *tw_b[3] = {nullptr, nullptr, nullptr};
     T *diag = nullptr, *lower = nullptr, *tscr = nullptr;
-    cufftHandle plan_x = 0, plan_y = 0, plan_z = 0, plan_xy = 0;
+    cufftHandle plan_x = 0, plan_y = 0, plan_z = 0, plan_xy = 0, plan_r2c = 0, plan_c2r = 0;
     bool has_x = false, has_y = false, has_z = false, has_xy = false;
+    bool r2c = false;   // fully periodic: 3-D real-to-complex / complex-to-real transforms on the half spectrum
+    T *Rr = nullptr;
+    int Nxh = 0;
     double scale_ = 1.0;
 
     static constexpr cufftType CT = std::is_same<T, double>::value ? CUFFT_Z2Z : CUFFT_C2C;
@@ -227,6 +232,31 @@ struct SolverT : ob_solver {
         tridiag = g->dzf_host != nullptr;
         if (tridiag && topo[2] != OB_BOUNDED) return fail(OB_ERR_UNSUPPORTED, "FourierTridiagonalPoissonSolver needs a Bounded stretched direction");
         const long n = (long)N[0] * N[1] * N[2];
+        r2c = !tridiag && topo[0] == OB_PERIODIC && topo[1] == OB_PERIODIC && topo[2] == OB_PERIODIC && N[0] > 1 && N[1] > 1 && N[2] > 1 &&
+              !getenv("OB_SOLVER_NO_R2C");
+        if (r2c) {
+            // The rhs is real, so a real-to-complex 3-D transform carries half the bytes of the reference's complex
+            // in-place FFTs (fft_based_poisson_solver.jl:94-124); same eigenvalue division on the half spectrum i <= Nx/2.
+            Nxh = N[0] / 2 + 1;
+            const long nh = (long)Nxh * N[1] * N[2];
+            CUDA_TRY(cudaMalloc(&S, sizeof(C) * nh));
+            CUDA_TRY(cudaMalloc(&Rr, sizeof(T) * n));
+            CUDA_TRY(cudaMemsetAsync(Rr, 0, sizeof(T) * n, ctx->stream));
+            for (int d = 0; d < 3; d++) {
+                std::vector<T> h(N[d]);
+                for (int i = 0; i < N[d]; i++) { double sn = 2 * sin(i * M_PI / N[d]) / (L[d] / N[d]); h[i] = (T)(sn * sn); }
+                CUDA_TRY(cudaMalloc(&lam[d], sizeof(T) * N[d]));
+                CUDA_TRY(cudaMemcpy(lam[d], h.data(), sizeof(T) * N[d], cudaMemcpyHostToDevice));
+            }
+            constexpr cufftType FWD = std::is_same<T, double>::value ? CUFFT_D2Z : CUFFT_R2C;
+            constexpr cufftType BWD = std::is_same<T, double>::value ? CUFFT_Z2D : CUFFT_C2R;
+            CUFFT_TRY(cufftPlan3d(&plan_r2c, N[2], N[1], N[0], FWD));
+            CUFFT_TRY(cufftPlan3d(&plan_c2r, N[2], N[1], N[0], BWD));
+            CUFFT_TRY(cufftSetStream(plan_r2c, ctx->stream));
+            CUFFT_TRY(cufftSetStream(plan_c2r, ctx->stream));
+            scale_ = 1.0 / ((double)N[0] * N[1] * N[2]);
+            return OB_OK;
+        }
         CUDA_TRY(cudaMalloc(&S, sizeof(C) * n));
         CUDA_TRY(cudaMemsetAsync(S, 0, sizeof(C) * n, ctx->stream));
         bool any_bounded = false;
@@ -324,9 +354,11 @@ struct SolverT : ob_solver {
         if (has_y) cufftDestroy(plan_y);
         if (has_z) cufftDestroy(plan_z);
         if (has_xy) cufftDestroy(plan_xy);
+        if (r2c) { cufftDestroy(plan_r2c); cufftDestroy(plan_c2r); cudaFree(Rr); }
     }
-    void *storage() override { return S; }
+    void *storage() override { return r2c ? (void *)Rr : (void *)S; }
     double scale() override { return scale_; }
+    bool real_storage() const override { return r2c; }
 
     int32_t fft_dim(C *data, int d, int dir) {
         if (d == 0) return exec(plan_x, data, dir);
@@ -338,6 +370,17 @@ struct SolverT : ob_solver {
         const long n = (long)N[0] * N[1] * N[2];
         const unsigned nb = nblk(n, 256);
         cudaStream_t st = ctx->stream;
+        if (r2c) {
+            if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecD2Z(plan_r2c, Rr, S));
+            else CUFFT_TRY(cufftExecR2C(plan_r2c, Rr, S));
+            const long nh = (long)Nxh * N[1] * N[2];
+            eigen_divide_kernel<T, C><<<nblk(nh, 256), 256, 0, st>>>(S, lam[0], lam[1], lam[2], Nxh, N[1], N[2]);
+            if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2D(plan_c2r, S, Rr));
+            else CUFFT_TRY(cufftExecC2R(plan_c2r, S, Rr));
+            launches += 3;
+            CUDA_TRY(cudaGetLastError());
+            return OB_OK;
+        }
         const int ndim_t = tridiag ? 2 : 3;
         auto transformed = [&](int d) { return d < ndim_t && topo[d] != OB_FLAT && N[d] > 1; };
         // forward: Bounded dims first (plan_transforms.jl:160-199), then Periodic
@@ -415,10 +458,24 @@ __global__ void unpack_real_kernel(const C *S, T *r, long n, T scale) {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) r[t] = S[t].x * scale;
 }
+template <typename T>
+__global__ void scale_copy_kernel(const T *in, T *out, long n, T scale) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = in[t] * scale;
+}
 extern "C" int32_t ob_poisson_solve(ob_solver *s, const void *rhs, void *phi) {
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     const long n = (long)s->N[0] * s->N[1] * s->N[2];
     cudaStream_t st = s->ctx->stream;
+    if (s->real_storage()) {
+        const size_t w = s->ft == OB_F64 ? 8 : 4;
+        CUDA_TRY(cudaMemcpyAsync(s->storage(), rhs, w * n, cudaMemcpyDeviceToDevice, st));
+        OB_TRY(s->solve_in_storage());
+        if (s->ft == OB_F64) scale_copy_kernel<double><<<nblk(n, 256), 256, 0, st>>>((const double *)s->storage(), (double *)phi, n, s->scale());
+        else scale_copy_kernel<float><<<nblk(n, 256), 256, 0, st>>>((const float *)s->storage(), (float *)phi, n, (float)s->scale());
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
     if (s->ft == OB_F64) pack_real_kernel<double, double2><<<nblk(n, 256), 256, 0, st>>>((const double *)rhs, (double2 *)s->storage(), n);
     else pack_real_kernel<float, float2><<<nblk(n, 256), 256, 0, st>>>((const float *)rhs, (float2 *)s->storage(), n);
     OB_TRY(s->solve_in_storage());
@@ -945,7 +1002,7 @@ struct ModelT : ob_model {
             P.out = (T *)solver->storage();
             P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
             P.times_dz = solver->tridiag ? 1 : 0;
-            P.cplx = 1;
+            P.cplx = solver->real_storage() ? 0 : 1;
             source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
             launches++;
         }
@@ -960,7 +1017,7 @@ struct ModelT : ob_model {
             P.in = (const T *)solver->storage();
             P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
             for (int k = 0; k < 3; k++) P.N[k] = g.N[k];
-            P.cplx = 1;
+            P.cplx = solver->real_storage() ? 0 : 1;
             P.scale = (T)solver->scale();
             copy_real_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
             launches++;

@@ -94,6 +94,21 @@ __device__ __forceinline__ T centered_face(const G &get, int i, int j, int k) {
 template <typename T, int N, bool FAST>
 __device__ __forceinline__ T weno_from_values(const T (&v)[2 * N - 1]) {
     const auto &tab = Tab<T>::get();
+    // smoothness coefficients (weno_interpolants.jl:169-192) come from the constant bank
+    auto wb = [&](int r, int c) -> T {
+#ifdef OB_BETA_LITERALS  // OFF: literal operands let the compiler re-associate the ill-conditioned quadratic form (measured: 1e-8 on a tracer with a large mean)
+        if constexpr (N == 3) {
+            constexpr T tbl[3][6] = {{10, -31, 11, 25, -19, 4}, {4, -13, 5, 13, -13, 4}, {4, -19, 11, 25, -31, 10}};
+            return tbl[r][c];
+        } else if constexpr (N == 2) {
+            constexpr T tbl[3] = {1, -2, 1};
+            return tbl[c];
+        } else
+#endif
+        {
+            return tab.weno_beta[N][r][c];
+        }
+    };
     T beta[N];
 #pragma unroll
     for (int r = 0; r < N; r++) {
@@ -107,13 +122,13 @@ __device__ __forceinline__ T weno_from_values(const T (&v)[2 * N - 1]) {
         T b = 0;
 #pragma unroll
         for (int s = 0; s < N - 1; s++) {
-            T inner = tab.weno_beta[N][r][c] * ps[s];
+            T inner = wb(r, c) * ps[s];
 #pragma unroll
-            for (int q = s + 1; q < N; q++) inner = fma_(tab.weno_beta[N][r][c + q - s], ps[q], inner);
+            for (int q = s + 1; q < N; q++) inner = fma_(wb(r, c + q - s), ps[q], inner);
             b = (s == 0) ? ps[s] * inner : fma_(ps[s], inner, b);
             c += N - s;
         }
-        b = fma_(ps[N - 1] * ps[N - 1], tab.weno_beta[N][r][c], b);
+        b = fma_(ps[N - 1] * ps[N - 1], wb(r, c), b);
         beta[r] = b;
     }
     T tau;

@@ -34,7 +34,7 @@ __device__ __forceinline__ T weno_sel(const T (&s)[2 * N], bool left) {
 
 template <typename T>
 struct FastGeom {
-    long sy, sz;          // row / plane strides in elements (identical for every field on this path)
+    int sy, sz;           // row / plane strides in elements (identical for every field on this path; parents < 2^31 elements)
     T dx, dy, dz;
     const T *dzc, *dzf;   // stretched z (pre-offset, logical k) or nullptr
     __device__ __forceinline__ T dzC(int k) const { return dzc ? __ldg(dzc + k) : dz; }
@@ -42,14 +42,14 @@ struct FastGeom {
 };
 
 template <int DIR, typename T>
-__device__ __forceinline__ long stride_of(const FastGeom<T> &g) { return DIR == 0 ? 1L : DIR == 1 ? g.sy : g.sz; }
+__device__ __forceinline__ int stride_of(const FastGeom<T> &g) { return DIR == 0 ? 1 : DIR == 1 ? g.sy : g.sz; }
 
 // q[m] = p[(lo + m) * stride<DIR>], m = 0 .. CNT-1
 template <int DIR, int CNT, typename T>
 __device__ __forceinline__ void load_line(const T *__restrict__ p, const FastGeom<T> &g, int lo, T (&out)[CNT]) {
-    const long st = stride_of<DIR>(g);
+    const int st = stride_of<DIR>(g);
 #pragma unroll
-    for (int m = 0; m < CNT; m++) out[m] = __ldg(p + (long)(lo + m) * st);
+    for (int m = 0; m < CNT; m++) out[m] = __ldg(p + (lo + m) * st);
 }
 
 // Advective flux in direction ADV of tendency WHICH for the thread whose own point is (i, j, kp) -- kp = k for the
@@ -90,8 +90,8 @@ template <typename T>
 struct FastTerms {
     const TendP<T> &P;
     const T *u, *v, *w;   // at the thread's (i, j, k)
-    long eo;              // element offset of (i, j, k) relative to logical (0, 0, 0): i + j*sy + k*sz
-    long sy, sz;
+    int eo;               // element offset of (i, j, k) relative to logical (0, 0, 0): i + j*sy + k*sz
+    int sy, sz;
     int k;
     __device__ __forceinline__ T ld(const T *p, int a, int b, int c) const { return __ldg(p + (a + b * sy + c * sz)); }
     __device__ __forceinline__ const T *at(const Fld<T> &f) const { return f.p + f.off + eo; }
@@ -209,11 +209,11 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
     const Fld<T> &qf = WHICH == 0 ? P.u : WHICH == 1 ? P.v : WHICH == 2 ? P.w : P.c[t];
     const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[t];
     FastGeom<T> g;
-    g.sy = P.u.sy; g.sz = P.u.sz; g.dx = gg.dx; g.dy = gg.dy; g.dz = gg.dz; g.dzc = gg.dzc; g.dzf = gg.dzf;
+    g.sy = P.u.sy; g.sz = (int)P.u.sz; g.dx = gg.dx; g.dy = gg.dy; g.dz = gg.dz; g.dzc = gg.dzc; g.dzf = gg.dzf;
     // Lanes outside the flux region (i > Nx+1, j > Ny+1) are clamped onto its edge: they compute valid-but-unused
     // fluxes, which keeps each level ONE branch-free block in which the three independent WENO chains interleave.
     const int ii = min(i, Nx + 1), jj = min(j, Ny + 1);
-    const long base = (long)ii + (long)jj * g.sy + (long)k0 * g.sz;  // every field has the same offsets on this path
+    const int base = ii + jj * g.sy + k0 * g.sz;  // every field has the same offsets on this path
     const T *pq = qf.p + qf.off + base;
     const T *pu = P.u.p + P.u.off + base, *pv = P.v.p + P.v.off + base, *pw = P.w.p + P.w.off + base;
     T lower = full_row ? fast_flux<T, N, FAST, WHICH, 2>(pq, pw, g, k0) : T(0);
@@ -232,7 +232,7 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
             const T fy1 = sy_buf[buf][ty + 1][tx];
             const T Vi = WHICH == 2 ? gg.rVf(k) : gg.rVc(k);
             const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower));
-            const long eo = (long)i + (long)j * g.sy + (long)k * g.sz;
+            const int eo = i + j * g.sy + k * g.sz;
             FastTerms<T> F{P, pu, pv, pw, eo, g.sy, g.sz, k};
             G.p[G.off + eo] = F.template finish<WHICH>(adv, t, pq);
         }
@@ -246,6 +246,7 @@ template <typename T, int N>
 __device__ __forceinline__ bool fast_path_ok(const TendP<T> &P, int k0, int k1) {
     const GridD<T> &g = P.g;
     if (g.topo[0] != PERIODIC || g.topo[1] != PERIODIC) return false;
+    if (P.u.sz * (long)(g.N[2] + 2 * g.H[2] + 1) >= 2147483647L) return false;  // 32-bit element offsets
     if (g.topo[2] == PERIODIC) return true;
     if (g.topo[2] == FLAT) return false;
     // Bounded z: face-type flux indices k0 .. k1+1 and centre-type k0-1 .. k1 must satisfy outside_*_halo for buffer N

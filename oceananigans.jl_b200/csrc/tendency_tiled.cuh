@@ -70,8 +70,8 @@ __device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int 
     }
 }
 
-template <typename T, class S, bool FAST, int TY, int KC>
-__global__ void __launch_bounds__(32 * TY, 3) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc) {
+template <typename T, class S, bool FAST, int TY, int KC, int MINB>
+__global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc) {
     __shared__ T sy[2][TY][32];
     const int which = blockIdx.y;
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
@@ -101,13 +101,8 @@ __global__ void __launch_bounds__(32 * TY, 3) tendency_march_kernel(const __grid
     else march_body<T, S, FAST, 3, TY, KC>(P, which - 3, i, j, k0, k1, sy);
 }
 
-// mode: 0 auto, 1 generic, 2 marching
-template <typename T, class S>
-static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done) {
-    (void)sm_count;
-    done = false;
-    if (mode == 1) return cudaSuccess;
-    constexpr int TY = 8, KC = 32;
+template <typename T, class S, int TY, int KC, int MINB>
+static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch) {
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
     int nb = 0;
     long nkc = (Nz + KC - 1) / KC;
@@ -116,13 +111,29 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
         nkc = 2 + (Nz - 2 * nb + KC - 1) / KC;
     }
     const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
-    if (ntx * nty * nkc > 2147483647L) return cudaSuccess;
+    if (ntx * nty * nkc > 2147483647L) return cudaErrorInvalidConfiguration;
     dim3 grid((unsigned)(ntx * nty * nkc), 3 + P.ntr), block(32, TY);
-    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC><<<grid, block, 0, st>>>(P, nb, (int)nkc);
-    else tendency_march_kernel<T, S, false, TY, KC><<<grid, block, 0, st>>>(P, nb, (int)nkc);
+    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc);
+    else tendency_march_kernel<T, S, false, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc);
     *nlaunch += 1;
-    done = true;
     return cudaGetLastError();
+}
+
+// mode: 0 auto, 1 generic, 2 marching (3.. = tuning variants when built with -DOB_TI_EXPERIMENT)
+template <typename T, class S>
+static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done) {
+    (void)sm_count;
+    done = false;
+    if (mode == 1) return cudaSuccess;
+    done = true;
+#ifdef OB_TI_EXPERIMENT
+    if (mode == 3) return launch_march<T, S, 8, 64, 4>(P, fast, st, nlaunch);
+    if (mode == 4) return launch_march<T, S, 4, 32, 8>(P, fast, st, nlaunch);
+    if (mode == 5) return launch_march<T, S, 16, 32, 2>(P, fast, st, nlaunch);
+    if (mode == 6) return launch_march<T, S, 8, 32, 3>(P, fast, st, nlaunch);
+    if (mode == 7) return launch_march<T, S, 8, 16, 4>(P, fast, st, nlaunch);
+#endif
+    return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch);
 }
 
 }  // namespace ob
