@@ -61,96 +61,122 @@ __global__ void __launch_bounds__(128) smagorinsky_kernel(const __grid_constant_
     P.nue[m](i, j, k) = cs2 * (Df * Df) * sqrt(2 * SS);
 }
 
+// AnisotropicMinimumDissipation: νₑ and every κₑ of one cell in one thread.  The 27 normalised velocity gradients the
+// "30 terms" are built from (3 at ccc; ∂x v, ∂y u at the 4 surrounding ffc points; ∂x w, ∂z u at the 4 fcf points;
+// ∂y w, ∂z v at the 4 cff points) are evaluated ONCE and every term of anisotropic_minimum_dissipation.jl:251-358 is then
+// formed from them with the reference's own expression order.  A Flat direction needs no special case: its index stride
+// is 0 (so δ = 0 exactly and ℑ = 0.5*(f+f) = f exactly) and its spacing is 1.
+template <typename T>
+__device__ __forceinline__ T interp4(const T (&f)[2][2]) {  // ℑ_outer(ℑ_inner f), f[inner][outer]
+    return T(0.5) * (T(0.5) * (f[0][0] + f[1][0]) + T(0.5) * (f[0][1] + f[1][1]));
+}
 template <typename T>
 __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<T> P, int m) {
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const GridD<T> &g = P.g;
-    Grad<T> G{P};
     const ClosureD<T> &cl = P.cl[m];
-    // filter widths: 2Δ at ccc, evaluated at the stencil point's own index whatever its location (:231-243)
-    auto dfx = [&](int) { return 2 * g.dx; };
-    auto dfy = [&](int) { return 2 * g.dy; };
-    auto dfz = [&](int c) { return 2 * g.dzC(c); };
-    auto n_dx_v = [&](int a, int b, int c) { return dfx(a) / dfy(b) * G.dx_v(a, b, c); };
-    auto n_dy_u = [&](int a, int b, int c) { return dfy(b) / dfx(a) * G.dy_u(a, b, c); };
-    auto n_dx_w = [&](int a, int b, int c) { return dfx(a) / dfz(c) * G.dx_w(a, b, c); };
-    auto n_dz_u = [&](int a, int b, int c) { return dfz(c) / dfx(a) * G.dz_u(a, b, c); };
-    auto n_dy_w = [&](int a, int b, int c) { return dfy(b) / dfz(c) * G.dy_w(a, b, c); };
-    auto n_dz_v = [&](int a, int b, int c) { return dfz(c) / dfy(b) * G.dz_v(a, b, c); };
-    const T fx = dfx(i), fy = dfy(j), fz = dfz(k);
-    const T delta2 = 3 / (1 / (fx * fx) + 1 / (fy * fy) + 1 / (fz * fz));
-    const T ux = G.dx_u(i, j, k), vy = G.dy_v(i, j, k), wz = G.dz_w(i, j, k);
-#define IXY(f) Ic2<T, 1, 0>(g, f, i, j, k)
-#define IXZ(f) Ic2<T, 2, 0>(g, f, i, j, k)
-#define IYZ(f) Ic2<T, 2, 1>(g, f, i, j, k)
-    if (blockIdx.y == 0) {
-        auto n_S12 = [&](int a, int b, int c) { return T(0.5) * (n_dy_u(a, b, c) + n_dx_v(a, b, c)); };
-        auto n_S13 = [&](int a, int b, int c) { return T(0.5) * (n_dz_u(a, b, c) + n_dx_w(a, b, c)); };
-        auto n_S23 = [&](int a, int b, int c) { return T(0.5) * (n_dz_v(a, b, c) + n_dy_w(a, b, c)); };
-        auto sq = [](T x) { return x * x; };
-        auto n_dx_v2 = [&](int a, int b, int c) { return sq(n_dx_v(a, b, c)); };
-        auto n_dy_u2 = [&](int a, int b, int c) { return sq(n_dy_u(a, b, c)); };
-        auto n_dx_w2 = [&](int a, int b, int c) { return sq(n_dx_w(a, b, c)); };
-        auto n_dz_u2 = [&](int a, int b, int c) { return sq(n_dz_u(a, b, c)); };
-        auto n_dy_w2 = [&](int a, int b, int c) { return sq(n_dy_w(a, b, c)); };
-        auto n_dz_v2 = [&](int a, int b, int c) { return sq(n_dz_v(a, b, c)); };
-        const T q = ux * ux + vy * vy + wz * wz + IXY(n_dx_v2) + IXY(n_dy_u2) + IXZ(n_dx_w2) + IXZ(n_dz_u2) + IYZ(n_dy_w2) + IYZ(n_dz_v2);
+    const int ox = g.topo[0] == FLAT ? 0 : 1;
+    // fields may differ in their strides (Face fields on Bounded directions): per-field accessors with relative offsets
+    auto at = [&](const Fld<T> &f, int a, int b, int c) -> T {
+        const long oy = g.topo[1] == FLAT ? 0 : f.sy, oz = g.topo[2] == FLAT ? 0 : f.sz;
+        return __ldg(f.p + (f.off + i + (long)j * f.sy + (long)k * f.sz + a * ox + b * oy + c * oz));
+    };
+    const T rdx = g.rdx, rdy = g.rdy;
+    const T fx = 2 * g.dx, fy = 2 * g.dy;
+    T fz[2], rdzf[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) { const int kc = g.topo[2] == FLAT ? k : k + c; fz[c] = 2 * g.dzC(kc); rdzf[c] = g.rdzF(kc); }
+    const T rxy = fx / fy, ryx = fy / fx;
+    T rxz[2], rzx[2], ryz[2], rzy[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) { rxz[c] = fx / fz[c]; rzx[c] = fz[c] / fx; ryz[c] = fy / fz[c]; rzy[c] = fz[c] / fy; }
+    const T delta2 = 3 / (1 / (fx * fx) + 1 / (fy * fy) + 1 / (fz[0] * fz[0]));
+    // ccc
+    const T ux = (at(P.u, 1, 0, 0) - at(P.u, 0, 0, 0)) * rdx;
+    const T vy = (at(P.v, 0, 1, 0) - at(P.v, 0, 0, 0)) * rdy;
+    const T wz = (at(P.w, 0, 0, 1) - at(P.w, 0, 0, 0)) * g.rdzC(k);
+    // ffc [a][b], fcf [a][c], cff [b][c]
+    T xv[2][2], yu[2][2], xw[2][2], zu[2][2], yw[2][2], zv[2][2], s12[2][2], s13[2][2], s23[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            xv[p][q] = rxy * ((at(P.v, p, q, 0) - at(P.v, p - 1, q, 0)) * rdx);
+            yu[p][q] = ryx * ((at(P.u, p, q, 0) - at(P.u, p, q - 1, 0)) * rdy);
+            s12[p][q] = T(0.5) * (yu[p][q] + xv[p][q]);
+            xw[p][q] = rxz[q] * ((at(P.w, p, 0, q) - at(P.w, p - 1, 0, q)) * rdx);
+            zu[p][q] = rzx[q] * ((at(P.u, p, 0, q) - at(P.u, p, 0, q - 1)) * rdzf[q]);
+            s13[p][q] = T(0.5) * (zu[p][q] + xw[p][q]);
+            yw[p][q] = ryz[q] * ((at(P.w, 0, p, q) - at(P.w, 0, p - 1, q)) * rdy);
+            zv[p][q] = rzy[q] * ((at(P.v, 0, p, q) - at(P.v, 0, p, q - 1)) * rdzf[q]);
+            s23[p][q] = T(0.5) * (zv[p][q] + yw[p][q]);
+        }
+    auto I = [&](auto fn) {  // interp4 of a pointwise expression fn(p, q)
+        T t[2][2];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int p = 0; p < 2; p++) t[p][q] = fn(p, q);
+        return interp4<T>(t);
+    };
+#define SQ(A) I([&](int p, int q) { return A[p][q] * A[p][q]; })
+#define PR(A, B) I([&](int p, int q) { return A[p][q] * B[p][q]; })
+#define ID(A) I([&](int p, int q) { return A[p][q]; })
+    const T I_xv2 = SQ(xv), I_yu2 = SQ(yu), I_xw2 = SQ(xw), I_zu2 = SQ(zu), I_yw2 = SQ(yw), I_zv2 = SQ(zv);
+    const T I_xv = ID(xv), I_yu = ID(yu), I_xw = ID(xw), I_zu = ID(zu), I_yw = ID(yw), I_zv = ID(zv);
+    {
+        const T q = ux * ux + vy * vy + wz * wz + I_xv2 + I_yu2 + I_xw2 + I_zu2 + I_yw2 + I_zv2;
         T nu = 0;
         if (q != 0) {
-            auto n_dx_v_S12 = [&](int a, int b, int c) { return n_dx_v(a, b, c) * n_S12(a, b, c); };
-            auto n_dy_u_S12 = [&](int a, int b, int c) { return n_dy_u(a, b, c) * n_S12(a, b, c); };
-            auto n_dx_w_S13 = [&](int a, int b, int c) { return n_dx_w(a, b, c) * n_S13(a, b, c); };
-            auto n_dz_u_S13 = [&](int a, int b, int c) { return n_dz_u(a, b, c) * n_S13(a, b, c); };
-            auto n_dz_v_S23 = [&](int a, int b, int c) { return n_dz_v(a, b, c) * n_S23(a, b, c); };
-            auto n_dy_w_S23 = [&](int a, int b, int c) { return n_dy_w(a, b, c) * n_S23(a, b, c); };
-            const T r1 = ux * (ux * ux) + vy * IXY(n_dx_v2) + wz * IXZ(n_dx_w2) + 2 * ux * IXY(n_dx_v_S12) + 2 * ux * IXZ(n_dx_w_S13) +
-                         2 * IXY(n_dx_v) * IXZ(n_dx_w) * IYZ(n_S23);
-            const T r2 = ux * IXY(n_dy_u2) + vy * (vy * vy) + wz * IYZ(n_dy_w2) + 2 * vy * IXY(n_dy_u_S12) +
-                         2 * IXY(n_dy_u) * IYZ(n_dy_w) * IXZ(n_S13) + 2 * vy * IYZ(n_dy_w_S23);
-            const T r3 = ux * IXZ(n_dz_u2) + vy * IYZ(n_dz_v2) + wz * (wz * wz) + 2 * IXZ(n_dz_u) * IYZ(n_dz_v) * IXY(n_S12) +
-                         2 * wz * IXZ(n_dz_u_S13) + 2 * wz * IYZ(n_dz_v_S23);
+            const T r1 = ux * (ux * ux) + vy * I_xv2 + wz * I_xw2 + 2 * ux * PR(xv, s12) + 2 * ux * PR(xw, s13) + 2 * I_xv * I_xw * ID(s23);
+            const T r2 = ux * I_yu2 + vy * (vy * vy) + wz * I_yw2 + 2 * vy * PR(yu, s12) + 2 * I_yu * I_yw * ID(s13) + 2 * vy * PR(yw, s23);
+            const T r3 = ux * I_zu2 + vy * I_zv2 + wz * (wz * wz) + 2 * I_zu * I_zv * ID(s12) + 2 * wz * PR(zu, s13) + 2 * wz * PR(zv, s23);
             const T r = r1 + r2 + r3;
             T cbz = 0;
-            if (cl.amd_has_cb) {
-                auto dxb = [&](int a, int b, int c) { return (g.topo[0] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a - 1, b, c)) * g.rdx; };
-                auto dyb = [&](int a, int b, int c) { return (g.topo[1] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a, b - 1, c)) * g.rdy; };
-                auto dzb = [&](int a, int b, int c) { return (g.topo[2] == FLAT ? T(0) : bpert(P, a, b, c) - bpert(P, a, b, c - 1)) * g.rdzF(c); };
-                const T wxbx = IXZ(n_dx_w) * fx * Ic1<T, 0>(g, dxb, i, j, k);
-                const T wyby = IYZ(n_dy_w) * fy * Ic1<T, 1>(g, dyb, i, j, k);
-                const T wzbz = wz * fz * Ic1<T, 2>(g, dzb, i, j, k);
-                cbz = cl.cb * (wxbx + wyby + wzbz);
+            if (cl.amd_has_cb) {  // Cb_norm_wᵢ_bᵢᶜᶜᶜ (:320-333): ℑ of ∂b at the faces (bpert needs absolute indices)
+                auto bp = [&](int a, int b, int c) { return bpert(P, i + a * ox, j + (g.topo[1] == FLAT ? 0 : b), k + (g.topo[2] == FLAT ? 0 : c)); };
+                const T bx = T(0.5) * ((bp(0, 0, 0) - bp(-1, 0, 0)) * rdx + (bp(1, 0, 0) - bp(0, 0, 0)) * rdx);
+                const T by = T(0.5) * ((bp(0, 0, 0) - bp(0, -1, 0)) * rdy + (bp(0, 1, 0) - bp(0, 0, 0)) * rdy);
+                const T bz = T(0.5) * ((bp(0, 0, 0) - bp(0, 0, -1)) * rdzf[0] + (bp(0, 0, 1) - bp(0, 0, 0)) * rdzf[1]);
+                cbz = cl.cb * (I_xw * fx * bx + I_yw * fy * by + wz * fz[0] * bz);
             }
-            cbz = cbz / fz;
+            cbz = cbz / fz[0];
             nu = -cl.Cnu * delta2 * (r - cbz) / q;
         }
         P.nue[m](i, j, k) = fmax(T(0), nu);
-    } else {
-        const int t = blockIdx.y - 1;
+    }
+    for (int t = 0; t < P.ntr; t++) {
         const Fld<T> &c = P.c[t];
-        auto n_dx_c = [&](int a, int b, int cc) { return dfx(a) * ((g.topo[0] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a - 1, b, cc)) * g.rdx); };
-        auto n_dy_c = [&](int a, int b, int cc) { return dfy(b) * ((g.topo[1] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a, b - 1, cc)) * g.rdy); };
-        auto n_dz_c = [&](int a, int b, int cc) { return dfz(cc) * ((g.topo[2] == FLAT ? T(0) : c.ld(a, b, cc) - c.ld(a, b, cc - 1)) * g.rdzF(cc)); };
-        auto n_dx_c2 = [&](int a, int b, int cc) { T x = n_dx_c(a, b, cc); return x * x; };
-        auto n_dy_c2 = [&](int a, int b, int cc) { T x = n_dy_c(a, b, cc); return x * x; };
-        auto n_dz_c2 = [&](int a, int b, int cc) { T x = n_dz_c(a, b, cc); return x * x; };
-        const T icx2 = Ic1<T, 0>(g, n_dx_c2, i, j, k), icy2 = Ic1<T, 1>(g, n_dy_c2, i, j, k), icz2 = Ic1<T, 2>(g, n_dz_c2, i, j, k);
+        T xc[2], yc[2], zc[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            xc[p] = fx * ((at(c, p, 0, 0) - at(c, p - 1, 0, 0)) * rdx);
+            yc[p] = fy * ((at(c, 0, p, 0) - at(c, 0, p - 1, 0)) * rdy);
+            zc[p] = fz[p] * ((at(c, 0, 0, p) - at(c, 0, 0, p - 1)) * rdzf[p]);
+        }
+        const T icx2 = T(0.5) * (xc[0] * xc[0] + xc[1] * xc[1]), icy2 = T(0.5) * (yc[0] * yc[0] + yc[1] * yc[1]), icz2 = T(0.5) * (zc[0] * zc[0] + zc[1] * zc[1]);
         const T sigma = icx2 + icy2 + icz2;
         T kap_ = 0;
         if (sigma != 0) {
-            const T icx = Ic1<T, 0>(g, n_dx_c, i, j, k), icy = Ic1<T, 1>(g, n_dy_c, i, j, k), icz = Ic1<T, 2>(g, n_dz_c, i, j, k);
-            // cy_uy uses ℑxzᶜᵃᶜ of norm_∂y_w exactly as the reference does (:345)
-            const T cx = ux * icx2 + IXY(n_dx_v) * icx * icy + IXZ(n_dx_w) * icx * icz;
-            const T cy = IXY(n_dy_u) * icy * icx + vy * icy2 + IXZ(n_dy_w) * icy * icz;
-            const T cz = IXZ(n_dz_u) * icz * icx + IYZ(n_dz_v) * icz * icy + wz * icz2;
+            const T icx = T(0.5) * (xc[0] + xc[1]), icy = T(0.5) * (yc[0] + yc[1]), icz = T(0.5) * (zc[0] + zc[1]);
+            // cy_uy uses ℑxzᶜᵃᶜ of norm_∂y_w exactly as the reference does (:345): norm_∂y_w at (i+a, j, k+c)
+            T yw_xz[2][2];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int p = 0; p < 2; p++) yw_xz[p][q] = ryz[q] * ((at(P.w, p, 0, q) - at(P.w, p, -1, q)) * rdy);
+            const T cx = ux * icx2 + I_xv * icx * icy + I_xw * icx * icz;
+            const T cy = I_yu * icy * icx + vy * icy2 + interp4<T>(yw_xz) * icy * icz;
+            const T cz = I_zu * icz * icx + I_zv * icz * icy + wz * icz2;
             const T theta = cx + cy + cz;
             kap_ = -cl.Ckappa[t] * delta2 * theta / sigma;
         }
         P.kappae[m][t](i, j, k) = fmax(T(0), kap_);
     }
-#undef IXY
-#undef IXZ
-#undef IYZ
+#undef SQ
+#undef PR
+#undef ID
 }
 
 }  // namespace ob

@@ -867,8 +867,7 @@ struct ModelT : ob_model {
                 smagorinsky_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m);
                 launches++;
             } else {
-                dim3 grid2(grid.x, 1 + ntr);
-                amd_kernel<T><<<grid2, bs, 0, ctx->stream>>>(P, m);
+                amd_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m);
                 launches++;
             }
         }
