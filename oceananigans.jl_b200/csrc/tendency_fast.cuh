@@ -32,21 +32,32 @@ __device__ __forceinline__ T weno_sel(const T (&s)[2 * N], bool left) {
     return weno_from_values<T, N, FAST>(v);
 }
 
-template <typename T>
+// Geometry of the fast path.  STR = stretched z: metrics are read per level from the host-built arrays; otherwise every
+// metric is a kernel constant (no pointer tests, no loads).
+template <typename T, bool STR>
 struct FastGeom {
     int sy, sz;           // row / plane strides in elements (identical for every field on this path; parents < 2^31 elements)
-    T dx, dy, dz;
-    const T *dzc, *dzf;   // stretched z (pre-offset, logical k) or nullptr
-    __device__ __forceinline__ T dzC(int k) const { return dzc ? __ldg(dzc + k) : dz; }
-    __device__ __forceinline__ T dzF(int k) const { return dzf ? __ldg(dzf + k) : dz; }
+    T dx, dy, rdx, rdy;
+    T dz, rdz, rvol;
+    const T *dzc, *dzf, *rdzc, *rdzf, *rvc, *rvf;  // pre-offset, logical k
+    __device__ __forceinline__ T dzC(int k) const { if constexpr (STR) return __ldg(dzc + k); else return dz; }
+    __device__ __forceinline__ T dzF(int k) const { if constexpr (STR) return __ldg(dzf + k); else return dz; }
+    __device__ __forceinline__ T rdzC(int k) const { if constexpr (STR) return __ldg(rdzc + k); else return rdz; }
+    __device__ __forceinline__ T rdzF(int k) const { if constexpr (STR) return __ldg(rdzf + k); else return rdz; }
+    __device__ __forceinline__ T rVc(int k) const { if constexpr (STR) return __ldg(rvc + k); else return rvol; }
+    __device__ __forceinline__ T rVf(int k) const { if constexpr (STR) return __ldg(rvf + k); else return rvol; }
+    __device__ __forceinline__ void init(const GridD<T> &gg, int sy_, long sz_) {
+        sy = sy_; sz = (int)sz_; dx = gg.dx; dy = gg.dy; rdx = gg.rdx; rdy = gg.rdy; dz = gg.dz; rdz = gg.rdz; rvol = gg.rvol;
+        dzc = gg.dzc; dzf = gg.dzf; rdzc = gg.rdzc; rdzf = gg.rdzf; rvc = gg.rvc; rvf = gg.rvf;
+    }
 };
 
-template <int DIR, typename T>
-__device__ __forceinline__ int stride_of(const FastGeom<T> &g) { return DIR == 0 ? 1 : DIR == 1 ? g.sy : g.sz; }
+template <int DIR, typename T, bool STR>
+__device__ __forceinline__ int stride_of(const FastGeom<T, STR> &g) { return DIR == 0 ? 1 : DIR == 1 ? g.sy : g.sz; }
 
 // q[m] = p[(lo + m) * stride<DIR>], m = 0 .. CNT-1
-template <int DIR, int CNT, typename T>
-__device__ __forceinline__ void load_line(const T *__restrict__ p, const FastGeom<T> &g, int lo, T (&out)[CNT]) {
+template <int DIR, int CNT, typename T, bool STR>
+__device__ __forceinline__ void load_line(const T *__restrict__ p, const FastGeom<T, STR> &g, int lo, T (&out)[CNT]) {
     const int st = stride_of<DIR>(g);
 #pragma unroll
     for (int m = 0; m < CNT; m++) out[m] = __ldg(p + (lo + m) * st);
@@ -55,8 +66,8 @@ __device__ __forceinline__ void load_line(const T *__restrict__ p, const FastGeo
 // Advective flux in direction ADV of tendency WHICH for the thread whose own point is (i, j, kp) -- kp = k for the
 // x/y fluxes, k+1 for the upper z flux.  pq / pa point at (i, j, kp) of the advected field and of the advecting
 // velocity component ADV.
-template <typename T, int N, bool FAST, int WHICH, int ADV>
-__device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__restrict__ pa, const FastGeom<T> &g, int kp) {
+template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR>
+__device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__restrict__ pa, const FastGeom<T, STR> &g, int kp) {
     T s[2 * N];
     load_line<ADV, 2 * N>(pq, g, -N, s);
     if constexpr (WHICH == 3) {
@@ -86,27 +97,27 @@ __device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__rest
 // from the thread's own point (a, b, c are compile-time after inlining) so that every load is base + constant.
 // Valid where x, y, z are not Flat and every field shares the strides (sy, sz).
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool STR>
 struct FastTerms {
     const TendP<T> &P;
+    const FastGeom<T, STR> &G;
     const T *u, *v, *w;   // at the thread's (i, j, k)
     int eo;               // element offset of (i, j, k) relative to logical (0, 0, 0): i + j*sy + k*sz
-    int sy, sz;
     int k;
-    __device__ __forceinline__ T ld(const T *p, int a, int b, int c) const { return __ldg(p + (a + b * sy + c * sz)); }
+    __device__ __forceinline__ T ld(const T *p, int a, int b, int c) const { return __ldg(p + (a + b * G.sy + c * G.sz)); }
     __device__ __forceinline__ const T *at(const Fld<T> &f) const { return f.p + f.off + eo; }
-    __device__ __forceinline__ T dzC(int c) const { return P.g.dzC(k + c); }
-    __device__ __forceinline__ T dzF(int c) const { return P.g.dzF(k + c); }
+    __device__ __forceinline__ T dzC(int c) const { return G.dzC(k + c); }
+    __device__ __forceinline__ T dzF(int c) const { return G.dzF(k + c); }
     // velocity gradients (velocity_tracer_gradients.jl:6-19)
-    __device__ __forceinline__ T dx_u(int a, int b, int c) const { return (ld(u, a + 1, b, c) - ld(u, a, b, c)) * P.g.rdx; }
-    __device__ __forceinline__ T dy_v(int a, int b, int c) const { return (ld(v, a, b + 1, c) - ld(v, a, b, c)) * P.g.rdy; }
-    __device__ __forceinline__ T dz_w(int a, int b, int c) const { return (ld(w, a, b, c + 1) - ld(w, a, b, c)) * P.g.rdzC(k + c); }
-    __device__ __forceinline__ T dx_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a - 1, b, c)) * P.g.rdx; }
-    __device__ __forceinline__ T dy_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b - 1, c)) * P.g.rdy; }
-    __device__ __forceinline__ T dx_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a - 1, b, c)) * P.g.rdx; }
-    __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b, c - 1)) * P.g.rdzF(k + c); }
-    __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a, b - 1, c)) * P.g.rdy; }
-    __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a, b, c - 1)) * P.g.rdzF(k + c); }
+    __device__ __forceinline__ T dx_u(int a, int b, int c) const { return (ld(u, a + 1, b, c) - ld(u, a, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dy_v(int a, int b, int c) const { return (ld(v, a, b + 1, c) - ld(v, a, b, c)) * G.rdy; }
+    __device__ __forceinline__ T dz_w(int a, int b, int c) const { return (ld(w, a, b, c + 1) - ld(w, a, b, c)) * G.rdzC(k + c); }
+    __device__ __forceinline__ T dx_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a - 1, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dy_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b - 1, c)) * G.rdy; }
+    __device__ __forceinline__ T dx_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a - 1, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b, c - 1)) * G.rdzF(k + c); }
+    __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a, b - 1, c)) * G.rdy; }
+    __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a, b, c - 1)) * G.rdzF(k + c); }
     __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * (dy_u(a, b, c) + dx_v(a, b, c)); }
     __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * (dz_u(a, b, c) + dx_w(a, b, c)); }
     __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * (dz_v(a, b, c) + dy_w(a, b, c)); }
@@ -123,38 +134,38 @@ struct FastTerms {
     __device__ __forceinline__ T nu_fcf(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 0, a, b, c) : P.cl[m].nu; }
     __device__ __forceinline__ T nu_cff(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 1, a, b, c) : P.cl[m].nu; }
     // Ax_q(viscous flux) = area * (-2 ν Σ) (closure_kernel_operators.jl:20-40)
-    __device__ __forceinline__ T ux(int m, const T *ne, int a, int b, int c) const { return (P.g.dy * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dx_u(a, b, c))); }
-    __device__ __forceinline__ T uy(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
-    __device__ __forceinline__ T uz(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * P.g.dy) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
-    __device__ __forceinline__ T vx(int m, const T *ne, int a, int b, int c) const { return (P.g.dy * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
-    __device__ __forceinline__ T vy(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dy_v(a, b, c))); }
-    __device__ __forceinline__ T vz(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * P.g.dy) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
-    __device__ __forceinline__ T wx(int m, const T *ne, int a, int b, int c) const { return (P.g.dy * dzF(c)) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
-    __device__ __forceinline__ T wy(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * dzF(c)) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
-    __device__ __forceinline__ T wz(int m, const T *ne, int a, int b, int c) const { return (P.g.dx * P.g.dy) * (-2 * (nu_ccc(m, ne, a, b, c) * dz_w(a, b, c))); }
+    __device__ __forceinline__ T ux(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dx_u(a, b, c))); }
+    __device__ __forceinline__ T uy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T uz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T vx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T vy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dy_v(a, b, c))); }
+    __device__ __forceinline__ T vz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzF(c)) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T wy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzF(c)) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_ccc(m, ne, a, b, c) * dz_w(a, b, c))); }
     __device__ __forceinline__ const T *nue_ptr(int m) const { return P.cl[m].kind == CL_SCALAR ? nullptr : at(P.nue[m]); }
     template <int WHICH> __device__ __forceinline__ T div_tau(int m) const {
         const T *ne = nue_ptr(m);
         if constexpr (WHICH == 0)
-            return P.g.rVc(k) * ((ux(m, ne, 0, 0, 0) - ux(m, ne, -1, 0, 0)) + (uy(m, ne, 0, 1, 0) - uy(m, ne, 0, 0, 0)) + (uz(m, ne, 0, 0, 1) - uz(m, ne, 0, 0, 0)));
+            return G.rVc(k) * ((ux(m, ne, 0, 0, 0) - ux(m, ne, -1, 0, 0)) + (uy(m, ne, 0, 1, 0) - uy(m, ne, 0, 0, 0)) + (uz(m, ne, 0, 0, 1) - uz(m, ne, 0, 0, 0)));
         else if constexpr (WHICH == 1)
-            return P.g.rVc(k) * ((vx(m, ne, 1, 0, 0) - vx(m, ne, 0, 0, 0)) + (vy(m, ne, 0, 0, 0) - vy(m, ne, 0, -1, 0)) + (vz(m, ne, 0, 0, 1) - vz(m, ne, 0, 0, 0)));
+            return G.rVc(k) * ((vx(m, ne, 1, 0, 0) - vx(m, ne, 0, 0, 0)) + (vy(m, ne, 0, 0, 0) - vy(m, ne, 0, -1, 0)) + (vz(m, ne, 0, 0, 1) - vz(m, ne, 0, 0, 0)));
         else
-            return P.g.rVf(k) * ((wx(m, ne, 1, 0, 0) - wx(m, ne, 0, 0, 0)) + (wy(m, ne, 0, 1, 0) - wy(m, ne, 0, 0, 0)) + (wz(m, ne, 0, 0, 0) - wz(m, ne, 0, 0, -1)));
+            return G.rVf(k) * ((wx(m, ne, 1, 0, 0) - wx(m, ne, 0, 0, 0)) + (wy(m, ne, 0, 1, 0) - wy(m, ne, 0, 0, 0)) + (wz(m, ne, 0, 0, 0) - wz(m, ne, 0, 0, -1)));
     }
     // diffusive flux of tracer t along D at the face (a, b, c) (abstract_scalar_diffusivity_closure.jl:260-262)
     __device__ __forceinline__ T qflux(int m, int t, const T *cp, const T *kf, int D, int a, int b, int c) const {
         const int kind = P.cl[m].kind;
         const T kap = kind == CL_SCALAR ? P.cl[m].kappa[t] : kind == CL_SMAG ? If1(kf, D, a, b, c) / P.cl[m].Pr[t] : If1(kf, D, a, b, c);
-        const T rd = D == 0 ? P.g.rdx : D == 1 ? P.g.rdy : P.g.rdzF(k + c);
-        const T A = D == 0 ? P.g.dy * dzC(c) : D == 1 ? P.g.dx * dzC(c) : P.g.dx * P.g.dy;
+        const T rd = D == 0 ? G.rdx : D == 1 ? G.rdy : G.rdzF(k + c);
+        const T A = D == 0 ? G.dy * dzC(c) : D == 1 ? G.dx * dzC(c) : G.dx * G.dy;
         const T dc = (ld(cp, a, b, c) - ld(cp, a - (D == 0), b - (D == 1), c - (D == 2))) * rd;
         return A * (-kap * dc);
     }
     __device__ __forceinline__ T div_q(int m, int t, const T *cp) const {
         const int kind = P.cl[m].kind;
         const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][t]);
-        return P.g.rVc(k) * ((qflux(m, t, cp, kf, 0, 1, 0, 0) - qflux(m, t, cp, kf, 0, 0, 0, 0)) + (qflux(m, t, cp, kf, 1, 0, 1, 0) - qflux(m, t, cp, kf, 1, 0, 0, 0)) +
+        return G.rVc(k) * ((qflux(m, t, cp, kf, 0, 1, 0, 0) - qflux(m, t, cp, kf, 0, 0, 0, 0)) + (qflux(m, t, cp, kf, 1, 0, 1, 0) - qflux(m, t, cp, kf, 1, 0, 0, 0)) +
                              (qflux(m, t, cp, kf, 2, 0, 0, 1) - qflux(m, t, cp, kf, 2, 0, 0, 0)));
     }
     __device__ __forceinline__ T bpert(int c) const {
@@ -168,19 +179,19 @@ struct FastTerms {
         if constexpr (WHICH == 0) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
-                const T A = P.g.dx * dzC(0);
+                const T A = G.dx * dzC(0);
                 const T I = T(0.5) * (T(0.5) * (A * ld(v, -1, 0, 0) + A * ld(v, 0, 0, 0)) + T(0.5) * (A * ld(v, -1, 1, 0) + A * ld(v, 0, 1, 0)));
-                r = r - (-fbar * I * (1 / (P.g.dx * dzC(0))));
+                r = r - (-fbar * I * (1 / (G.dx * dzC(0))));
             }
-            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, -1, 0, 0)) * P.g.rdx; }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, -1, 0, 0)) * G.rdx; }
         } else if constexpr (WHICH == 1) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
-                const T A = P.g.dy * dzC(0);
+                const T A = G.dy * dzC(0);
                 const T I = T(0.5) * (T(0.5) * (A * ld(u, 0, -1, 0) + A * ld(u, 1, -1, 0)) + T(0.5) * (A * ld(u, 0, 0, 0) + A * ld(u, 1, 0, 0)));
-                r = r - (fbar * I * (1 / (P.g.dy * dzC(0))));
+                r = r - (fbar * I * (1 / (G.dy * dzC(0))));
             }
-            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, 0, -1, 0)) * P.g.rdy; }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, 0, -1, 0)) * G.rdy; }
         } else if constexpr (WHICH == 2) {
             if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
         }
@@ -199,7 +210,7 @@ struct FastTerms {
     }
 };
 
-template <typename T, int N, bool FAST, int WHICH, int TY, int KC>
+template <typename T, int N, bool FAST, int WHICH, int TY, int KC, bool STR>
 __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i, int j, int k0, int k1, T (*sy_buf)[TY][32]) {
     const GridD<T> &gg = P.g;
     const int Nx = gg.N[0], Ny = gg.N[1];
@@ -208,21 +219,21 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
     const bool full_row = ty < TY - 1;  // warp-uniform: the overlap row only supplies its y-direction flux
     const Fld<T> &qf = WHICH == 0 ? P.u : WHICH == 1 ? P.v : WHICH == 2 ? P.w : P.c[t];
     const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[t];
-    FastGeom<T> g;
-    g.sy = P.u.sy; g.sz = (int)P.u.sz; g.dx = gg.dx; g.dy = gg.dy; g.dz = gg.dz; g.dzc = gg.dzc; g.dzf = gg.dzf;
+    FastGeom<T, STR> g;
+    g.init(gg, P.u.sy, P.u.sz);
     // Lanes outside the flux region (i > Nx+1, j > Ny+1) are clamped onto its edge: they compute valid-but-unused
     // fluxes, which keeps each level ONE branch-free block in which the three independent WENO chains interleave.
     const int ii = min(i, Nx + 1), jj = min(j, Ny + 1);
     const int base = ii + jj * g.sy + k0 * g.sz;  // every field has the same offsets on this path
     const T *pq = qf.p + qf.off + base;
     const T *pu = P.u.p + P.u.off + base, *pv = P.v.p + P.v.off + base, *pw = P.w.p + P.w.off + base;
-    T lower = full_row ? fast_flux<T, N, FAST, WHICH, 2>(pq, pw, g, k0) : T(0);
+    T lower = full_row ? fast_flux<T, N, FAST, WHICH, 2, STR>(pq, pw, g, k0) : T(0);
     for (int k = k0; k <= k1; k++) {
         T fx = T(0), upper = T(0);
-        const T fy = fast_flux<T, N, FAST, WHICH, 1>(pq, pv, g, k);
+        const T fy = fast_flux<T, N, FAST, WHICH, 1, STR>(pq, pv, g, k);
         if (full_row) {
-            fx = fast_flux<T, N, FAST, WHICH, 0>(pq, pu, g, k);
-            upper = fast_flux<T, N, FAST, WHICH, 2>(pq + g.sz, pw + g.sz, g, k + 1);
+            fx = fast_flux<T, N, FAST, WHICH, 0, STR>(pq, pu, g, k);
+            upper = fast_flux<T, N, FAST, WHICH, 2, STR>(pq + g.sz, pw + g.sz, g, k + 1);
         }
         const T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
         const int buf = k & 1;
@@ -230,10 +241,10 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
         __syncthreads();
         if (do_out) {
             const T fy1 = sy_buf[buf][ty + 1][tx];
-            const T Vi = WHICH == 2 ? gg.rVf(k) : gg.rVc(k);
+            const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
             const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower));
             const int eo = i + j * g.sy + k * g.sz;
-            FastTerms<T> F{P, pu, pv, pw, eo, g.sy, g.sz, k};
+            FastTerms<T, STR> F{P, g, pu, pv, pw, eo, k};
             G.p[G.off + eo] = F.template finish<WHICH>(adv, t, pq);
         }
         lower = upper;

@@ -88,10 +88,18 @@ __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __g
     else { k0 = nb + 1 + (kc - 1) * KC; k1 = min(k0 + KC - 1, Nz - nb); }
     if constexpr (S::kind == ADV_WENO) {
         if (fast_path_ok<T, S::n>(P, k0, k1)) {  // CTA-uniform
-            if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC>(P, 0, i, j, k0, k1, sy);
-            else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC>(P, 0, i, j, k0, k1, sy);
-            else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC>(P, 0, i, j, k0, k1, sy);
-            else march_fast_body<T, S::n, FAST, 3, TY, KC>(P, which - 3, i, j, k0, k1, sy);
+            const int t = which - 3;
+            if (P.g.dzc) {
+                if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC, true>(P, 0, i, j, k0, k1, sy);
+                else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC, true>(P, 0, i, j, k0, k1, sy);
+                else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC, true>(P, 0, i, j, k0, k1, sy);
+                else march_fast_body<T, S::n, FAST, 3, TY, KC, true>(P, t, i, j, k0, k1, sy);
+            } else {
+                if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC, false>(P, 0, i, j, k0, k1, sy);
+                else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC, false>(P, 0, i, j, k0, k1, sy);
+                else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC, false>(P, 0, i, j, k0, k1, sy);
+                else march_fast_body<T, S::n, FAST, 3, TY, KC, false>(P, t, i, j, k0, k1, sy);
+            }
             return;
         }
     }
