@@ -109,14 +109,15 @@ __global__ void __launch_bounds__(256) pull_x_to_z_kernel(const __grid_constant_
 
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) eigen_divide_zslab_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
-                                                                 const T *__restrict__ lz, int NxG, int Ny, int nz, int z0, int zero_mode) {
+                                                                 const T *__restrict__ lz, int NxG, int Ny, int nz, int z0, int nlev, int zero_mode) {
     const long n = (long)NxG * Ny * nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int i = (int)(t % NxG), j = (int)((t / NxG) % Ny), k = (int)(t / ((long)NxG * Ny));
     C v = A[t];
-    const T lam = lx[i] + ly[j] + lz[z0 + k];
     C o;
+    if (z0 + k >= nlev) { o.x = 0; o.y = 0; A[t] = o; return; }   // zero padding levels of the half spectrum
+    const T lam = lx[i] + ly[j] + lz[z0 + k];
     if (t == 0 && zero_mode) { o.x = 0; o.y = 0; }
     else { o.x = -v.x / lam; o.y = -v.y / lam; }
     A[t] = o;
@@ -147,6 +148,12 @@ struct DistSolverT : ob_solver {
     bool zx = false;   // x<->z transposition (FFT-based solvers with Nz % R == 0), else y<->x
     cufftHandle plan_xy = 0;
     bool has_xy = false;
+    // zr: periodic z -> real-to-complex transform along z in the slab layout; the half spectrum (Nz/2+1 levels, padded
+    // with zero levels to a multiple of R) is what gets transposed and transformed in (x, y): half the NVLink and HBM bytes
+    bool zr = false;
+    int Nzh = 0, NzT = 0;
+    T *Rr = nullptr;
+    cufftHandle plan_zr2c = 0, plan_zc2r = 0;
     bool use_ipc = false;           // pull transposes through CUDA-IPC peer mappings instead of NCCL send/recv
     ob::PeerPtrs<C> peerS, peerT;
     int *d_bar = nullptr;
@@ -175,11 +182,21 @@ struct DistSolverT : ob_solver {
         if (topo[2] == OB_FLAT) return fail(OB_ERR_UNSUPPORTED, "distributed solver: Flat z");
         tridiag = g->dzf_host != nullptr;
         zx = !tridiag && (N[2] % R == 0) && !getenv("OB_DIST_FORCE_YX");
-        if (!zx && N[1] % R) return fail(OB_ERR_INVALID, "distributed solver: Ny = %d (or Nz = %d) must be divisible by the number of ranks %d", N[1], N[2], R);
+        const bool zr_possible = !tridiag && g->topology[2] == OB_PERIODIC && N[2] > 1 && !getenv("OB_DIST_FORCE_YX") && !getenv("OB_SOLVER_NO_R2C");
+        if (!zx && !zr_possible && N[1] % R) return fail(OB_ERR_INVALID, "distributed solver: Ny = %d (or Nz = %d) must be divisible by the number of ranks %d", N[1], N[2], R);
+        zr = !tridiag && topo[2] == OB_PERIODIC && N[2] > 1 && !getenv("OB_DIST_FORCE_YX") && !getenv("OB_SOLVER_NO_R2C");
+        if (zr) zx = true;
+        Nzh = N[2] / 2 + 1;
+        NzT = zr ? R * ((Nzh + R - 1) / R) : N[2];   // levels held by the complex slab storage
         ny = zx ? N[1] : N[1] / R;
-        nz = zx ? N[2] / R : N[2];
-        const long n = (long)nx * N[1] * N[2];
+        nz = zx ? NzT / R : N[2];
+        const long n = (long)nx * N[1] * NzT;
         for (C **p : {&S, &Tt, &buf_a, &buf_b}) { CUDA_TRY(cudaMalloc(p, sizeof(C) * n)); CUDA_TRY(cudaMemsetAsync(*p, 0, sizeof(C) * n, ctx->stream)); }
+        if (zr) {
+            const long nr = (long)nx * N[1] * N[2];
+            CUDA_TRY(cudaMalloc(&Rr, sizeof(T) * nr));
+            CUDA_TRY(cudaMemsetAsync(Rr, 0, sizeof(T) * nr, ctx->stream));
+        }
         // eigenvalues with the GLOBAL x extent (poisson_eigenvalues.jl:8-32)
         const int Ng[3] = {NxG, N[1], N[2]};
         const double Lg[3] = {L[0] * R, L[1], L[2]};
@@ -199,9 +216,19 @@ struct DistSolverT : ob_solver {
         if (z_fft) scale_ /= N[2];
         if (zx) {
             int nzz[1] = {N[2]};   // z in the slab layout: stride nx*Ny, contiguous batch nx*Ny
-            CUFFT_TRY(cufftPlanMany(&plan_z, 1, nzz, nzz, nx * N[1], 1, nzz, nx * N[1], 1, CT, nx * N[1]));
-            CUFFT_TRY(cufftSetStream(plan_z, ctx->stream));
-            has_z = true;
+            if (zr) {
+                constexpr cufftType FWD = std::is_same<T, double>::value ? CUFFT_D2Z : CUFFT_R2C;
+                constexpr cufftType BWD = std::is_same<T, double>::value ? CUFFT_Z2D : CUFFT_C2R;
+                int nre[1] = {N[2]}, nco[1] = {Nzh};
+                CUFFT_TRY(cufftPlanMany(&plan_zr2c, 1, nzz, nre, nx * N[1], 1, nco, nx * N[1], 1, FWD, nx * N[1]));
+                CUFFT_TRY(cufftPlanMany(&plan_zc2r, 1, nzz, nco, nx * N[1], 1, nre, nx * N[1], 1, BWD, nx * N[1]));
+                CUFFT_TRY(cufftSetStream(plan_zr2c, ctx->stream));
+                CUFFT_TRY(cufftSetStream(plan_zc2r, ctx->stream));
+            } else {
+                CUFFT_TRY(cufftPlanMany(&plan_z, 1, nzz, nzz, nx * N[1], 1, nzz, nx * N[1], 1, CT, nx * N[1]));
+                CUFFT_TRY(cufftSetStream(plan_z, ctx->stream));
+                has_z = true;
+            }
             int nn[2] = {N[1], NxG};   // (x, y) in the z-local layout: contiguous, batched over the local levels
             CUFFT_TRY(cufftPlanMany(&plan_xy, 2, nn, nullptr, 1, NxG * N[1], nullptr, 1, NxG * N[1], CT, nz));
             CUFFT_TRY(cufftSetStream(plan_xy, ctx->stream));
@@ -328,9 +355,11 @@ struct DistSolverT : ob_solver {
         if (has_z) cufftDestroy(plan_z);
         if (has_x) cufftDestroy(plan_x);
         if (has_xy) cufftDestroy(plan_xy);
+        if (zr) { cufftDestroy(plan_zr2c); cufftDestroy(plan_zc2r); cudaFree(Rr); }
     }
-    void *storage() override { return S; }
+    void *storage() override { return zr ? (void *)Rr : (void *)S; }
     double scale() override { return scale_; }
+    bool real_storage() const override { return zr; }
 
     // all-to-all of per-peer chunks (nccl_transpose.jl:47-75: grouped Send/Recv, complex as 2 x real)
     int32_t alltoall(const C *send, C *recv) {
@@ -354,7 +383,7 @@ struct DistSolverT : ob_solver {
         return OB_OK;
     }
     int32_t solve_in_storage() override {
-        const long n = (long)nx * N[1] * N[2];
+        const long n = (long)nx * N[1] * NzT;
         const unsigned nb = nblk(n, 256);
         cudaStream_t st = ctx->stream;
         const bool z_dct = !tridiag && topo[2] == OB_BOUNDED;
@@ -365,22 +394,26 @@ struct DistSolverT : ob_solver {
                 OB_TRY(exec(plan_z, buf_a, CUFFT_FORWARD));
                 twiddle_fwd_kernel<T, C><<<nb, 256, 0, st>>>(buf_a, S, tw_f, nx, N[1], N[2], 2);
                 launches += 2;
+            } else if (zr) {
+                launches++;
+                if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecD2Z(plan_zr2c, Rr, S));
+                else CUFFT_TRY(cufftExecR2C(plan_zr2c, Rr, S));
             } else {
                 OB_TRY(exec(plan_z, S, CUFFT_FORWARD));
             }
             if (use_ipc) {
                 OB_TRY(barrier());        // every peer's z transform is complete
-                pull_z_to_x_kernel<C><<<nb, 256, 0, st>>>(peerS, Tt, nx, NxG, N[1], nz, N[2], rank);
+                pull_z_to_x_kernel<C><<<nb, 256, 0, st>>>(peerS, Tt, nx, NxG, N[1], nz, NzT, rank);
             } else {
                 OB_TRY(alltoall(S, buf_b));   // chunks are contiguous in S: no pack
                 unpack_z_to_x_kernel<C><<<nb, 256, 0, st>>>(buf_b, Tt, nx, NxG, N[1], nz);
             }
             OB_TRY(exec(plan_xy, Tt, CUFFT_FORWARD));
-            eigen_divide_zslab_kernel<T, C><<<nb, 256, 0, st>>>(Tt, lam[0], lam[1], lam[2], NxG, N[1], nz, rank * nz, rank == 0 ? 1 : 0);
+            eigen_divide_zslab_kernel<T, C><<<nb, 256, 0, st>>>(Tt, lam[0], lam[1], lam[2], NxG, N[1], nz, rank * nz, zr ? Nzh : N[2], rank == 0 ? 1 : 0);
             OB_TRY(exec(plan_xy, Tt, CUFFT_INVERSE));
             if (use_ipc) {
                 OB_TRY(barrier());        // every peer's inverse (x, y) transform is complete (and its forward pull long done)
-                pull_x_to_z_kernel<C><<<nb, 256, 0, st>>>(peerT, S, nx, NxG, N[1], nz, N[2], rank);
+                pull_x_to_z_kernel<C><<<nb, 256, 0, st>>>(peerT, S, nx, NxG, N[1], nz, NzT, rank);
             } else {
                 pack_x_to_z_kernel<C><<<nb, 256, 0, st>>>(Tt, buf_a, nx, NxG, N[1], nz);
                 OB_TRY(alltoall(buf_a, S));   // received chunks land contiguously in S: no unpack
@@ -391,6 +424,10 @@ struct DistSolverT : ob_solver {
                 OB_TRY(exec(plan_z, buf_a, CUFFT_INVERSE));
                 unpermute_kernel<C><<<nb, 256, 0, st>>>(buf_a, S, nx, N[1], N[2], 2);
                 launches += 2;
+            } else if (zr) {
+                launches++;
+                if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2D(plan_zc2r, S, Rr));
+                else CUFFT_TRY(cufftExecC2R(plan_zc2r, S, Rr));
             } else {
                 OB_TRY(exec(plan_z, S, CUFFT_INVERSE));
             }
