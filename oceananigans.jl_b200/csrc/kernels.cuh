@@ -112,6 +112,58 @@ __global__ void __launch_bounds__(256) xhalo_unpack_kernel(const __grid_constant
     q[B.N + B.H + h] = recv_e[t.offset + tid];   // east halo <- east neighbour's west interior slab
 }
 
+// Peer-to-peer form of the same exchange (NVLink, CUDA-IPC mapped peer buffers; no NCCL on the data path):
+//   push:   every rank stores its west / east interior slabs DIRECTLY into the staging buffer of its west / east
+//           neighbour, then -- once the last block has finished (system-scope fences + a block counter) -- publishes the
+//           exchange's epoch number into the neighbour's flag with a release store;
+//   unpack: waits (acquire loads) until both of its own flags carry the epoch, then copies the staged slabs into the halos.
+// Staging buffers and flags are double-buffered by epoch parity: a neighbour can never be more than one exchange ahead,
+// because its next unpack needs this rank's next push, which is stream-ordered after this rank's current unpack.
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int *p) { int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+template <typename T>
+__global__ void __launch_bounds__(256) xhalo_push_kernel(const __grid_constant__ XHaloBatch<T> B, T *__restrict__ west_nbr_recv_e,
+                                                         T *__restrict__ east_nbr_recv_w, int *west_nbr_flag_e, int *east_nbr_flag_w,
+                                                         unsigned *block_counter, int epoch) {
+    const XHaloTask<T> &t = B.t[blockIdx.y];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < t.rows * B.H) {
+        const int h = (int)(tid % B.H);
+        const long row = tid / B.H;
+        const T *q = t.p + row * t.Px;
+        west_nbr_recv_e[t.offset + tid] = q[B.H + h];   // my west interior slab -> west neighbour's east halo
+        east_nbr_recv_w[t.offset + tid] = q[B.N + h];   // my east interior slab -> east neighbour's west halo
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(block_counter, 1u) == total - 1) {
+            *block_counter = 0;
+            __threadfence_system();
+            st_release_sys(west_nbr_flag_e, epoch);
+            st_release_sys(east_nbr_flag_w, epoch);
+        }
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) xhalo_wait_unpack_kernel(const __grid_constant__ XHaloBatch<T> B, const T *__restrict__ recv_w,
+                                                                const T *__restrict__ recv_e, const int *flag_w, const int *flag_e, int epoch) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_sys(flag_w) < epoch) {}
+        while (ld_acquire_sys(flag_e) < epoch) {}
+    }
+    __syncthreads();
+    const XHaloTask<T> &t = B.t[blockIdx.y];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= t.rows * B.H) return;
+    const int h = (int)(tid % B.H);
+    const long row = tid / B.H;
+    T *q = t.p + row * t.Px;
+    q[h] = __ldcv(recv_w + t.offset + tid);
+    q[B.N + B.H + h] = __ldcv(recv_e + t.offset + tid);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K7: constant-flux boundary contributions (compute_flux_bcs.jl:113-162): Gc[1] += flux*A/V ; Gc[N] -= flux*A/V
 // ------------------------------------------------------------------------------------------------------------

@@ -588,10 +588,23 @@ struct ModelT : ob_model {
     bool dist = false;
     T *d_halo_buf = nullptr;
     size_t halo_buf_elems = 0;
+    // peer-to-peer halo exchange state (CUDA IPC): staging [parity][side(w,e)][cap] + flags [parity][side]
+    bool p2p_halo = false;
+    T *d_stage = nullptr; int *d_flags = nullptr; unsigned *d_blockctr = nullptr;
+    T *west_stage = nullptr, *east_stage = nullptr; int *west_flags = nullptr, *east_flags = nullptr;
+    size_t stage_cap = 0;
+    int halo_epoch = 0;
 
     ~ModelT() override {
         cudaFree(d_dzf); cudaFree(d_dzc); cudaFree(d_partial);
         cudaFree(d_rdzf); cudaFree(d_rdzc); cudaFree(d_rvf); cudaFree(d_rvc); cudaFree(d_halo_buf);
+        if (p2p_halo) {
+            cudaStreamSynchronize(ctx->stream);
+            const int R = ctx->world, west = (ctx->rank + R - 1) % R, east = (ctx->rank + 1) % R;
+            cudaIpcCloseMemHandle(west_stage); cudaIpcCloseMemHandle(west_flags);
+            if (east != west) { cudaIpcCloseMemHandle(east_stage); cudaIpcCloseMemHandle(east_flags); }
+        }
+        cudaFree(d_stage); cudaFree(d_flags); cudaFree(d_blockctr);
         delete solver;
         for (auto e : pool) cudaEventDestroy(e);
     }
@@ -696,6 +709,7 @@ struct ModelT : ob_model {
         OB_TRY(make_solver<T>(ctx, &d->grid, &solver));
         dist = ctx->world > 1;
         if (dist && g.topo[0] != PERIODIC) return fail(OB_ERR_UNSUPPORTED, "slab-x distributed models need a Periodic x");
+        if (dist && !getenv("OB_DIST_NO_IPC")) OB_TRY(setup_p2p_halo());
         return OB_OK;
     }
 
@@ -765,6 +779,64 @@ struct ModelT : ob_model {
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
+    // staging buffers large enough for every field of the model in one exchange; handles all-gathered over NCCL
+    int32_t setup_p2p_halo() {
+        size_t cap = 0;
+        for (int id = 0; id < 128; id++) if (F[id].exists) cap += (size_t)g.H[0] * F[id].P[1] * F[id].P[2];
+        stage_cap = cap;
+        CUDA_TRY(cudaMalloc(&d_stage, sizeof(T) * 4 * cap));
+        CUDA_TRY(cudaMalloc(&d_flags, sizeof(int) * 4));
+        CUDA_TRY(cudaMalloc(&d_blockctr, sizeof(unsigned)));
+        CUDA_TRY(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(d_blockctr, 0, sizeof(unsigned), ctx->stream));
+        struct Pair { cudaIpcMemHandle_t s, f; };
+        Pair mine;
+        const int R = ctx->world, rank = ctx->rank, west = (rank + R - 1) % R, east = (rank + 1) % R;
+        int ok = 1;
+        if (cudaIpcGetMemHandle(&mine.s, d_stage) != cudaSuccess || cudaIpcGetMemHandle(&mine.f, d_flags) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&mine, 0, sizeof(mine)); }
+        Pair *d_all = nullptr;
+        CUDA_TRY(cudaMalloc(&d_all, sizeof(Pair) * R));
+        CUDA_TRY(cudaMemcpyAsync(d_all + rank, &mine, sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ncclAllGather(d_all + rank, d_all, sizeof(Pair), ncclChar, (ncclComm_t)ctx->comm, ctx->stream));
+        std::vector<Pair> all(R);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(Pair) * R, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_all);
+        if (ok) {
+            void *ps = nullptr, *pf = nullptr;
+            if (cudaIpcOpenMemHandle(&ps, all[west].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&pf, all[west].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            west_stage = (T *)ps; west_flags = (int *)pf;
+            if (ok && east != west) {
+                if (cudaIpcOpenMemHandle(&ps, all[east].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&pf, all[east].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+                east_stage = (T *)ps; east_flags = (int *)pf;
+            } else if (ok) { east_stage = west_stage; east_flags = west_flags; }
+        }
+        int *d_ok = nullptr;   // every rank must take the same path
+        CUDA_TRY(cudaMalloc(&d_ok, sizeof(int)));
+        CUDA_TRY(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_ok);
+        p2p_halo = ok != 0;
+        return OB_OK;
+    }
+    int32_t exchange_x_halos_p2p(const XHaloBatch<T> &B, size_t total, long maxrows) {
+        if (total > stage_cap) return fail(OB_ERR_INVALID, "halo staging buffer too small");
+        const int epoch = ++halo_epoch, par = epoch & 1;
+        // layout: stage[(par*2 + side)*cap], side 0 = west halo data, 1 = east halo data ; flags[par*2 + side]
+        auto stage = [&](T *base, int side) { return base + (size_t)(par * 2 + side) * stage_cap; };
+        dim3 grid(nblk(maxrows * g.H[0], 256), B.count);
+        xhalo_push_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, stage(west_stage, 1), stage(east_stage, 0), west_flags + par * 2 + 1,
+                                                            east_flags + par * 2 + 0, d_blockctr, epoch);
+        xhalo_wait_unpack_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, stage(d_stage, 0), stage(d_stage, 1), d_flags + par * 2 + 0,
+                                                                   d_flags + par * 2 + 1, epoch);
+        launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
     // Distributed west/east halos (halo_communication.jl:96-203; nccl_distributed.jl:209-246): ONE pack launch, one
     // grouped Send/Recv pair per side carrying every field of the batch, ONE unpack launch.  Slabs span the full
     // parent extent in y and z (OneDBuffer, communication_buffers.jl:96-114), so corners stay consistent exactly as
@@ -783,6 +855,11 @@ struct ModelT : ob_model {
             total += (size_t)g.H[0] * t.rows;
         }
         if (B.count == 0) return OB_OK;
+        if (p2p_halo) {
+            long mr = 0;
+            for (int q = 0; q < B.count; q++) mr = std::max(mr, B.t[q].rows);
+            return exchange_x_halos_p2p(B, total, mr);
+        }
         if (4 * total > halo_buf_elems) {
             cudaFree(d_halo_buf);
             CUDA_TRY(cudaMalloc(&d_halo_buf, sizeof(T) * 4 * total));
