@@ -184,6 +184,8 @@ int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first);
 /* implementation options (testing / profiling): OB_OPT_TENDENCY_KERNEL = 0 auto, 1 generic one-thread-per-cell kernel,
  * 2 flux-sharing marching kernel */
 #define OB_OPT_TENDENCY_KERNEL 1
+/* OB_OPT_FUSE_PROJECTION = 1 (default): single-device substeps fuse real-copy + correction + p rescale; 0: reference kernel sequence */
+#define OB_OPT_FUSE_PROJECTION 2
 int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t value);
 /* number of kernels/library launches issued by this model so far (bench.py's gpu_launches) */
 int32_t ob_launch_count(ob_model *m, int64_t *n);

@@ -352,6 +352,36 @@ __global__ void __launch_bounds__(256) pressure_correct_kernel(const __grid_cons
     if (P.g.topo[2] != FLAT) P.w(i, j, k) -= (pc - P.p.ld(i, j, k - 1)) * P.g.rdzF(k);
 }
 
+// K15 + K16 + rescale fused (single-device path of rk3_substep! / ab2_step!): reads the solver output directly,
+// p = real(ϕ)·scale (copy_real_component!), u -= ∂x p etc. (make_pressure_correction!), then stores p / Δτ -- the same
+// values, in the same order of operations, as the three separate reference kernels; the halo cells of p that the
+// correction needs are resolved by index (periodic wrap / no-flux mirror) instead of a halo fill in between.
+template <typename T>
+struct CorrectFusedP {
+    GridD<T> g;
+    Fld<T> u, v, w, p;
+    const T *sol;
+    long ldx, ldxy;
+    int cplx;
+    T scale, denom;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) correct_fused_kernel(const __grid_constant__ CorrectFusedP<T> P) {
+    int i, j, k;
+    if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
+    auto S = [&](int a, int b, int c) -> T {
+        const long o = (a - 1) + (b - 1) * P.ldx + (long)(c - 1) * P.ldxy;
+        return mul_rn(P.cplx ? __ldg(P.sol + 2 * o) : __ldg(P.sol + o), P.scale);   // rounded like the stored p of the reference
+    };
+    // index of the lower neighbour along d: periodic wrap, or the cell itself where the no-flux halo mirrors it
+    auto lower = [&](int idx, int d) { return idx > 1 ? idx - 1 : (P.g.topo[d] == PERIODIC ? P.g.N[d] : 1); };
+    const T pc = S(i, j, k);
+    if (P.g.topo[0] != FLAT) P.u(i, j, k) -= sub_rn(pc, S(lower(i, 0), j, k)) * P.g.rdx;
+    if (P.g.topo[1] != FLAT) P.v(i, j, k) -= sub_rn(pc, S(i, lower(j, 1), k)) * P.g.rdy;
+    if (P.g.topo[2] != FLAT) P.w(i, j, k) -= sub_rn(pc, S(i, j, lower(k, 2))) * P.g.rdzF(k);
+    P.p(i, j, k) = pc / P.denom;
+}
+
 // pNHS ./= Δt over the whole parent array (pressure_correction.jl:101-103)
 template <typename T>
 __global__ void scale_kernel(T *p, long n, T denom) {

@@ -524,6 +524,7 @@ struct ob_model {
     int64_t launches = 0;
     bool timing = false;
     int opt_tendency_kernel = 0;  // OB_OPT_TENDENCY_KERNEL: 0 auto, 1 generic (one thread per cell), 2 marching
+    int opt_fuse = 1;             // OB_OPT_FUSE_PROJECTION: 1 fused single-device projection, 0 the reference kernel sequence
     double phase_ms[PH_COUNT] = {0};
     int64_t phase_calls[PH_COUNT] = {0};
     struct Ev { int phase; cudaEvent_t a, b; };
@@ -1011,6 +1012,7 @@ struct ModelT : ob_model {
             }
         return OB_OK;
     }
+    bool fused_substep() const { return !dist && opt_fuse != 0; }
     int32_t launch_update(int mode, double dt, double gamma, double zeta, double chi, bool cache) {
         PhaseScope ps(this, PH_UPDATE);
         OB_TRY(flux_bc_tendencies());
@@ -1033,21 +1035,65 @@ struct ModelT : ob_model {
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
+    // compute_pressure_correction! + make_pressure_correction! of one substep.  Single device: the real-part copy, the
+    // correction and the p rescale are ONE kernel reading the solver output (correct_fused_kernel); distributed: the
+    // reference sequence (the x neighbours of p live on other ranks and arrive through the halo exchange).
+    int32_t project(double dtau) {
+        if (!fused_substep()) {
+            OB_TRY(compute_pressure_correction(dtau));
+            return make_pressure_correction(dtau);
+        }
+        OB_TRY(fill_halos({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W}, true));
+        const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
+        dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], 1);
+        {
+            PhaseScope ps(this, PH_SOURCE);
+            SourceP<T> P;
+            memset(&P, 0, sizeof(P));
+            P.g = g; P.u = fld(OB_FIELD_U); P.v = fld(OB_FIELD_V); P.w = fld(OB_FIELD_W);
+            P.out = (T *)solver->storage();
+            P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
+            P.times_dz = solver->tridiag ? 1 : 0;
+            P.cplx = solver->real_storage() ? 0 : 1;
+            source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            launches++;
+        }
+        {
+            PhaseScope ps(this, PH_SOLVE);
+            int64_t before = solver->launches;
+            OB_TRY(solver->solve_in_storage());
+            launches += solver->launches - before;
+        }
+        {
+            PhaseScope ps(this, PH_CORRECT);
+            CorrectFusedP<T> P;
+            memset(&P, 0, sizeof(P));
+            P.g = g; P.u = fld(OB_FIELD_U); P.v = fld(OB_FIELD_V); P.w = fld(OB_FIELD_W); P.p = fld(OB_FIELD_PNHS);
+            P.sol = (const T *)solver->storage();
+            P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
+            P.cplx = solver->real_storage() ? 0 : 1;
+            P.scale = (T)solver->scale();
+            P.denom = std::max(std::numeric_limits<T>::epsilon(), (T)dtau);
+            correct_fused_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            launches++;
+        }
+        OB_TRY(fill_halos({OB_FIELD_PNHS}, true));   // halos of the final p: copies of interior values, as after the reference's rescale
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
     int32_t rk3_substep(double dt, double gamma, double zeta, int has_zeta, bool cache) override {
         OB_TRY(need_all());
         OB_TRY(launch_update(has_zeta ? 1 : 0, dt, gamma, zeta, 0, cache));
         // Δτ = convert(FT, Δt * (γ + ζ)) with γ, ζ of the grid float type (runge_kutta_3.jl:186-187)
         T gz = has_zeta ? (T)((T)gamma + (T)zeta) : (T)gamma;
         double dtau = (double)(T)(dt * (double)gz);
-        OB_TRY(compute_pressure_correction(dtau));
-        return make_pressure_correction(dtau);
+        return project(dtau);
     }
     int32_t ab2_step(double dt, double chi, bool cache) override {
         OB_TRY(need_all());
         OB_TRY(launch_update(2, dt, 0, 0, chi, cache));
         double dtau = (double)(T)dt;
-        OB_TRY(compute_pressure_correction(dtau));
-        return make_pressure_correction(dtau);
+        return project(dtau);
     }
     int32_t cache_tendencies() override {
         OB_TRY(need_all());
@@ -1186,6 +1232,7 @@ extern "C" int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t valu
     if (!m) return fail(OB_ERR_INVALID, "null model");
     switch (option) {
         case OB_OPT_TENDENCY_KERNEL: m->opt_tendency_kernel = value; return OB_OK;
+        case OB_OPT_FUSE_PROJECTION: m->opt_fuse = value; return OB_OK;
     }
     return fail(OB_ERR_INVALID, "unknown option %d", option);
 }

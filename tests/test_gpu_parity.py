@@ -206,3 +206,22 @@ def test_fine_grained_entry_points_equal_fused_step(arch):
     f1, f2 = b200_fields(m1), b200_fields(m2)
     for n in f1:
         assert np.array_equal(f1[n], f2[n]), n
+
+
+@pytest.mark.parametrize("name", ["ppp_weno5", "les_amd", "stretched", "lilly_bbb", "readme_2d"])
+def test_fused_projection_is_bit_identical_to_reference_sequence(arch, name):
+    """the fused single-device projection (real copy + correction + p rescale in one kernel) reproduces the reference
+    kernel sequence bit for bit, halos of pNHS included"""
+    import ocean_b200 as ob
+    from ocean_b200 import _abi
+    cfg = CONFIGS[name]
+    ic = cfg.initial_conditions(13)
+    m1, m2 = cfg.b200_model(arch), cfg.b200_model(arch)
+    m2.set_option(_abi.OB_OPT_FUSE_PROJECTION, 0)
+    ob.set(m1, **ic); ob.set(m2, **ic)
+    dt = 1e-3 if name in ("ppp_weno5", "readme_2d", "lilly_bbb") else 0.5
+    for _ in range(2):
+        ob.time_step(m1, dt); ob.time_step(m2, dt)
+    f1, f2 = b200_fields(m1), b200_fields(m2)
+    for n in f1:
+        assert np.array_equal(f1[n], f2[n]), n
