@@ -77,11 +77,18 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<
     const GridD<T> &g = P.g;
     const ClosureD<T> &cl = P.cl[m];
     const int ox = g.topo[0] == FLAT ? 0 : 1;
-    // fields may differ in their strides (Face fields on Bounded directions): per-field accessors with relative offsets
-    auto at = [&](const Fld<T> &f, int a, int b, int c) -> T {
-        const long oy = g.topo[1] == FLAT ? 0 : f.sy, oz = g.topo[2] == FLAT ? 0 : f.sz;
-        return __ldg(f.p + (f.off + i + (long)j * f.sy + (long)k * f.sz + a * ox + b * oy + c * oz));
+    // fields may differ in their strides (Face fields on Bounded directions): one base pointer per field, then 32-bit
+    // relative offsets (a, b, c are compile-time after unrolling)
+    struct Cur { const T *p; int oy, oz; };
+    auto cur = [&](const Fld<T> &f) {
+        Cur c;
+        c.p = f.p + (f.off + i + (long)j * f.sy + (long)k * f.sz);
+        c.oy = g.topo[1] == FLAT ? 0 : f.sy;
+        c.oz = g.topo[2] == FLAT ? 0 : (int)f.sz;
+        return c;
     };
+    const Cur cu = cur(P.u), cv = cur(P.v), cw = cur(P.w);
+    auto at = [&](const Cur &f, int a, int b, int c) -> T { return __ldg(f.p + (a * ox + b * f.oy + c * f.oz)); };
     const T rdx = g.rdx, rdy = g.rdy;
     const T fx = 2 * g.dx, fy = 2 * g.dy;
     T fz[2], rdzf[2];
@@ -93,23 +100,23 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<
     for (int c = 0; c < 2; c++) { rxz[c] = fx / fz[c]; rzx[c] = fz[c] / fx; ryz[c] = fy / fz[c]; rzy[c] = fz[c] / fy; }
     const T delta2 = 3 / (1 / (fx * fx) + 1 / (fy * fy) + 1 / (fz[0] * fz[0]));
     // ccc
-    const T ux = (at(P.u, 1, 0, 0) - at(P.u, 0, 0, 0)) * rdx;
-    const T vy = (at(P.v, 0, 1, 0) - at(P.v, 0, 0, 0)) * rdy;
-    const T wz = (at(P.w, 0, 0, 1) - at(P.w, 0, 0, 0)) * g.rdzC(k);
+    const T ux = (at(cu, 1, 0, 0) - at(cu, 0, 0, 0)) * rdx;
+    const T vy = (at(cv, 0, 1, 0) - at(cv, 0, 0, 0)) * rdy;
+    const T wz = (at(cw, 0, 0, 1) - at(cw, 0, 0, 0)) * g.rdzC(k);
     // ffc [a][b], fcf [a][c], cff [b][c]
     T xv[2][2], yu[2][2], xw[2][2], zu[2][2], yw[2][2], zv[2][2], s12[2][2], s13[2][2], s23[2][2];
 #pragma unroll
     for (int q = 0; q < 2; q++)
 #pragma unroll
         for (int p = 0; p < 2; p++) {
-            xv[p][q] = rxy * ((at(P.v, p, q, 0) - at(P.v, p - 1, q, 0)) * rdx);
-            yu[p][q] = ryx * ((at(P.u, p, q, 0) - at(P.u, p, q - 1, 0)) * rdy);
+            xv[p][q] = rxy * ((at(cv, p, q, 0) - at(cv, p - 1, q, 0)) * rdx);
+            yu[p][q] = ryx * ((at(cu, p, q, 0) - at(cu, p, q - 1, 0)) * rdy);
             s12[p][q] = T(0.5) * (yu[p][q] + xv[p][q]);
-            xw[p][q] = rxz[q] * ((at(P.w, p, 0, q) - at(P.w, p - 1, 0, q)) * rdx);
-            zu[p][q] = rzx[q] * ((at(P.u, p, 0, q) - at(P.u, p, 0, q - 1)) * rdzf[q]);
+            xw[p][q] = rxz[q] * ((at(cw, p, 0, q) - at(cw, p - 1, 0, q)) * rdx);
+            zu[p][q] = rzx[q] * ((at(cu, p, 0, q) - at(cu, p, 0, q - 1)) * rdzf[q]);
             s13[p][q] = T(0.5) * (zu[p][q] + xw[p][q]);
-            yw[p][q] = ryz[q] * ((at(P.w, 0, p, q) - at(P.w, 0, p - 1, q)) * rdy);
-            zv[p][q] = rzy[q] * ((at(P.v, 0, p, q) - at(P.v, 0, p, q - 1)) * rdzf[q]);
+            yw[p][q] = ryz[q] * ((at(cw, 0, p, q) - at(cw, 0, p - 1, q)) * rdy);
+            zv[p][q] = rzy[q] * ((at(cv, 0, p, q) - at(cv, 0, p, q - 1)) * rdzf[q]);
             s23[p][q] = T(0.5) * (zv[p][q] + yw[p][q]);
         }
     auto I = [&](auto fn) {  // interp4 of a pointwise expression fn(p, q)
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<
         P.nue[m](i, j, k) = fmax(T(0), nu);
     }
     for (int t = 0; t < P.ntr; t++) {
-        const Fld<T> &c = P.c[t];
+        const Cur c = cur(P.c[t]);
         T xc[2], yc[2], zc[2];
 #pragma unroll
         for (int p = 0; p < 2; p++) {
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<
 #pragma unroll
             for (int q = 0; q < 2; q++)
 #pragma unroll
-                for (int p = 0; p < 2; p++) yw_xz[p][q] = ryz[q] * ((at(P.w, p, 0, q) - at(P.w, p, -1, q)) * rdy);
+                for (int p = 0; p < 2; p++) yw_xz[p][q] = ryz[q] * ((at(cw, p, 0, q) - at(cw, p, -1, q)) * rdy);
             const T cx = ux * icx2 + I_xv * icx * icy + I_xw * icx * icz;
             const T cy = I_yu * icy * icx + vy * icy2 + interp4<T>(yw_xz) * icy * icz;
             const T cz = I_zu * icz * icx + I_zv * icz * icy + wz * icz2;

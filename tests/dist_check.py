@@ -85,6 +85,31 @@ for name, (cfg, dt) in CASES.items():
         print("%s: ranks=%d  worst rel-L2 after set! %.2e, after 3 steps %.2e" % (name, world, w0, w3), flush=True)
     del dm, sm, solo
 
+# distributed Poisson solvers against the single-GPU solvers (test_distributed_poisson_solvers.jl:31-135), and the
+# transposes they are built from: identical up to the rounding of a different transform order
+for name, cfg in {"fft_ppp": Config((32, 16, 24), ((0, 1.0), (0, 2.0), (0, 3.0)), "PPP"),
+                  "fft_ppb": Config((32, 16, 24), ((0, 1.0), (0, 2.0), (0, 3.0)), "PPB"),
+                  "fft_ppp_odd_levels": Config((32, 16, 18), ((0, 1.0), (0, 2.0), (0, 3.0)), "PPP"),
+                  "tridiagonal": Config((32, 16, 12), ((0, 1.0), (0, 2.0), stretched_faces(12, 3.0)), "PPB")}.items():
+    dg, sg = cfg.b200_grid(arch), cfg.b200_grid(ob.B200(local))
+    cls = ob.FourierTridiagonalPoissonSolver if name == "tridiagonal" else ob.FFTBasedPoissonSolver
+    ds, ss = cls(dg), cls(sg)
+    rhs = np.random.default_rng(5).standard_normal(cfg.size[::-1])
+    rhs -= rhs.mean()
+    n = cfg.size[0] // world
+    a = ob.solve(ds, np.ascontiguousarray(rhs[:, :, rank * n:(rank + 1) * n]))
+    b = ob.solve(ss, rhs)[:, :, rank * n:(rank + 1) * n]
+    err = rel_l2(a - a.mean() * 0, b)
+    if name == "tridiagonal":   # the solution is defined up to the (removed) mean: compare mean-free parts
+        full = ob.gather_x(arch, a)
+        err = rel_l2(a - full.mean(), b - ob.solve(ss, rhs).mean())
+    if not err <= 1e-11:
+        ok = False
+        print("[rank %d] distributed Poisson solver %s: rel-L2 %.3e" % (rank, name, err), flush=True)
+    elif rank == 0:
+        print("poisson %s: rel-L2 vs single GPU %.2e" % (name, err), flush=True)
+    del ds, ss
+
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.barrier()
