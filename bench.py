@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is --size x size x size whatever N (default: weak, size^3 per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -159,13 +160,14 @@ def main():
         arch = ob.B200(local)
     ft = np.float32 if args.f32 else np.float64
     n = args.size
-    cfg = workload_config(n, ft=ft, nx=n * world)
+    cfg = workload_config(n, ft=ft, nx=n if args.strong else n * world)
+    nx_local = n // world if args.strong else n
     model = cfg.b200_model(arch)
     ic = cfg.initial_conditions(2)
     if world > 1:
-        ic = {k: v[:, :, rank * n:(rank + 1) * n] for k, v in ic.items()}
+        ic = {k: v[:, :, rank * nx_local:(rank + 1) * nx_local] for k, v in ic.items()}
     ob.set(model, **ic)
-    cells_local = n ** 3
+    cells_local = nx_local * n * n
     cells_total = cells_local * world
 
     def barrier():
@@ -239,6 +241,21 @@ def main():
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "note": "Float64 WENO-5 is FP64-issue bound on B200, not HBM bound (DESIGN.md §roofline)"}
+    # second roofline of the same kernel: FP64 issue.  FP64 thread-instructions per cell come from the committed ncu capture
+    # (profiles/tendency_traffic.json: DFMA+DMUL+DADD executed / cells, tile-overlap lanes included); the peak is measured
+    # live with a DFMA microbenchmark (ob_fp64_peak).
+    if roofline is not None and not args.f32:
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "tendency_traffic.json")))
+            per_cell = tj.get("fp64_instructions_per_cell")
+            pk = C.c_double(0)
+            _abi.call("ob_fp64_peak", arch.ctx, C.byref(pk))
+            if per_cell:
+                ach = per_cell * cells_local / (roofline["avg_launch_ms"] * 1e-3)
+                roofline["fp64_issue"] = {"achieved": ach / 1e12, "peak": pk.value / 1e12, "unit": "T thread-instr/s", "frac": ach / pk.value,
+                                          "fp64_instructions_per_cell": per_cell, "peak_source": "measured DFMA microbenchmark (ob_fp64_peak)"}
+        except Exception:
+            pass
     step_bytes = 1440 * cells_local * (wsize / 8.0)  # ≈ 1.44 KB/cell/RK3 step
     step_roof = {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": step_bytes}
@@ -280,10 +297,10 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                 "dtype": "f32" if args.f32 else "f64", "data": "synthetic",
                 "config": {"workload": "3D triply-periodic NonhydrostaticModel, WENO-5, BuoyancyTracer, ScalarDiffusivity, %dx%dx%d %s "
-                                       "(BASELINE.json configs[1]; %d^3 per GPU, slab-x)" % (n * world, n, n, "Float32" if args.f32 else "Float64", n),
+                                       "(BASELINE.json configs[1]; %dx%dx%d per GPU, slab-x)" % (nx_local * world, n, n, "Float32" if args.f32 else "Float64", nx_local, n, n),
                            "timestepper": "RK3 (3 stages, 3 pressure solves per step)", "dt": DT, "halo": 3,
                            "l2": "inputs larger than L2: every kernel streams >= 4 parent arrays of %.0f MB" % (model.velocities["u"].nbytes / 1e6),
                            "parallelism": "slab-x%d" % world},

@@ -143,6 +143,9 @@ int32_t ob_sync(ob_ctx *ctx);                                         /* Archite
 /* CUDA-event timer on the context's stream: start records, stop records + synchronises and returns milliseconds */
 int32_t ob_timer_start(ob_ctx *ctx);
 int32_t ob_timer_stop(ob_ctx *ctx, double *ms);
+/* measured FP64 FMA issue rate of the device (thread-level instructions per second): the second roofline of the
+ * FP64-bound tendency kernel in bench.py */
+int32_t ob_fp64_peak(ob_ctx *ctx, double *instr_per_s);
 int32_t ob_malloc(ob_ctx *ctx, size_t bytes, void **ptr);             /* Base.zeros(::B200, FT, dims...) */
 int32_t ob_free(ob_ctx *ctx, void *ptr);                              /* finalizer / unsafe_free! */
 int32_t ob_malloc_host(ob_ctx *ctx, size_t bytes, void **ptr);        /* pinned staging buffers */

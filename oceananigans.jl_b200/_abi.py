@@ -76,6 +76,7 @@ _i32, _i64, _dbl, _sz = C.c_int32, C.c_int64, C.c_double, C.c_size_t
 # name -> argtypes (all return int32 status unless listed in _STR)
 PROTOTYPES = {
     "ob_init": [_i32, _PP], "ob_shutdown": [_P], "ob_device_count": [C.POINTER(_i32)], "ob_sync": [_P],
+    "ob_fp64_peak": [_P, C.POINTER(_dbl)],
     "ob_timer_start": [_P], "ob_timer_stop": [_P, C.POINTER(_dbl)],
     "ob_malloc": [_P, _sz, _PP], "ob_free": [_P, _P], "ob_malloc_host": [_P, _sz, _PP], "ob_free_host": [_P, _P],
     "ob_memcpy_h2d": [_P, _P, _P, _sz], "ob_memcpy_d2h": [_P, _P, _P, _sz], "ob_memcpy_d2d": [_P, _P, _P, _sz],

@@ -122,6 +122,35 @@ extern "C" int32_t ob_timer_stop(ob_ctx *ctx, double *ms) {
     *ms = f;
     return OB_OK;
 }
+// FP64 issue-rate microbenchmark (bench.py: the second roofline of the FP64-bound tendency kernel): 8 independent DFMA
+// chains per thread, enough CTAs to fill the device; returns thread-level FP64 instructions per second.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; it++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+extern "C" int32_t ob_fp64_peak(ob_ctx *ctx, double *instr_per_s) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double)));
+    const int iters = 20000, blocks = ctx->sm_count * 8;
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+    fp64_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(d, 100);
+    CUDA_TRY(cudaEventRecord(a, ctx->stream));
+    fp64_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(b, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    *instr_per_s = (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3);
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return OB_OK;
+}
 extern "C" int32_t ob_sync(ob_ctx *ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -2,7 +2,11 @@
 (ocean_b200, through the C ABI), seed both with identical initial conditions, compare fields."""
 import numpy as np
 
-from oracle import model as M
+
+def _oracle():
+    """the CPU oracle is imported lazily: bench.py's GPU arm uses Config without ever touching oracle/"""
+    from oracle import model as M
+    return M
 
 TOPO_CLS = {"P": "Periodic", "B": "Bounded", "F": "Flat"}
 
@@ -30,9 +34,10 @@ class Config:
 
     # ---- oracle ---------------------------------------------------------------------------------------------
     def oracle_grid(self):
-        return M.Grid(self.size, self.extent, topology=tuple(self.topology), halo=self.halo, ft=self.ft)
+        return _oracle().Grid(self.size, self.extent, topology=tuple(self.topology), halo=self.halo, ft=self.ft)
 
     def oracle_model(self):
+        M = _oracle()
         cl = []
         for c in self.closure:
             if c[0] == "scalar":
@@ -95,21 +100,29 @@ class Config:
     def initial_conditions(self, seed, amp=0.1, tracer_amp=1e-3, tracer_mean=None):
         """interior arrays (numpy (nz, ny, nx)) for every prognostic field; identical for both models"""
         rng = np.random.default_rng(seed)
-        g = self.oracle_grid()
+        N = self.size
+        bounded = [t == "B" for t in self.topology]
+
+        def shape(loc):  # interior shape (nz, ny, nx): +1 for a Face location along a Bounded direction
+            return tuple(N[d] + (1 if (loc[d] == "f" and bounded[d]) else 0) for d in (2, 1, 0))
+
         out = {}
         for name, loc in (("u", "fcc"), ("v", "cfc"), ("w", "ccf")):
             d = "uvw".index(name)
-            shape = tuple(g.field_size(loc[dd], dd) for dd in (2, 1, 0))
-            a = amp * rng.uniform(-1, 1, shape)
+            a = amp * rng.uniform(-1, 1, shape(loc))
             if self.topology[d] == "F":
                 a[...] = 0  # no flow in a Flat direction
             out[name] = a.astype(self.ft)
+        if self.topology[2] == "F":
+            zc = 0.0
+        else:
+            e = self.extent[2]
+            faces = np.linspace(e[0], e[1], N[2] + 1) if isinstance(e, tuple) else np.asarray(e, dtype=np.float64)
+            zc = (0.5 * (faces[1:] + faces[:-1])).astype(self.ft)[:, None, None]
         for t in self.tracers:
-            shape = tuple(g.N[dd] for dd in (2, 1, 0))
             mean = (tracer_mean or {}).get(t, 0.0)
-            zc = g.nodes(2, "c")[:, None, None] if self.topology[2] != "F" else 0.0
             base = {"b": 1.0 * zc, "T": 20 + 0.005 * zc, "S": 35.0 + 0 * zc}.get(t, 0 * zc) + mean
-            out[t] = (base + tracer_amp * rng.uniform(-1, 1, shape)).astype(self.ft)
+            out[t] = (base + tracer_amp * rng.uniform(-1, 1, shape("ccc"))).astype(self.ft)
         return out
 
 
