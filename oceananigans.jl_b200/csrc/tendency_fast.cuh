@@ -173,8 +173,36 @@ struct FastTerms {
         if (P.buoy == BUOY_SEAWATER) return P.grav * (P.alpha * ld(at(P.c[P.iT]), 0, 0, c) - P.beta * ld(at(P.c[P.iS]), 0, 0, c));
         return 0;
     }
-    // the tendency assemblers (nonhydrostatic_tendency_kernel_functions.jl:71-302), same term order as G*_finish
-    template <int WHICH> __device__ __forceinline__ T finish(T adv, int t, const T *cp) const {
+    // closure flux of tendency WHICH through the face this thread OWNS in direction D (same ownership as the advective
+    // fluxes: centre-type directions own the face one index below; D == 2 is the UPPER face, evaluated from level k)
+    template <int WHICH, int D> __device__ __forceinline__ T own_closure_flux(int m, int t, const T *cp) const {
+        if constexpr (WHICH == 3) {
+            const int kind = P.cl[m].kind;
+            const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][t]);
+            return qflux(m, t, cp, kf, D, 0, 0, D == 2 ? 1 : 0);
+        } else {
+            const T *ne = nue_ptr(m);
+            if constexpr (WHICH == 0) return D == 0 ? ux(m, ne, -1, 0, 0) : D == 1 ? uy(m, ne, 0, 0, 0) : uz(m, ne, 0, 0, 1);
+            else if constexpr (WHICH == 1) return D == 0 ? vx(m, ne, 0, 0, 0) : D == 1 ? vy(m, ne, 0, -1, 0) : vz(m, ne, 0, 0, 1);
+            else return D == 0 ? wx(m, ne, 0, 0, 0) : D == 1 ? wy(m, ne, 0, 0, 0) : wz(m, ne, 0, 0, 0);
+        }
+    }
+    // lower z face at the first level of a chunk
+    template <int WHICH> __device__ __forceinline__ T first_lower_closure_flux(int m, int t, const T *cp) const {
+        if constexpr (WHICH == 3) {
+            const int kind = P.cl[m].kind;
+            const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][t]);
+            return qflux(m, t, cp, kf, 2, 0, 0, 0);
+        } else {
+            const T *ne = nue_ptr(m);
+            if constexpr (WHICH == 0) return uz(m, ne, 0, 0, 0);
+            else if constexpr (WHICH == 1) return vz(m, ne, 0, 0, 0);
+            else return wz(m, ne, 0, 0, -1);
+        }
+    }
+    // the tendency assemblers (nonhydrostatic_tendency_kernel_functions.jl:71-302), same term order as G*_finish;
+    // SHARED: the closure term (sum over closures of V⁻¹ Σ δ(flux)) was formed from face fluxes shared between cells
+    template <int WHICH, bool SHARED = false> __device__ __forceinline__ T finish(T adv, int t, const T *cp, T closure_term = T(0)) const {
         T r = -adv;
         if constexpr (WHICH == 0) {
             if (P.has_cor) {
@@ -196,7 +224,9 @@ struct FastTerms {
             if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
         }
         if (P.ncl > 0) {
-            if constexpr (WHICH == 3) {
+            if constexpr (SHARED) {
+                r = r - closure_term;
+            } else if constexpr (WHICH == 3) {
                 T q = div_q(0, t, cp);
                 for (int m = 1; m < P.ncl; m++) q = q + div_q(m, t, cp);
                 r = r - q;
@@ -210,8 +240,10 @@ struct FastTerms {
     }
 };
 
+#define OB_SHARED_CL 2   // closures whose face fluxes are shared between cells on the fast path (more: pointwise)
 template <typename T, int N, bool FAST, int WHICH, int TY, int KC, bool STR>
-__device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i, int j, int k0, int k1, T (*sy_buf)[TY][32]) {
+__device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i, int j, int k0, int k1, T (*sy_buf)[TY][32],
+                                                T (*sv_buf)[OB_SHARED_CL][TY][32]) {
     const GridD<T> &gg = P.g;
     const int Nx = gg.N[0], Ny = gg.N[1];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -227,7 +259,16 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
     const int base = ii + jj * g.sy + k0 * g.sz;  // every field has the same offsets on this path
     const T *pq = qf.p + qf.off + base;
     const T *pu = P.u.p + P.u.off + base, *pv = P.v.p + P.v.off + base, *pw = P.w.p + P.w.off + base;
+    // closure face fluxes are shared exactly like the advective ones when there are 1..OB_SHARED_CL closures
+    const int ncl = P.ncl;
+    const bool share_cl = ncl >= 1 && ncl <= OB_SHARED_CL;   // launch-uniform
     T lower = full_row ? fast_flux<T, N, FAST, WHICH, 2, STR>(pq, pw, g, k0) : T(0);
+    T lower_c[OB_SHARED_CL] = {T(0), T(0)};
+    if (share_cl && full_row) {
+        FastTerms<T, STR> F0{P, g, pu, pv, pw, base, k0};
+#pragma unroll
+        for (int m = 0; m < OB_SHARED_CL; m++) if (m < ncl) lower_c[m] = F0.template first_lower_closure_flux<WHICH>(m, t, pq);
+    }
     for (int k = k0; k <= k1; k++) {
         T fx = T(0), upper = T(0);
         const T fy = fast_flux<T, N, FAST, WHICH, 1, STR>(pq, pv, g, k);
@@ -235,19 +276,54 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
             fx = fast_flux<T, N, FAST, WHICH, 0, STR>(pq, pu, g, k);
             upper = fast_flux<T, N, FAST, WHICH, 2, STR>(pq + g.sz, pw + g.sz, g, k + 1);
         }
+        const int eo = ii + jj * g.sy + k * g.sz;
+        FastTerms<T, STR> F{P, g, pu, pv, pw, eo, k};
+        T cx[OB_SHARED_CL] = {T(0), T(0)}, cy[OB_SHARED_CL] = {T(0), T(0)}, cup[OB_SHARED_CL] = {T(0), T(0)};
+        if (share_cl) {
+#pragma unroll
+            for (int m = 0; m < OB_SHARED_CL; m++)
+                if (m < ncl) {
+                    cy[m] = F.template own_closure_flux<WHICH, 1>(m, t, pq);
+                    if (full_row) {
+                        cx[m] = F.template own_closure_flux<WHICH, 0>(m, t, pq);
+                        cup[m] = F.template own_closure_flux<WHICH, 2>(m, t, pq);
+                    }
+                }
+        }
         const T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
+        T cx1[OB_SHARED_CL];
+#pragma unroll
+        for (int m = 0; m < OB_SHARED_CL; m++) cx1[m] = share_cl ? __shfl_down_sync(0xffffffffu, cx[m], 1) : T(0);
         const int buf = k & 1;
         sy_buf[buf][ty][tx] = fy;
+        if (share_cl) {
+#pragma unroll
+            for (int m = 0; m < OB_SHARED_CL; m++) if (m < ncl) sv_buf[buf][m][ty][tx] = cy[m];
+        }
         __syncthreads();
         if (do_out) {
             const T fy1 = sy_buf[buf][ty + 1][tx];
             const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
             const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower));
-            const int eo = i + j * g.sy + k * g.sz;
-            FastTerms<T, STR> F{P, g, pu, pv, pw, eo, k};
-            G.p[G.off + eo] = F.template finish<WHICH>(adv, t, pq);
+            T r;
+            if (share_cl) {
+                T term = T(0);
+#pragma unroll
+                for (int m = 0; m < OB_SHARED_CL; m++)
+                    if (m < ncl) {
+                        const T cy1 = sv_buf[buf][m][ty + 1][tx];
+                        const T d = Vi * ((cx1[m] - cx[m]) + (cy1 - cy[m]) + (cup[m] - lower_c[m]));
+                        term = m == 0 ? d : term + d;
+                    }
+                r = F.template finish<WHICH, true>(adv, t, pq, term);
+            } else {
+                r = F.template finish<WHICH, false>(adv, t, pq);
+            }
+            G.p[G.off + eo] = r;
         }
         lower = upper;
+#pragma unroll
+        for (int m = 0; m < OB_SHARED_CL; m++) lower_c[m] = cup[m];
         pq += g.sz; pu += g.sz; pv += g.sz; pw += g.sz;
     }
 }

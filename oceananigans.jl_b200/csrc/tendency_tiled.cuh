@@ -73,6 +73,7 @@ __device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int 
 template <typename T, class S, bool FAST, int TY, int KC, int MINB>
 __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc) {
     __shared__ T sy[2][TY][32];
+    __shared__ T sv[2][OB_SHARED_CL][TY][32];
     const int which = blockIdx.y;
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
     const int ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
@@ -90,15 +91,15 @@ __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __g
         if (fast_path_ok<T, S::n>(P, k0, k1)) {  // CTA-uniform
             const int t = which - 3;
             if (P.g.dzc) {
-                if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC, true>(P, 0, i, j, k0, k1, sy);
-                else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC, true>(P, 0, i, j, k0, k1, sy);
-                else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC, true>(P, 0, i, j, k0, k1, sy);
-                else march_fast_body<T, S::n, FAST, 3, TY, KC, true>(P, t, i, j, k0, k1, sy);
+                if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC, true>(P, 0, i, j, k0, k1, sy, sv);
+                else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC, true>(P, 0, i, j, k0, k1, sy, sv);
+                else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC, true>(P, 0, i, j, k0, k1, sy, sv);
+                else march_fast_body<T, S::n, FAST, 3, TY, KC, true>(P, t, i, j, k0, k1, sy, sv);
             } else {
-                if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC, false>(P, 0, i, j, k0, k1, sy);
-                else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC, false>(P, 0, i, j, k0, k1, sy);
-                else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC, false>(P, 0, i, j, k0, k1, sy);
-                else march_fast_body<T, S::n, FAST, 3, TY, KC, false>(P, t, i, j, k0, k1, sy);
+                if (which == 0) march_fast_body<T, S::n, FAST, 0, TY, KC, false>(P, 0, i, j, k0, k1, sy, sv);
+                else if (which == 1) march_fast_body<T, S::n, FAST, 1, TY, KC, false>(P, 0, i, j, k0, k1, sy, sv);
+                else if (which == 2) march_fast_body<T, S::n, FAST, 2, TY, KC, false>(P, 0, i, j, k0, k1, sy, sv);
+                else march_fast_body<T, S::n, FAST, 3, TY, KC, false>(P, t, i, j, k0, k1, sy, sv);
             }
             return;
         }
