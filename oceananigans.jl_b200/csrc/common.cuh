@@ -82,6 +82,9 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
+// Makhoul (1980) permutation of a DCT line (index_permutations.jl:18-36), 0-based: even i -> i/2 ; odd i -> N-1-(i-1)/2
+__device__ __forceinline__ int makhoul_index(int i, int N) { const int h = i >> 1; return (i & 1) ? N - 1 - h : h; }  // i >= 0
+
 // Flattened launch geometry: blockIdx.x enumerates (x-block, j, k); returns false for the x tail.
 __device__ __forceinline__ bool cell_from_block(int Nx, int Ny, int &i, int &j, int &k) {
     const int nbx = (Nx + blockDim.x - 1) / blockDim.x;

@@ -299,6 +299,7 @@ struct SourceP {
     long ldx, ldxy;
     int times_dz;
     int cplx;  // write complex (re, 0) pairs instead of reals
+    int zperm; // write level k at the Makhoul-permuted position (real DCT path): even k-1 -> (k-1)/2, odd -> Nz-1-(k-2)/2
 };
 template <typename T>
 __global__ void __launch_bounds__(256) source_term_kernel(const __grid_constant__ SourceP<T> P) {
@@ -312,7 +313,8 @@ __global__ void __launch_bounds__(256) source_term_kernel(const __grid_constant_
     const T Vi = P.g.rVc(k);
     T div = Vi * (ddx + ddy + ddz);
     if (P.times_dz) div = dzc * div;
-    const long o = (i - 1) + (j - 1) * P.ldx + (long)(k - 1) * P.ldxy;
+    const int kk = P.zperm ? makhoul_index(k - 1, P.g.N[2]) : k - 1;
+    const long o = (i - 1) + (j - 1) * P.ldx + (long)kk * P.ldxy;
     if (P.cplx) { P.out[2 * o] = div; P.out[2 * o + 1] = T(0); }
     else P.out[o] = div;
 }
@@ -326,13 +328,15 @@ struct CopyRealP {
     long ldx, ldxy;
     int N[3];
     int cplx;
+    int zperm;
     T scale;
 };
 template <typename T>
 __global__ void __launch_bounds__(256) copy_real_kernel(const __grid_constant__ CopyRealP<T> P) {
     int i, j, k;
     if (!cell_from_block(P.N[0], P.N[1], i, j, k)) return;
-    const long o = (i - 1) + (j - 1) * P.ldx + (long)(k - 1) * P.ldxy;
+    const int kk = P.zperm ? makhoul_index(k - 1, P.N[2]) : k - 1;
+    const long o = (i - 1) + (j - 1) * P.ldx + (long)kk * P.ldxy;
     P.p(i, j, k) = (P.cplx ? P.in[2 * o] : P.in[o]) * P.scale;
 }
 
@@ -362,7 +366,7 @@ struct CorrectFusedP {
     Fld<T> u, v, w, p;
     const T *sol;
     long ldx, ldxy;
-    int cplx;
+    int cplx, zperm;
     T scale, denom;
 };
 template <typename T>
@@ -370,7 +374,8 @@ __global__ void __launch_bounds__(256) correct_fused_kernel(const __grid_constan
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     auto S = [&](int a, int b, int c) -> T {
-        const long o = (a - 1) + (b - 1) * P.ldx + (long)(c - 1) * P.ldxy;
+        const int cc = P.zperm ? makhoul_index(c - 1, P.g.N[2]) : c - 1;
+        const long o = (a - 1) + (b - 1) * P.ldx + (long)cc * P.ldxy;
         return mul_rn(P.cplx ? __ldg(P.sol + 2 * o) : __ldg(P.sol + o), P.scale);   // rounded like the stored p of the reference
     };
     // index of the lower neighbour along d: periodic wrap, or the cell itself where the no-flux halo mirrors it

@@ -229,6 +229,8 @@ struct ob_solver {
     virtual double scale() = 0;
     // true: storage() holds REAL numbers (Nx,Ny,Nz) on input and output (real-to-complex transforms inside)
     virtual bool real_storage() const { return false; }
+    // true: level k of storage() lives at the Makhoul-permuted position (real DCT path)
+    virtual bool z_permuted() const { return false; }
 };
 
 template <typename T>
@@ -241,6 +243,10 @@ struct SolverT : ob_solver {
     cufftHandle plan_x = 0, plan_y = 0, plan_z = 0, plan_xy = 0, plan_r2c = 0, plan_c2r = 0;
     bool has_x = false, has_y = false, has_z = false, has_xy = false;
     bool r2c = false;   // fully periodic: 3-D real-to-complex / complex-to-real transforms on the half spectrum
+    bool rdct = false;  // x, y Periodic + z Bounded: real DCT along z, real-to-complex 2-D transform in (x, y)
+    C *Cz = nullptr, *tw_zf = nullptr, *tw_zb = nullptr;
+    int Nzh = 0;
+    cufftHandle plan_zr2c = 0, plan_zc2r = 0, plan_xyr2c = 0, plan_xyc2r = 0;
     T *Rr = nullptr;
     int Nxh = 0;
     double scale_ = 1.0;
@@ -263,6 +269,43 @@ struct SolverT : ob_solver {
         const long n = (long)N[0] * N[1] * N[2];
         r2c = !tridiag && topo[0] == OB_PERIODIC && topo[1] == OB_PERIODIC && topo[2] == OB_PERIODIC && N[0] > 1 && N[1] > 1 && N[2] > 1 &&
               !getenv("OB_SOLVER_NO_R2C");
+        rdct = !tridiag && topo[0] == OB_PERIODIC && topo[1] == OB_PERIODIC && topo[2] == OB_BOUNDED && N[0] > 1 && N[1] > 1 && N[2] > 1 &&
+               !getenv("OB_SOLVER_NO_R2C");
+        if (rdct) {
+            Nxh = N[0] / 2 + 1; Nzh = N[2] / 2 + 1;
+            const long nh = (long)Nxh * N[1] * N[2], nz2 = (long)N[0] * N[1] * Nzh;
+            CUDA_TRY(cudaMalloc(&S, sizeof(C) * nh));
+            CUDA_TRY(cudaMalloc(&Cz, sizeof(C) * nz2));
+            CUDA_TRY(cudaMalloc(&Rr, sizeof(T) * n));
+            CUDA_TRY(cudaMemsetAsync(Rr, 0, sizeof(T) * n, ctx->stream));
+            for (int d = 0; d < 3; d++) {
+                std::vector<T> h(N[d]);
+                for (int i = 0; i < N[d]; i++) {
+                    double sn = 2 * sin(i * M_PI / ((d == 2 ? 2.0 : 1.0) * N[d])) / (L[d] / N[d]);
+                    h[i] = (T)(sn * sn);
+                }
+                CUDA_TRY(cudaMalloc(&lam[d], sizeof(T) * N[d]));
+                CUDA_TRY(cudaMemcpy(lam[d], h.data(), sizeof(T) * N[d], cudaMemcpyHostToDevice));
+            }
+            std::vector<C> f(N[2]), b(Nzh);
+            for (int k = 0; k < N[2]; k++) { double a = -M_PI * k / (2.0 * N[2]); f[k].x = (T)cos(a); f[k].y = (T)sin(a); }
+            for (int k = 0; k < Nzh; k++) { double a = M_PI * k / (2.0 * N[2]); b[k].x = (T)(0.5 * cos(a)); b[k].y = (T)(0.5 * sin(a)); }
+            CUDA_TRY(cudaMalloc(&tw_zf, sizeof(C) * N[2])); CUDA_TRY(cudaMalloc(&tw_zb, sizeof(C) * Nzh));
+            CUDA_TRY(cudaMemcpy(tw_zf, f.data(), sizeof(C) * N[2], cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(tw_zb, b.data(), sizeof(C) * Nzh, cudaMemcpyHostToDevice));
+            constexpr cufftType FWD = std::is_same<T, double>::value ? CUFFT_D2Z : CUFFT_R2C;
+            constexpr cufftType BWD = std::is_same<T, double>::value ? CUFFT_Z2D : CUFFT_C2R;
+            const int plane = N[0] * N[1];
+            int nzz[1] = {N[2]}, nre[1] = {N[2]}, nco[1] = {Nzh};
+            CUFFT_TRY(cufftPlanMany(&plan_zr2c, 1, nzz, nre, plane, 1, nco, plane, 1, FWD, plane));
+            CUFFT_TRY(cufftPlanMany(&plan_zc2r, 1, nzz, nco, plane, 1, nre, plane, 1, BWD, plane));
+            int nxy[2] = {N[1], N[0]}, exy_r[2] = {N[1], N[0]}, exy_c[2] = {N[1], Nxh};
+            CUFFT_TRY(cufftPlanMany(&plan_xyr2c, 2, nxy, exy_r, 1, plane, exy_c, 1, Nxh * N[1], FWD, N[2]));
+            CUFFT_TRY(cufftPlanMany(&plan_xyc2r, 2, nxy, exy_c, 1, Nxh * N[1], exy_r, 1, plane, BWD, N[2]));
+            for (cufftHandle h : {plan_zr2c, plan_zc2r, plan_xyr2c, plan_xyc2r}) CUFFT_TRY(cufftSetStream(h, ctx->stream));
+            scale_ = 1.0 / ((double)N[0] * N[1] * N[2]);
+            return OB_OK;
+        }
         if (r2c) {
             // The rhs is real, so a real-to-complex 3-D transform carries half the bytes of the reference's complex
             // in-place FFTs (fft_based_poisson_solver.jl:94-124); same eigenvalue division on the half spectrum i <= Nx/2.
@@ -384,10 +427,12 @@ struct SolverT : ob_solver {
         if (has_z) cufftDestroy(plan_z);
         if (has_xy) cufftDestroy(plan_xy);
         if (r2c) { cufftDestroy(plan_r2c); cufftDestroy(plan_c2r); cudaFree(Rr); }
+        if (rdct) { cufftDestroy(plan_zr2c); cufftDestroy(plan_zc2r); cufftDestroy(plan_xyr2c); cufftDestroy(plan_xyc2r); cudaFree(Rr); cudaFree(Cz); cudaFree(tw_zf); cudaFree(tw_zb); }
     }
-    void *storage() override { return r2c ? (void *)Rr : (void *)S; }
+    void *storage() override { return (r2c || rdct) ? (void *)Rr : (void *)S; }
     double scale() override { return scale_; }
-    bool real_storage() const override { return r2c; }
+    bool real_storage() const override { return r2c || rdct; }
+    bool z_permuted() const override { return rdct; }
 
     int32_t fft_dim(C *data, int d, int dir) {
         if (d == 0) return exec(plan_x, data, dir);
@@ -399,6 +444,20 @@ struct SolverT : ob_solver {
         const long n = (long)N[0] * N[1] * N[2];
         const unsigned nb = nblk(n, 256);
         cudaStream_t st = ctx->stream;
+        if (rdct) {
+            const long nz2 = (long)N[0] * N[1] * Nzh, nh = (long)Nxh * N[1] * N[2];
+            constexpr bool DBL = std::is_same<T, double>::value;
+            if constexpr (DBL) CUFFT_TRY(cufftExecD2Z(plan_zr2c, Rr, Cz)); else CUFFT_TRY(cufftExecR2C(plan_zr2c, (cufftReal *)Rr, (cufftComplex *)Cz));
+            dct_z_real_fwd_kernel<T, C><<<nb, 256, 0, st>>>(Cz, Rr, tw_zf, N[0], N[1], N[2], Nzh);
+            if constexpr (DBL) CUFFT_TRY(cufftExecD2Z(plan_xyr2c, Rr, S)); else CUFFT_TRY(cufftExecR2C(plan_xyr2c, (cufftReal *)Rr, (cufftComplex *)S));
+            eigen_divide_kernel<T, C><<<nblk(nh, 256), 256, 0, st>>>(S, lam[0], lam[1], lam[2], Nxh, N[1], N[2]);
+            if constexpr (DBL) CUFFT_TRY(cufftExecZ2D(plan_xyc2r, S, Rr)); else CUFFT_TRY(cufftExecC2R(plan_xyc2r, (cufftComplex *)S, (cufftReal *)Rr));
+            dct_z_real_bwd_kernel<T, C><<<nblk(nz2, 256), 256, 0, st>>>(Rr, Cz, tw_zb, N[0], N[1], N[2], Nzh);
+            if constexpr (DBL) CUFFT_TRY(cufftExecZ2D(plan_zc2r, Cz, Rr)); else CUFFT_TRY(cufftExecC2R(plan_zc2r, (cufftComplex *)Cz, (cufftReal *)Rr));
+            launches += 7;
+            CUDA_TRY(cudaGetLastError());
+            return OB_OK;
+        }
         if (r2c) {
             if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecD2Z(plan_r2c, Rr, S));
             else CUFFT_TRY(cufftExecR2C(plan_r2c, Rr, S));
@@ -487,21 +546,33 @@ __global__ void unpack_real_kernel(const C *S, T *r, long n, T scale) {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) r[t] = S[t].x * scale;
 }
+// copy with an optional Makhoul permutation of the levels: forward = 1 writes level k at its permuted position,
+// forward = 0 reads it from there (Nz = 0: plain copy); out = in * scale
 template <typename T>
-__global__ void scale_copy_kernel(const T *in, T *out, long n, T scale) {
+__global__ void zperm_copy_kernel(const T *in, T *out, long n, long plane, int Nz, int forward, T scale) {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) out[t] = in[t] * scale;
+    if (t >= n) return;
+    long o = t;
+    if (Nz > 0) {
+        const long k = t / plane, ij = t - k * plane;
+        const long kp = (k & 1) ? (long)Nz - 1 - (k >> 1) : (k >> 1);
+        o = ij + kp * plane;
+    }
+    if (forward) out[o] = in[t] * scale;
+    else out[t] = in[o] * scale;
 }
 extern "C" int32_t ob_poisson_solve(ob_solver *s, const void *rhs, void *phi) {
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     const long n = (long)s->N[0] * s->N[1] * s->N[2];
     cudaStream_t st = s->ctx->stream;
     if (s->real_storage()) {
-        const size_t w = s->ft == OB_F64 ? 8 : 4;
-        CUDA_TRY(cudaMemcpyAsync(s->storage(), rhs, w * n, cudaMemcpyDeviceToDevice, st));
+        const long plane = (long)s->N[0] * s->N[1];
+        const int zp = s->z_permuted() ? s->N[2] : 0;
+        if (s->ft == OB_F64) zperm_copy_kernel<double><<<nblk(n, 256), 256, 0, st>>>((const double *)rhs, (double *)s->storage(), n, plane, zp, 1, 1.0);
+        else zperm_copy_kernel<float><<<nblk(n, 256), 256, 0, st>>>((const float *)rhs, (float *)s->storage(), n, plane, zp, 1, 1.0f);
         OB_TRY(s->solve_in_storage());
-        if (s->ft == OB_F64) scale_copy_kernel<double><<<nblk(n, 256), 256, 0, st>>>((const double *)s->storage(), (double *)phi, n, s->scale());
-        else scale_copy_kernel<float><<<nblk(n, 256), 256, 0, st>>>((const float *)s->storage(), (float *)phi, n, (float)s->scale());
+        if (s->ft == OB_F64) zperm_copy_kernel<double><<<nblk(n, 256), 256, 0, st>>>((const double *)s->storage(), (double *)phi, n, plane, zp, 0, s->scale());
+        else zperm_copy_kernel<float><<<nblk(n, 256), 256, 0, st>>>((const float *)s->storage(), (float *)phi, n, plane, zp, 0, (float)s->scale());
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
@@ -1084,6 +1155,7 @@ struct ModelT : ob_model {
             P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
             P.times_dz = solver->tridiag ? 1 : 0;
             P.cplx = solver->real_storage() ? 0 : 1;
+            P.zperm = solver->z_permuted() ? 1 : 0;
             source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
             launches++;
         }
@@ -1101,6 +1173,7 @@ struct ModelT : ob_model {
             P.sol = (const T *)solver->storage();
             P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
             P.cplx = solver->real_storage() ? 0 : 1;
+            P.zperm = solver->z_permuted() ? 1 : 0;
             P.scale = (T)solver->scale();
             P.denom = std::max(std::numeric_limits<T>::epsilon(), (T)dtau);
             correct_fused_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
@@ -1154,6 +1227,7 @@ struct ModelT : ob_model {
             P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
             P.times_dz = solver->tridiag ? 1 : 0;
             P.cplx = solver->real_storage() ? 0 : 1;
+            P.zperm = solver->z_permuted() ? 1 : 0;
             source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
             launches++;
         }
@@ -1169,6 +1243,7 @@ struct ModelT : ob_model {
             P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
             for (int k = 0; k < 3; k++) P.N[k] = g.N[k];
             P.cplx = solver->real_storage() ? 0 : 1;
+            P.zperm = solver->z_permuted() ? 1 : 0;
             P.scale = (T)solver->scale();
             copy_real_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
             launches++;

@@ -90,6 +90,42 @@ __global__ void __launch_bounds__(256) eigen_divide_kernel(C *__restrict__ A, co
     A[t] = o;
 }
 
+// Real-data DCT path (x, y Periodic, z Bounded and regular): the rhs is real, so the z transform is a real-to-complex FFT
+// of the Makhoul-permuted line and the DCT-II coefficients X[k] = 2 Re(ω_k V[k]) are REAL; V[k] for k > N/2 comes from
+// the conjugate symmetry V[N-k] = conj(V[k]).  The (x, y) transform is then a real-to-complex 2-D FFT of X.  Backward:
+// V[k] = ω⁻_k (X[k] - i X[N-k]) / 2 (X[N] = 0) is the Hermitian half spectrum whose complex-to-real FFT is the permuted
+// line.  Same transforms as REDFT10 / REDFT01 (plan_transforms.jl:16-34), a quarter of the bytes of the complex route.
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) dct_z_real_fwd_kernel(const C *__restrict__ V, T *__restrict__ X, const C *__restrict__ w,
+                                                             int Nx, int Ny, int Nz, int Nzh) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long plane = (long)Nx * Ny;
+    const int k = (int)(t / plane);
+    const long ij = t - (long)k * plane;
+    (void)Nzh;
+    C v;
+    if (2 * k <= Nz) v = V[ij + (long)k * plane];
+    else { v = V[ij + (long)(Nz - k) * plane]; v.y = -v.y; }
+    const C r = cmul(w[k], v);
+    X[t] = 2 * r.x;
+}
+template <typename T, typename C>
+__global__ void __launch_bounds__(256) dct_z_real_bwd_kernel(const T *__restrict__ X, C *__restrict__ V, const C *__restrict__ w,
+                                                             int Nx, int Ny, int Nz, int Nzh) {
+    const long n = (long)Nx * Ny * Nzh;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long plane = (long)Nx * Ny;
+    const int k = (int)(t / plane);
+    const long ij = t - (long)k * plane;
+    const T a = X[ij + (long)k * plane];
+    const T b = k == 0 ? T(0) : X[ij + (long)(Nz - k) * plane];
+    C z; z.x = a; z.y = -b;                 // X[k] - i X[N-k]
+    V[t] = cmul(w[k], z);                    // w[k] = ω⁻_k / 2
+}
+
 // Complex Thomas sweep along z, one thread per (i,j) column, coalesced along x
 // (batched_tridiagonal_solver.jl:217-243).  a = c = lower diagonal (Nz-1), D = main diagonal (Nx,Ny,Nz),
 // tscr = real scratch (Nx,Ny,Nz).  In place on the complex array A (f and ϕ alias).
