@@ -244,6 +244,7 @@ struct SolverT : ob_solver {
     bool has_x = false, has_y = false, has_z = false, has_xy = false;
     bool r2c = false;   // fully periodic: 3-D real-to-complex / complex-to-real transforms on the half spectrum
     bool rdct = false;  // x, y Periodic + z Bounded: real DCT along z, real-to-complex 2-D transform in (x, y)
+    bool rtri = false;  // x, y Periodic + stretched z: real-to-complex 2-D transform, Thomas sweep on the half spectrum
     C *Cz = nullptr, *tw_zf = nullptr, *tw_zb = nullptr;
     int Nzh = 0;
     cufftHandle plan_zr2c = 0, plan_zc2r = 0, plan_xyr2c = 0, plan_xyc2r = 0;
@@ -271,6 +272,47 @@ struct SolverT : ob_solver {
               !getenv("OB_SOLVER_NO_R2C");
         rdct = !tridiag && topo[0] == OB_PERIODIC && topo[1] == OB_PERIODIC && topo[2] == OB_BOUNDED && N[0] > 1 && N[1] > 1 && N[2] > 1 &&
                !getenv("OB_SOLVER_NO_R2C");
+        rtri = tridiag && topo[0] == OB_PERIODIC && topo[1] == OB_PERIODIC && N[0] > 1 && N[1] > 1 && !getenv("OB_SOLVER_NO_R2C");
+        if (rtri) {
+            // FourierTridiagonalPoissonSolver on the half spectrum of the real rhs (fourier_tridiagonal_poisson_solver.jl:199-260)
+            Nxh = N[0] / 2 + 1;
+            const long nh = (long)Nxh * N[1] * N[2];
+            CUDA_TRY(cudaMalloc(&S, sizeof(C) * nh));
+            CUDA_TRY(cudaMalloc(&Rr, sizeof(T) * n));
+            CUDA_TRY(cudaMemsetAsync(Rr, 0, sizeof(T) * n, ctx->stream));
+            std::vector<T> lx(N[0]), ly(N[1]);
+            for (int d = 0; d < 2; d++)
+                for (int i = 0; i < N[d]; i++) { double sn = 2 * sin(i * M_PI / N[d]) / (L[d] / N[d]); (d == 0 ? lx : ly)[i] = (T)(sn * sn); }
+            const int Nz = N[2], Hz = g->H[2];
+            const T *dzf = (const T *)g->dzf_host, *dzc = (const T *)g->dzc_host;
+            auto DZF = [&](int k) { return dzf[k + Hz]; };
+            auto DZC = [&](int k) { return dzc[k + Hz - 1]; };
+            std::vector<T> D((size_t)nh), low(std::max(1, Nz - 1));
+            for (int k = 1; k <= Nz; k++)
+                for (int j = 0; j < N[1]; j++)
+                    for (int i = 0; i < Nxh; i++) {
+                        T l = lx[i] + ly[j];
+                        T v;
+                        if (k == 1) v = (T)-1 / DZF(2) - DZC(1) * l;
+                        else if (k == Nz) v = (T)-1 / DZF(Nz) - DZC(Nz) * l;
+                        else v = -((T)1 / DZF(k + 1) + (T)1 / DZF(k)) - DZC(k) * l;
+                        D[i + (size_t)Nxh * (j + (size_t)N[1] * (k - 1))] = v;
+                    }
+            for (int q = 1; q <= Nz - 1; q++) low[q - 1] = (T)1 / DZF(q + 1);
+            CUDA_TRY(cudaMalloc(&diag, sizeof(T) * nh)); CUDA_TRY(cudaMalloc(&tscr, sizeof(T) * nh));
+            CUDA_TRY(cudaMalloc(&lower, sizeof(T) * low.size()));
+            CUDA_TRY(cudaMemcpy(diag, D.data(), sizeof(T) * nh, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(lower, low.data(), sizeof(T) * low.size(), cudaMemcpyHostToDevice));
+            constexpr cufftType FWD = std::is_same<T, double>::value ? CUFFT_D2Z : CUFFT_R2C;
+            constexpr cufftType BWD = std::is_same<T, double>::value ? CUFFT_Z2D : CUFFT_C2R;
+            const int plane = N[0] * N[1];
+            int nxy[2] = {N[1], N[0]}, exy_r[2] = {N[1], N[0]}, exy_c[2] = {N[1], Nxh};
+            CUFFT_TRY(cufftPlanMany(&plan_xyr2c, 2, nxy, exy_r, 1, plane, exy_c, 1, Nxh * N[1], FWD, N[2]));
+            CUFFT_TRY(cufftPlanMany(&plan_xyc2r, 2, nxy, exy_c, 1, Nxh * N[1], exy_r, 1, plane, BWD, N[2]));
+            CUFFT_TRY(cufftSetStream(plan_xyr2c, ctx->stream)); CUFFT_TRY(cufftSetStream(plan_xyc2r, ctx->stream));
+            scale_ = 1.0 / ((double)N[0] * N[1]);
+            return OB_OK;
+        }
         if (rdct) {
             Nxh = N[0] / 2 + 1; Nzh = N[2] / 2 + 1;
             const long nh = (long)Nxh * N[1] * N[2], nz2 = (long)N[0] * N[1] * Nzh;
@@ -427,11 +469,12 @@ struct SolverT : ob_solver {
         if (has_z) cufftDestroy(plan_z);
         if (has_xy) cufftDestroy(plan_xy);
         if (r2c) { cufftDestroy(plan_r2c); cufftDestroy(plan_c2r); cudaFree(Rr); }
+        if (rtri) { cufftDestroy(plan_xyr2c); cufftDestroy(plan_xyc2r); cudaFree(Rr); }
         if (rdct) { cufftDestroy(plan_zr2c); cufftDestroy(plan_zc2r); cufftDestroy(plan_xyr2c); cufftDestroy(plan_xyc2r); cudaFree(Rr); cudaFree(Cz); cudaFree(tw_zf); cudaFree(tw_zb); }
     }
-    void *storage() override { return (r2c || rdct) ? (void *)Rr : (void *)S; }
+    void *storage() override { return (r2c || rdct || rtri) ? (void *)Rr : (void *)S; }
     double scale() override { return scale_; }
-    bool real_storage() const override { return r2c || rdct; }
+    bool real_storage() const override { return r2c || rdct || rtri; }
     bool z_permuted() const override { return rdct; }
 
     int32_t fft_dim(C *data, int d, int dir) {
@@ -444,6 +487,16 @@ struct SolverT : ob_solver {
         const long n = (long)N[0] * N[1] * N[2];
         const unsigned nb = nblk(n, 256);
         cudaStream_t st = ctx->stream;
+        if (rtri) {
+            constexpr bool DBL = std::is_same<T, double>::value;
+            if constexpr (DBL) CUFFT_TRY(cufftExecD2Z(plan_xyr2c, Rr, S)); else CUFFT_TRY(cufftExecR2C(plan_xyr2c, (cufftReal *)Rr, (cufftComplex *)S));
+            dim3 grid(nblk(Nxh, 128), N[1]);
+            thomas_kernel<T, C><<<grid, 128, 0, st>>>(S, lower, lower, diag, tscr, Nxh, N[1], N[2], (T)(10 * std::numeric_limits<T>::epsilon()), 1);
+            if constexpr (DBL) CUFFT_TRY(cufftExecZ2D(plan_xyc2r, S, Rr)); else CUFFT_TRY(cufftExecC2R(plan_xyc2r, (cufftComplex *)S, (cufftReal *)Rr));
+            launches += 3;
+            CUDA_TRY(cudaGetLastError());
+            return OB_OK;
+        }
         if (rdct) {
             const long nz2 = (long)N[0] * N[1] * Nzh, nh = (long)Nxh * N[1] * N[2];
             constexpr bool DBL = std::is_same<T, double>::value;
