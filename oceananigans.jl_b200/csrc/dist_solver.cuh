@@ -107,6 +107,18 @@ __global__ void __launch_bounds__(256) pull_x_to_z_kernel(const __grid_constant_
     S[t] = peers.p[r][(rank * nx + xl) + (long)NxG * (y + (long)Ny * zl)];     // peer r's z-local layout (Nx, Ny, nz)
 }
 
+// Stream-ordered barrier across the ranks without a collective: lane r publishes this rank's epoch into peer r's flag
+// array (release store over NVLink) and then waits until peer r's epoch has arrived in the local array.
+struct PeerFlags { int *p[OB_MAX_PEERS]; };
+__global__ void ipc_barrier_kernel(const __grid_constant__ PeerFlags peers, int *mine, int R, int rank, int epoch) {
+    const int r = threadIdx.x;
+    if (r < R) {
+        __threadfence_system();
+        st_release_sys(peers.p[r] + rank, epoch);
+        while (ld_acquire_sys(mine + r) < epoch) {}
+    }
+}
+
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) eigen_divide_zslab_kernel(C *__restrict__ A, const T *__restrict__ lx, const T *__restrict__ ly,
                                                                  const T *__restrict__ lz, int NxG, int Ny, int nz, int z0, int nlev, int zero_mode) {
@@ -157,6 +169,9 @@ struct DistSolverT : ob_solver {
     bool use_ipc = false;           // pull transposes through CUDA-IPC peer mappings instead of NCCL send/recv
     ob::PeerPtrs<C> peerS, peerT;
     int *d_bar = nullptr;
+    int *d_bflags = nullptr;   // [R] epochs published by the peers (IPC-exported)
+    ob::PeerFlags peerF;
+    int bar_epoch = 0;
     C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
     T *lam[3] = {nullptr, nullptr, nullptr};
     C *tw_f = nullptr, *tw_b = nullptr;          // z DCT twiddles (Bounded regular z)
@@ -307,9 +322,12 @@ struct DistSolverT : ob_solver {
     // exchange cudaIpcMemHandle_t of S and Tt between the ranks (all-gather over NCCL) and map the peers' arrays
     int32_t setup_ipc() {
         if (R > OB_MAX_PEERS) return OB_OK;
-        struct Pair { cudaIpcMemHandle_t s, t; };
+        struct Pair { cudaIpcMemHandle_t s, t, f; };
         Pair mine;
-        if (cudaIpcGetMemHandle(&mine.s, S) != cudaSuccess || cudaIpcGetMemHandle(&mine.t, Tt) != cudaSuccess) { cudaGetLastError(); return OB_OK; }
+        CUDA_TRY(cudaMalloc(&d_bflags, sizeof(int) * OB_MAX_PEERS));
+        CUDA_TRY(cudaMemsetAsync(d_bflags, 0, sizeof(int) * OB_MAX_PEERS, ctx->stream));
+        if (cudaIpcGetMemHandle(&mine.s, S) != cudaSuccess || cudaIpcGetMemHandle(&mine.t, Tt) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine.f, d_bflags) != cudaSuccess) { cudaGetLastError(); return OB_OK; }
         Pair *d_all = nullptr;
         CUDA_TRY(cudaMalloc(&d_all, sizeof(Pair) * R));
         CUDA_TRY(cudaMemcpyAsync(d_all + rank, &mine, sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
@@ -320,11 +338,12 @@ struct DistSolverT : ob_solver {
         cudaFree(d_all);
         int ok = 1;
         for (int r = 0; r < R; r++) {
-            if (r == rank) { peerS.p[r] = S; peerT.p[r] = Tt; continue; }
-            void *ps = nullptr, *pt = nullptr;
+            if (r == rank) { peerS.p[r] = S; peerT.p[r] = Tt; peerF.p[r] = d_bflags; continue; }
+            void *ps = nullptr, *pt = nullptr, *pf = nullptr;
             if (cudaIpcOpenMemHandle(&ps, all[r].s, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-                cudaIpcOpenMemHandle(&pt, all[r].t, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-            peerS.p[r] = (const C *)ps; peerT.p[r] = (const C *)pt;
+                cudaIpcOpenMemHandle(&pt, all[r].t, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&pf, all[r].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            peerS.p[r] = (const C *)ps; peerT.p[r] = (const C *)pt; peerF.p[r] = (int *)pf;
         }
         // every rank must take the same path: agree through an all-reduce (min)
         CUDA_TRY(cudaMalloc(&d_bar, sizeof(int)));
@@ -337,16 +356,16 @@ struct DistSolverT : ob_solver {
     }
     // stream-ordered barrier across the ranks
     int32_t barrier() {
-        NCCL_TRY(ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+        ipc_barrier_kernel<<<1, 32, 0, ctx->stream>>>(peerF, d_bflags, R, rank, ++bar_epoch);
         launches++;
         return OB_OK;
     }
     ~DistSolverT() override {
         if (use_ipc) {
             cudaStreamSynchronize(ctx->stream);
-            for (int r = 0; r < R; r++) if (r != rank) { cudaIpcCloseMemHandle((void *)peerS.p[r]); cudaIpcCloseMemHandle((void *)peerT.p[r]); }
+            for (int r = 0; r < R; r++) if (r != rank) { cudaIpcCloseMemHandle((void *)peerS.p[r]); cudaIpcCloseMemHandle((void *)peerT.p[r]); cudaIpcCloseMemHandle((void *)peerF.p[r]); }
         }
-        cudaFree(d_bar);
+        cudaFree(d_bar); cudaFree(d_bflags);
         cudaFree(S); cudaFree(Tt); cudaFree(buf_a); cudaFree(buf_b);
         for (int d = 0; d < 3; d++) cudaFree(lam[d]);
         cudaFree(tw_f); cudaFree(tw_b); cudaFree(diag); cudaFree(lower); cudaFree(tscr);
