@@ -136,10 +136,107 @@ function grid_desc(grid::RectilinearGrid{FT}) where FT
     return desc, (dzf, dzc)   # keep the host arrays alive across ob_model_create
 end
 
-# bc_desc, closure_desc, model_desc: translate FieldBoundaryConditions / closures / buoyancy / coriolis into the POD
-# structs, throwing ArgumentError for anything the ABI cannot express (function-valued BCs and forcings, background
-# fields, immersed boundaries, other closures / equations of state) -- see models.py for the executable twin of this
-# validation logic.
+# ---- translation of the model description; anything the ABI cannot express throws (no CPU fallback) -----------------
+unsupported(what) = throw(ArgumentError("B200: $what is outside the accelerated NonhydrostaticModel path (SURVEY.md §2)"))
+
+bc_kind(::Nothing) = (Int32(0), 0.0)
+function bc_kind(bc::BoundaryCondition)
+    c = bc.classification
+    c isa PBC && return (Int32(1), 0.0)
+    v = bc.condition
+    (v isa Number || v === nothing) || unsupported("a function- or array-valued boundary condition")
+    val = v === nothing ? 0.0 : Float64(v)
+    c isa Flux     && return (Int32(2), val)
+    c isa Value    && return (Int32(3), val)
+    c isa Gradient && return (Int32(4), val)
+    c isa Open     && (v === nothing ? (return (Int32(5), 0.0)) : unsupported("an open boundary with a prescribed value"))
+    unsupported("boundary condition $(typeof(c))")
+end
+function bc_desc(bcs::FieldBoundaryConditions)
+    ks = map(bc_kind, (bcs.west, bcs.east, bcs.south, bcs.north, bcs.bottom, bcs.top))
+    return ObBcDesc(ntuple(i -> ks[i][1], 6), ntuple(i -> ks[i][2], 6))
+end
+bc_desc(::Nothing) = ObBcDesc(ntuple(_ -> Int32(0), 6), ntuple(_ -> 0.0, 6))
+
+pad8(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, 8)
+closure_desc(c::ScalarDiffusivity, names) =
+    (c.ν isa Number && all(κ -> κ isa Number, values(c.κ))) ?
+        ObClosureDesc(1, Float64(c.ν), pad8(values(c.κ)), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0) : unsupported("a function-valued diffusivity")
+function closure_desc(c::Smagorinsky, names)
+    coeff = c.coefficient
+    lilly = !(coeff isa Number)
+    cs = lilly ? coeff.smagorinsky : coeff
+    cb = lilly ? coeff.reduction_factor : 0.0
+    (cs isa Number) || unsupported("DynamicSmagorinsky")
+    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0)
+end
+closure_desc(c::AnisotropicMinimumDissipation, names) =
+    ObClosureDesc(3, 0.0, pad8(()), 0.0, 0, c.Cb === nothing ? 0.0 : Float64(c.Cb), pad8(()), Float64(c.Cν), pad8(values(c.Cκ)), Int32(c.Cb !== nothing))
+closure_desc(c, names) = unsupported("closure $(typeof(c))")
+
+function model_desc(model::NonhydrostaticModel)
+    grid = model.grid
+    gd, keep = grid_desc(grid)
+    adv = model.advection.momentum   # the shim requires one scheme for momentum and tracers
+    kind, order = adv isa WENO ? (Int32(2), 2 * Oceananigans.Advection.required_halo_size_x(adv) - 1) :
+                  adv isa Centered ? (Int32(1), 2 * Oceananigans.Advection.required_halo_size_x(adv)) : unsupported("advection $(typeof(adv))")
+    closures = model.closure === nothing ? () : model.closure isa Tuple ? model.closure : (model.closure,)
+    length(closures) <= 4 || unsupported("more than 4 closures")
+    names = keys(model.tracers)
+    length(names) <= 8 || unsupported("more than 8 tracers")
+    cds = ntuple(i -> i <= length(closures) ? closure_desc(closures[i], names) : ObClosureDesc(0, 0.0, pad8(()), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0), 4)
+    b = model.buoyancy === nothing ? nothing : model.buoyancy.formulation
+    bk, ib, iT, iS, g, α, β = Int32(0), Int32(0), Int32(0), Int32(0), 0.0, 0.0, 0.0
+    if b isa Oceananigans.BuoyancyFormulations.BuoyancyTracer
+        bk, ib = Int32(1), Int32(findfirst(==(:b), names) - 1)
+    elseif b isa Oceananigans.BuoyancyFormulations.SeawaterBuoyancy
+        eos = b.equation_of_state
+        eos isa Oceananigans.BuoyancyFormulations.LinearEquationOfState || unsupported("a nonlinear equation of state")
+        bk, iT, iS = Int32(2), Int32(findfirst(==(:T), names) - 1), Int32(findfirst(==(:S), names) - 1)
+        g, α, β = Float64(b.gravitational_acceleration), Float64(eos.thermal_expansion), Float64(eos.haline_contraction)
+    elseif b !== nothing
+        unsupported("buoyancy $(typeof(b))")
+    end
+    cor = model.coriolis
+    (cor === nothing || cor isa Oceananigans.Coriolis.FPlane) || unsupported("Coriolis $(typeof(cor))")
+    all(f -> f isa Oceananigans.Forcings.zeroforcing |> typeof || f === Oceananigans.Forcings.zeroforcing, values(model.forcing)) || unsupported("user forcing functions")
+    ts = model.timestepper
+    tr_bcs = ntuple(i -> i <= length(names) ? bc_desc(model.tracers[i].boundary_conditions) : bc_desc(nothing), 8)
+    K = model.closure_fields
+    nue_bcs = ntuple(i -> bc_desc(nothing), 4); kap_bcs = ntuple(i -> ntuple(j -> bc_desc(nothing), 8), 4)   # defaults are filled in by the library
+    pHY = model.pressures.pHY′
+    desc = ObModelDesc(gd, kind, Int32(order), Int32(1), Int32(length(closures)), cds, bk, ib, iT, iS, g, α, β,
+                       Int32(cor !== nothing), cor === nothing ? 0.0 : Float64(cor.f), Int32(length(names)),
+                       ts isa RungeKutta3TimeStepper ? Int32(0) : Int32(1), ts isa RungeKutta3TimeStepper ? 0.1 : Float64(ts.χ),
+                       Int32(pHY !== nothing), bc_desc(model.velocities.u.boundary_conditions), bc_desc(model.velocities.v.boundary_conditions),
+                       bc_desc(model.velocities.w.boundary_conditions), bc_desc(model.pressures.pNHS.boundary_conditions),
+                       pHY === nothing ? bc_desc(nothing) : bc_desc(pHY.boundary_conditions), tr_bcs, nue_bcs, kap_bcs)
+    return desc, keep
+end
+
+function create_handle(model)
+    desc, keep = model_desc(model)
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep @ob ob_model_create (Ptr{Cvoid}, Ref{ObModelDesc}, Ref{Ptr{Cvoid}}) model.architecture.ctx Ref(desc) ref
+    h = ref[]
+    bind!(h, 0, model.velocities.u); bind!(h, 1, model.velocities.v); bind!(h, 2, model.velocities.w)
+    bind!(h, 3, model.pressures.pNHS)
+    model.pressures.pHY′ === nothing || bind!(h, 4, model.pressures.pHY′)
+    for (t, c) in enumerate(model.tracers); bind!(h, 16 + t - 1, c); end
+    Gⁿ, G⁻ = model.timestepper.Gⁿ, model.timestepper.G⁻
+    for (n, (a, b)) in enumerate(zip(Gⁿ, G⁻)); bind!(h, 32 + n - 1, a); bind!(h, 48 + n - 1, b); end
+    closures = model.closure === nothing ? () : model.closure isa Tuple ? model.closure : (model.closure,)
+    for (m, c) in enumerate(closures)
+        K = model.closure isa Tuple ? model.closure_fields[m] : model.closure_fields
+        c isa ScalarDiffusivity && continue
+        bind!(h, 64 + m - 1, K.νₑ)
+        if c isa AnisotropicMinimumDissipation
+            for (t, κ) in enumerate(K.κₑ); bind!(h, 80 + (m - 1) * 8 + t - 1, κ); end
+        end
+    end
+    finalizer(_ -> ccall((:ob_model_destroy, lib), Int32, (Ptr{Cvoid},), h), model.timestepper)
+    return h
+end
 
 # ---- model handle cached on the Julia model --------------------------------------------------------------------------
 const HANDLES = IdDict{Any, Ptr{Cvoid}}()
@@ -181,7 +278,16 @@ cache_previous_tendencies!(model::B200Model) = @ob ob_cache_tendencies (Ptr{Cvoi
 compute_pressure_correction!(model::B200Model, Δt) = @ob ob_compute_pressure_correction (Ptr{Cvoid}, Float64) handle(model) Float64(Δt)
 make_pressure_correction!(model::B200Model, Δt) = @ob ob_make_pressure_correction (Ptr{Cvoid}, Float64) handle(model) Float64(Δt)
 
-# fill_halo_regions!(field) for fields that belong to a B200 model: ob_fill_halo(model, field_id, fill_normal_flow_bcs)
-# TimeStepWizard: cell_advection_timescale(model::B200Model) -> ob_cell_advection_timescale(handle, Ref{Float64})
+# fill_halo_regions! of a prognostic / pressure field of a B200 model (fill_halo_regions.jl:20-38)
+function fill_model_halo!(model::B200Model, field_id::Integer; fill_normal_flow_bcs = true)
+    @ob ob_fill_halo (Ptr{Cvoid}, Int32, Int32) handle(model) Int32(field_id) Int32(fill_normal_flow_bcs)
+end
+
+# TimeStepWizard (cell_advection_timescale.jl:14-35): device min-reduction
+function Oceananigans.Advection.cell_advection_timescale(model::B200Model)
+    τ = Ref{Float64}(0)
+    @ob ob_cell_advection_timescale (Ptr{Cvoid}, Ref{Float64}) handle(model) τ
+    return τ[]
+end
 
 end # module
