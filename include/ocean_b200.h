@@ -185,7 +185,7 @@ int32_t ob_make_pressure_correction(ob_model *m, double dtau);
 int32_t ob_time_step_rk3(ob_model *m, double dt, int32_t first);
 int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first);
 /* implementation options (testing / profiling): OB_OPT_TENDENCY_KERNEL = 0 auto, 1 generic one-thread-per-cell kernel,
- * 2 flux-sharing marching kernel */
+ * 2 flux-sharing marching kernel, 3 marching kernel with TMA-staged stencil planes (falls back to 2 where TMA does not apply) */
 #define OB_OPT_TENDENCY_KERNEL 1
 /* OB_OPT_FUSE_PROJECTION = 1 (default): single-device substeps fuse real-copy + correction + p rescale; 0: reference kernel sequence */
 #define OB_OPT_FUSE_PROJECTION 2

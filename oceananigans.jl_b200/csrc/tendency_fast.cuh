@@ -66,19 +66,17 @@ __device__ __forceinline__ void load_line(const T *__restrict__ p, const FastGeo
 // Advective flux in direction ADV of tendency WHICH for the thread whose own point is (i, j, kp) -- kp = k for the
 // x/y fluxes, k+1 for the upper z flux.  pq / pa point at (i, j, kp) of the advected field and of the advecting
 // velocity component ADV.
+// The flux from already-loaded stencil values: s[m] = q at offsets -N .. N-1 along ADV; a[] = the advecting component
+// at offsets -(N-1) .. N-2 along axis WHICH (momentum) or its single value at the face (tracer).
 template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR>
-__device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__restrict__ pa, const FastGeom<T, STR> &g, int kp) {
-    T s[2 * N];
-    load_line<ADV, 2 * N>(pq, g, -N, s);
+__device__ __forceinline__ T flux_from_values(const T (&s)[2 * N], T (&a)[WHICH == 3 ? 1 : 2 * (N - 1)], const FastGeom<T, STR> &g, int kp) {
     if constexpr (WHICH == 3) {
         const T A = ADV == 0 ? g.dy * g.dzC(kp) : ADV == 1 ? g.dx * g.dzC(kp) : g.dx * g.dy;
-        const T ut = __ldg(pa);
+        const T ut = a[0];
         const T cr = weno_sel<T, N, FAST>(s, ut > 0);
         return A * ut * cr;
     } else {
         constexpr int NC = N - 1;
-        T a[2 * NC];
-        load_line<WHICH, 2 * NC>(pa, g, -NC, a);
 #pragma unroll
         for (int m = 0; m < 2 * NC; m++) {
             // Ax_qᶠᶜᶜ = Δy Δzᶜ(k') u, Ay_qᶜᶠᶜ = Δx Δzᶜ(k') v, Az_qᶜᶜᶠ = Δx Δy w, k' the level of the stencil point
@@ -89,6 +87,21 @@ __device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__rest
         const T ut = centered_vals<T, NC>(a);
         const T qr = weno_sel<T, N, FAST>(s, ut > 0);
         return ut * qr;
+    }
+}
+
+template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR>
+__device__ __forceinline__ T fast_flux(const T *__restrict__ pq, const T *__restrict__ pa, const FastGeom<T, STR> &g, int kp) {
+    T s[2 * N];
+    load_line<ADV, 2 * N>(pq, g, -N, s);
+    if constexpr (WHICH == 3) {
+        T a[1] = {__ldg(pa)};
+        return flux_from_values<T, N, FAST, WHICH, ADV, STR>(s, a, g, kp);
+    } else {
+        constexpr int NC = N - 1;
+        T a[2 * NC];
+        load_line<WHICH, 2 * NC>(pa, g, -NC, a);
+        return flux_from_values<T, N, FAST, WHICH, ADV, STR>(s, a, g, kp);
     }
 }
 

@@ -19,7 +19,7 @@
 // L1 bound, so no shared-memory staging of the input tile is needed.
 #pragma once
 #include "tendency.cuh"
-#include "tendency_fast.cuh"
+#include "tendency_tma.cuh"
 
 namespace ob {
 
@@ -128,6 +128,121 @@ static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, in
     return cudaGetLastError();
 }
 
+// ---- TMA-staged variant (tendency_tma.cuh) ------------------------------------------------------------------------
+template <typename T, class S, bool FAST, int TY, int KC, int MINB>
+__global__ void __launch_bounds__(32 * TY, MINB) tendency_march_tma_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M,
+                                                                          int nb, int nkc) {
+    __shared__ T sy[2][TY][32];
+    __shared__ T sv[2][OB_SHARED_CL][TY][32];
+    __shared__ __align__(8) uint64_t bars[3];
+    extern __shared__ __align__(128) unsigned char ring[];
+    const int which = blockIdx.y;
+    const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
+    const int ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+    const int b = blockIdx.x;
+    const int tile_x = b % ntx, tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
+    const int i0 = 1 + tile_x * 31, j0 = 1 + tile_y * (TY - 1);
+    const int i = i0 + (int)threadIdx.x, j = j0 + (int)threadIdx.y;
+    int k0, k1;
+    if (nb == 0) { k0 = 1 + kc * KC; k1 = min(k0 + KC - 1, Nz); }
+    else if (kc == 0) { k0 = 1; k1 = nb; }
+    else if (kc == nkc - 1) { k0 = Nz - nb + 1; k1 = Nz; }
+    else { k0 = nb + 1 + (kc - 1) * KC; k1 = min(k0 + KC - 1, Nz - nb); }
+    if constexpr (S::kind == ADV_WENO) {
+        if (fast_path_ok<T, S::n>(P, k0, k1)) {  // CTA-uniform
+            if (threadIdx.x == 0 && threadIdx.y == 0) {
+                for (int s = 0; s < 3; s++) mbar_init(&bars[s], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            const int t = which - 3;
+            if (P.g.dzc) {
+                if (which == 0) march_tma_body<T, S::n, FAST, 0, TY, KC, true>(P, M, 0, i0, j0, k0, k1, sy, sv, ring, bars);
+                else if (which == 1) march_tma_body<T, S::n, FAST, 1, TY, KC, true>(P, M, 0, i0, j0, k0, k1, sy, sv, ring, bars);
+                else if (which == 2) march_tma_body<T, S::n, FAST, 2, TY, KC, true>(P, M, 0, i0, j0, k0, k1, sy, sv, ring, bars);
+                else march_tma_body<T, S::n, FAST, 3, TY, KC, true>(P, M, t, i0, j0, k0, k1, sy, sv, ring, bars);
+            } else {
+                if (which == 0) march_tma_body<T, S::n, FAST, 0, TY, KC, false>(P, M, 0, i0, j0, k0, k1, sy, sv, ring, bars);
+                else if (which == 1) march_tma_body<T, S::n, FAST, 1, TY, KC, false>(P, M, 0, i0, j0, k0, k1, sy, sv, ring, bars);
+                else if (which == 2) march_tma_body<T, S::n, FAST, 2, TY, KC, false>(P, M, 0, i0, j0, k0, k1, sy, sv, ring, bars);
+                else march_tma_body<T, S::n, FAST, 3, TY, KC, false>(P, M, t, i0, j0, k0, k1, sy, sv, ring, bars);
+            }
+            return;
+        }
+    }
+    if (which == 0) march_body<T, S, FAST, 0, TY, KC>(P, 0, i, j, k0, k1, sy);
+    else if (which == 1) march_body<T, S, FAST, 1, TY, KC>(P, 0, i, j, k0, k1, sy);
+    else if (which == 2) march_body<T, S, FAST, 2, TY, KC>(P, 0, i, j, k0, k1, sy);
+    else march_body<T, S, FAST, 3, TY, KC>(P, which - 3, i, j, k0, k1, sy);
+}
+
+typedef CUresult (*ob_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ob_encode_tiled_fn encode_tiled_fn() {
+    static ob_encode_tiled_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (ob_encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+// true when the TMA variant applies: WENO, (Periodic, Periodic, non-Flat), 16-byte row pitch, one parent shape per field
+template <typename T, class S>
+static bool tma_applicable(const TendP<T> &P) {
+    if (S::kind != ADV_WENO) return false;
+    if (P.g.topo[0] != PERIODIC || P.g.topo[1] != PERIODIC || P.g.topo[2] == FLAT) return false;
+    if ((P.u.sy * sizeof(T)) % 16 != 0) return false;
+    return encode_tiled_fn() != nullptr;
+}
+
+template <typename T, class S, int TY, int KC, int MINB>
+static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch) {
+    if constexpr (S::kind != ADV_WENO) return cudaErrorNotSupported;
+    else {
+        using TT = TmaTile<T, S::n, TY>;
+        const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
+        int nb = 0;
+        long nkc = (Nz + KC - 1) / KC;
+        if (P.g.topo[2] == BOUNDED && Nz > 2 * S::n) { nb = S::n; nkc = 2 + (Nz - 2 * nb + KC - 1) / KC; }
+        const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+        if (ntx * nty * nkc > 2147483647L) return cudaErrorInvalidConfiguration;
+        TmaMaps M;
+        memset(&M, 0, sizeof(M));
+        const cuuint64_t Px = (cuuint64_t)P.u.sy, Py = (cuuint64_t)(P.u.sz / P.u.sy);
+        auto encode = [&](CUtensorMap *m, const Fld<T> &f, bool face_z) -> bool {
+            const cuuint64_t Pz = (cuuint64_t)(Nz + 2 * P.g.H[2] + ((face_z && P.g.topo[2] == BOUNDED) ? 1 : 0));
+            const cuuint64_t dims[3] = {Px, Py, Pz};
+            const cuuint64_t strides[2] = {Px * sizeof(T), Px * Py * sizeof(T)};
+            const cuuint32_t box[3] = {(cuuint32_t)TT::TW, (cuuint32_t)TT::TH, 1u};
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            return encode_tiled_fn()(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)f.p, dims,
+                                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        bool ok = encode(&M.m[0], P.u, false) && encode(&M.m[1], P.v, false) && encode(&M.m[2], P.w, true);
+        for (int t = 0; ok && t < P.ntr; t++) ok = encode(&M.m[3 + t], P.c[t], false);
+        if (!ok) return cudaErrorInvalidValue;
+        dim3 grid((unsigned)(ntx * nty * nkc), 3 + P.ntr), block(32, TY);
+        cudaError_t e;
+        if (fast) {
+            auto kern = tendency_march_tma_kernel<T, S, true, TY, KC, MINB>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, block, TT::SMEM_BYTES, st>>>(P, M, nb, (int)nkc);
+        } else {
+            auto kern = tendency_march_tma_kernel<T, S, false, TY, KC, MINB>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, block, TT::SMEM_BYTES, st>>>(P, M, nb, (int)nkc);
+        }
+        *nlaunch += 1;
+        return cudaGetLastError();
+    }
+}
+
 // mode: 0 auto, 1 generic, 2 marching (3.. = tuning variants when built with -DOB_TI_EXPERIMENT)
 template <typename T, class S>
 static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done) {
@@ -135,8 +250,11 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     done = false;
     if (mode == 1) return cudaSuccess;
     done = true;
+    if (mode == 3) {   // TMA-staged planes (falls back to the LDG marching kernel where TMA does not apply)
+        if (tma_applicable<T, S>(P)) return launch_march_tma<T, S, 8, 32, 4>(P, fast, st, nlaunch);
+        return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch);
+    }
 #ifdef OB_TI_EXPERIMENT
-    if (mode == 3) return launch_march<T, S, 8, 64, 4>(P, fast, st, nlaunch);
     if (mode == 4) return launch_march<T, S, 4, 32, 8>(P, fast, st, nlaunch);
     if (mode == 5) return launch_march<T, S, 16, 32, 2>(P, fast, st, nlaunch);
     if (mode == 6) return launch_march<T, S, 8, 32, 3>(P, fast, st, nlaunch);

@@ -65,6 +65,12 @@ def test_marching_and_generic_tendency_kernels_agree_at_256(big):
     m.compute_tendencies()
     for r, g in zip(ref, m.Gn):
         assert rel_l2(g.interior(), r) <= 1e-13
+    march = [g.interior() for g in m.Gn]
+    m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, 3)   # TMA-staged planes: same arithmetic, bit-identical
+    m.compute_tendencies()
+    for r, g in zip(march, m.Gn):
+        assert np.array_equal(g.interior(), r)
+    m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, 0)
 
 
 def test_poisson_solver_inverts_the_laplacian_at_256(arch):

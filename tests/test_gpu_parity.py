@@ -45,6 +45,11 @@ CONFIGS = {
     # WENO-9 on the interior fast path (buffer 5), WENO-7 periodic
     "weno9_ppp": Config((16, 12, 14), ((0, 1.0),) * 3, "PPP", halo=(5, 5, 5), advection=("weno", 9), closure=[("scalar", 1e-3, 1e-3)], tracers=("c",)),
     "weno7_ppp": Config((16, 12, 14), ((0, 1.0),) * 3, "PPP", halo=(4, 4, 4), advection=("weno", 7), tracers=("c",)),
+    # three x-tiles (odd and even tile origins: the TMA boxes must start on 16-byte boundaries), two y-tiles
+    "wide_ppp": Config((70, 12, 10), ((0, 7.0), (0, 1.2), (0, 1.0)), "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
+                       buoyancy=("tracer",), tracers=("b",)),
+    "wide_stretched": Config((66, 9, 14), ((0, 6.6), (0, 0.9), stretched_faces(14, 1.4)), "PPB", advection=("weno", 5),
+                             closure=[("lilly", 0.16, 1.0, 1.0)], buoyancy=("tracer",), tracers=("b", "c")),
     # Flat x and Flat y (2-D vertical slices)
     "flat_x": Config((1, 16, 12), (None, (0, 1.0), (-1.0, 0.0)), "FPB", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
                      buoyancy=("tracer",), tracers=("b",)),
@@ -94,7 +99,7 @@ def _sync_state_from_oracle(om, bm):
         bm.tracers[n].set_parent(f.data)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["generic", "marching"])
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["generic", "marching", "tma"])
 @pytest.mark.parametrize("division", ["NormalDivision", "BackendOptimizedDivision"])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
 def test_tendencies_match_oracle(arch, name, division, kernel):
@@ -129,6 +134,30 @@ def test_tendencies_match_oracle(arch, name, division, kernel):
             assert rel_l2(f.parent(), om.kappae[m][t].data) <= 1e-13, (name, "kappae", t)
     if om.pHY is not None:
         assert rel_l2(bm.pressures["pHY"].parent(), om.pHY.data) <= 1e-14
+
+
+@pytest.mark.parametrize("ft", ["f64", "f32"])
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_tma_staged_kernel_is_bit_identical_to_the_ldg_marching_kernel(arch, name, ft):
+    """OB_OPT_TENDENCY_KERNEL = 3 stages the x/y stencil planes through shared memory with TMA; the flux arithmetic is
+    the same function, so every tendency must agree bit for bit (configs where TMA does not apply take the LDG path)"""
+    from ocean_b200 import _abi
+    d = dict(CONFIGS[name].__dict__)
+    d["ft"] = np.float64 if ft == "f64" else np.float32
+    cfg = Config(**d)
+    bm = cfg.b200_model(arch)
+    import ocean_b200 as ob
+    ob.set(bm, **cfg.initial_conditions(5))
+    bm.update_state()
+    bm.set_option(_abi.OB_OPT_TENDENCY_KERNEL, 2)
+    bm.compute_tendencies()
+    ref = [g.parent() for g in bm.Gn]
+    for g in bm.Gn:
+        g.set_parent(np.zeros(g.P[::-1], g.grid.FT))
+    bm.set_option(_abi.OB_OPT_TENDENCY_KERNEL, 3)
+    bm.compute_tendencies()
+    for r, g in zip(ref, bm.Gn):
+        assert np.array_equal(r, g.parent()), name
 
 
 @pytest.mark.parametrize("name", sorted(CONFIGS))

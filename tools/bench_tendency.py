@@ -18,7 +18,7 @@ for ft in (np.float64, np.float32):
     cfg = workload_config(n, ft=ft)
     m = cfg.b200_model(arch)
     ob.set(m, **cfg.initial_conditions(2))
-    modes = [(2, "marching"), (1, "generic")] + [(int(x), "variant%s" % x) for x in os.environ.get("OB_VARIANTS", "").split(",") if x]
+    modes = [(2, "marching"), (3, "tma"), (1, "generic")] + [(int(x), "variant%s" % x) for x in os.environ.get("OB_VARIANTS", "").split(",") if x]
     for mode, name in modes:
         m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, mode)
         for _ in range(3):
