@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="device lanes (independent host-resident members) of the e2e leg; 1 = serial only")
     ap.add_argument("--f32", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is --size x size x size whatever N (default: weak, size^3 per GPU)")
     args = ap.parse_args()
@@ -283,10 +284,46 @@ def main():
             e2e_step()
         ke = max(3, min(args.steps, 10))
         ms_e = timed(e2e_step, ke)
-        e2e = {"value": cells_total * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": ms_e / ke, "steps": ke,
+        serial = {"value": cells_total * ke / (ms_e * 1e-3), "ms_per_step": ms_e / ke, "steps": ke,
+                  "what": "one stream: copy in, time_step!, copy out strictly one after the other"}
+        e2e = {"value": serial["value"], "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": ms_e / ke, "steps": ke, "lanes": 1,
                "what": "per step: pinned-host -> device copy of every prognostic field (u,v,w,b parents), time_step! through the C ABI, "
                        "device -> host copy of every prognostic field"}
+        if world == 1 and args.lanes > 1:
+            # host-streamed ensemble (ocean_b200.HostStreamedStepper): `lanes` independent members whose states live in pinned
+            # host memory; every step of every member is upload -> time_step! -> download, the lanes overlap on the device
+            stepper = ob.HostStreamedStepper(lambda a: cfg.b200_model(a), lanes=args.lanes, device=local, first_arch=arch, first_model=model)
+            for m in stepper.models[1:]:
+                ob.set(m, **ic)
+            members = [stepper.new_member() for _ in range(args.lanes)]
+            for lane, mem in enumerate(members):
+                stepper.download(mem, lane)
+
+            def round_robin(nsteps):
+                for s_ in range(nsteps):
+                    mem = members[s_ % args.lanes]
+                    stepper.step(mem, mem, DT)
+
+            round_robin(2 * args.lanes)
+            stepper.synchronize()
+            kp = args.lanes * max(2, min(args.steps, 12) // args.lanes)
+            _abi.call("ob_timer_start", arch.ctx)
+            round_robin(kp)
+            stepper.join_into(0)
+            msp = C.c_double(0)
+            _abi.call("ob_timer_stop", arch.ctx, C.byref(msp))
+            stepper.synchronize()
+            e2e.update({"value": cells_total * kp / (msp.value * 1e-3), "ms_per_step": msp.value / kp, "steps": kp, "lanes": args.lanes,
+                        "serial": serial,
+                        "what": "%d independent ensemble members whose prognostic fields (u,v,w,b parents) live in pinned host memory; every step of "
+                                "every member = pinned-host -> device copy of all of them, time_step! through the C ABI, device -> host copy "
+                                "of all of them; each member has its own device lane (library context = stream), so the copies of one member "
+                                "overlap the kernels of another (ocean_b200.HostStreamedStepper). `serial` is the same loop on one lane."
+                                % args.lanes})
+            for mem in members:
+                mem.free()
+            del stepper
         for p in pinned:
             _abi.call("ob_free_host", arch.ctx, p)
 

@@ -153,6 +153,12 @@ int32_t ob_free_host(ob_ctx *ctx, void *ptr);
 int32_t ob_memcpy_h2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes); /* on_architecture(::B200, ::Array) */
 int32_t ob_memcpy_d2h(ob_ctx *ctx, void *dst, const void *src, size_t bytes); /* on_architecture(::CPU, ::B200Array) */
 int32_t ob_memcpy_d2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes); /* copyto! / device_copy_to! */
+/* stream-ordered copy into PINNED host memory; the host may read dst after ob_sync(ctx) */
+int32_t ob_memcpy_d2h_async(ob_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* later calls on ctx wait (on the device) for everything submitted so far on `other` (same device); the host is not
+ * blocked.  Joins the lanes of a host-streamed ensemble: several contexts = several streams whose copies and kernels
+ * overlap (no reference counterpart: the reference's CPU() path has no host<->device boundary) */
+int32_t ob_stream_wait(ob_ctx *ctx, ob_ctx *other);
 int32_t ob_fill(ob_ctx *ctx, void *ptr, size_t n, int32_t float_type, double value); /* fill! */
 int32_t ob_any_nan(ob_ctx *ctx, const void *ptr, size_t n, int32_t float_type, int32_t *flag); /* NaNChecker */
 /* Diagnostics used by TimeStepWizard (src/Advection/cell_advection_timescale.jl:14-35) */

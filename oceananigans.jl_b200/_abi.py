@@ -80,6 +80,7 @@ PROTOTYPES = {
     "ob_timer_start": [_P], "ob_timer_stop": [_P, C.POINTER(_dbl)],
     "ob_malloc": [_P, _sz, _PP], "ob_free": [_P, _P], "ob_malloc_host": [_P, _sz, _PP], "ob_free_host": [_P, _P],
     "ob_memcpy_h2d": [_P, _P, _P, _sz], "ob_memcpy_d2h": [_P, _P, _P, _sz], "ob_memcpy_d2d": [_P, _P, _P, _sz],
+    "ob_memcpy_d2h_async": [_P, _P, _P, _sz], "ob_stream_wait": [_P, _P],
     "ob_fill": [_P, _P, _sz, _i32, _dbl], "ob_any_nan": [_P, _P, _sz, _i32, C.POINTER(_i32)],
     "ob_cell_advection_timescale": [_P, C.POINTER(_dbl)],
     "ob_model_create": [_P, C.POINTER(ModelDesc), _PP], "ob_model_destroy": [_P],

@@ -186,6 +186,24 @@ extern "C" int32_t ob_memcpy_d2h(ob_ctx *ctx, void *dst, const void *src, size_t
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return OB_OK;
 }
+// stream-ordered device -> pinned-host copy: the host may read dst after ob_sync (or after a later blocking call on ctx)
+extern "C" int32_t ob_memcpy_d2h_async(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return OB_OK;
+}
+// make every later call on `ctx` wait for the work submitted so far on `other` (cudaStreamWaitEvent across contexts of
+// the same device): joins the lanes of a host-streamed ensemble (streaming.py) without blocking the host
+extern "C" int32_t ob_stream_wait(ob_ctx *ctx, ob_ctx *other) {
+    if (!ctx || !other) return fail(OB_ERR_INVALID, "null context");
+    if (ctx->device != other->device) return fail(OB_ERR_INVALID, "ob_stream_wait: contexts on different devices");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, other->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    CUDA_TRY(cudaEventDestroy(ev));   // released once the wait has been satisfied
+    return OB_OK;
+}
 extern "C" int32_t ob_memcpy_d2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return OB_OK;

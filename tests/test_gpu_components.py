@@ -194,3 +194,39 @@ def test_time_step_wizard(arch):
     ob.conjure_time_step_wizard(sim, ob.IterationInterval(2), cfl=0.5, max_change=1.5)
     ob.run(sim)
     assert 1e-4 < sim.dt <= 1e-4 * 1.5 ** 3
+
+
+def test_host_streamed_stepper_matches_resident_stepping(arch):
+    """ocean_b200.HostStreamedStepper: three members living in pinned host memory, each advanced through its own device
+    lane (upload, time_step!, asynchronous download), reproduce resident time stepping bit for bit"""
+    import ctypes as C
+    import ocean_b200 as ob
+    cfg = Config((24, 20, 16), ((0, 2 * np.pi),) * 3, "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
+                 buoyancy=("tracer",), tracers=("b",))
+    ics = [cfg.initial_conditions(seed) for seed in (1, 2, 3)]
+    # resident reference: one model per member, 3 steps each
+    want = []
+    for ic in ics:
+        m = cfg.b200_model(arch)
+        ob.set(m, **ic)
+        for _ in range(3):
+            ob.time_step(m, 1e-3)
+        want.append([f.parent() for f in m.prognostic_fields.values()])
+        del m
+    stepper = ob.HostStreamedStepper(lambda a: cfg.b200_model(a), lanes=3, device=arch.device)
+    members = []
+    for lane, ic in enumerate(ics):
+        ob.set(stepper.models[lane], **ic)
+        mem = stepper.new_member()
+        stepper.download(mem, lane)
+        members.append(mem)
+    for s in range(9):
+        mem = members[s % 3]
+        assert stepper.step(mem, mem, 1e-3) == s % 3
+    stepper.join_into(0)
+    stepper.synchronize()
+    for mem, ref, model in zip(members, want, stepper.models):
+        for p, nb, r, f in zip(mem.ptrs, mem.nbytes, ref, model.prognostic_fields.values()):
+            got = np.frombuffer((C.c_char * nb).from_address(p.value), dtype=r.dtype).reshape(r.shape)
+            assert np.array_equal(got, r), f.name
+        mem.free()
