@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="device lanes (independent host-resident members) of the e2e leg; 1 = serial only")
+    ap.add_argument("--overlap", action="store_true", help="distributed: compute interior tendency tiles while the x halos are in flight (OB_OPT_OVERLAP_HALO)")
     ap.add_argument("--f32", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is --size x size x size whatever N (default: weak, size^3 per GPU)")
     args = ap.parse_args()
@@ -164,6 +165,8 @@ def main():
     cfg = workload_config(n, ft=ft, nx=n if args.strong else n * world)
     nx_local = n // world if args.strong else n
     model = cfg.b200_model(arch)
+    if args.overlap:
+        model.set_option(_abi.OB_OPT_OVERLAP_HALO, 1)
     ic = cfg.initial_conditions(2)
     if world > 1:
         ic = {k: v[:, :, rank * nx_local:(rank + 1) * nx_local] for k, v in ic.items()}

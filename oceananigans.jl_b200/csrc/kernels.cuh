@@ -23,6 +23,7 @@ struct HaloTask {
     T d_lo, d_hi;  // Δ at the boundary (flipped location) for Value/Gradient
 };
 #define OB_MAX_HALO_TASKS 24
+#define OB_HALO_SLOTS 4   // ring depth of the P2P halo staging buffers / flags (ocean_b200.cu: exchange_x_halos_p2p)
 template <typename T>
 struct HaloBatch {
     HaloTask<T> t[OB_MAX_HALO_TASKS];
@@ -117,8 +118,9 @@ __global__ void __launch_bounds__(256) xhalo_unpack_kernel(const __grid_constant
 //           neighbour, then -- once the last block has finished (system-scope fences + a block counter) -- publishes the
 //           exchange's epoch number into the neighbour's flag with a release store;
 //   unpack: waits (acquire loads) until both of its own flags carry the epoch, then copies the staged slabs into the halos.
-// Staging buffers and flags are double-buffered by epoch parity: a neighbour can never be more than one exchange ahead,
-// because its next unpack needs this rank's next push, which is stream-ordered after this rank's current unpack.
+// Staging buffers and flags form a ring of OB_HALO_SLOTS exchanges indexed by the epoch: with at most two exchanges
+// pending per rank (pushes issued, waits deferred behind the interior tendency tiles) a neighbour can never overwrite
+// a slot this rank has not unpacked yet (argument at exchange_x_halos_p2p).
 __device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int ld_acquire_sys(const int *p) { int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 template <typename T>

@@ -695,6 +695,8 @@ struct ob_model {
     int64_t launches = 0;
     bool timing = false;
     int opt_tendency_kernel = 0;  // OB_OPT_TENDENCY_KERNEL: 0 auto, 1 generic (one thread per cell), 2 marching
+    int opt_overlap = 0;          // OB_OPT_OVERLAP_HALO: distributed update_state computes interior tendency tiles while x halos are in flight
+                                  // (off by default: at 256^3 per GPU the split launch costs 0.2 ms/step more than the exchange it hides)
     int opt_fuse = 1;             // OB_OPT_FUSE_PROJECTION: 1 fused single-device projection, 0 the reference kernel sequence
     double phase_ms[PH_COUNT] = {0};
     int64_t phase_calls[PH_COUNT] = {0};
@@ -903,14 +905,14 @@ struct ModelT : ob_model {
     // ---- halos --------------------------------------------------------------------------------------------------
     // fill_halo_regions! for a list of fields: per direction ONE launch for all fields; Bounded directions first,
     // then Periodic (boundary_condition_ordering.jl:17-46,116-142; within a class the reference order is z, y, x).
-    int32_t fill_halos(const std::vector<int> &ids, bool fill_normal) {
+    int32_t fill_halos(const std::vector<int> &ids, bool fill_normal, bool defer_x = false) {
         PhaseScope ps(this, PH_HALO);
         for (int pass = 0; pass < 2; pass++)
             for (int d = 2; d >= 0; d--) {
                 if (g.topo[d] == FLAT) continue;
                 const bool per = g.topo[d] == PERIODIC;
                 if ((pass == 0) == per) continue;
-                if (dist && d == 0) { OB_TRY(exchange_x_halos(ids)); continue; }
+                if (dist && d == 0) { OB_TRY(exchange_x_halos(ids, defer_x)); continue; }
                 size_t pos = 0;
                 while (pos < ids.size()) {
                     HaloBatch<T> B;
@@ -956,10 +958,10 @@ struct ModelT : ob_model {
         size_t cap = 0;
         for (int id = 0; id < 128; id++) if (F[id].exists) cap += (size_t)g.H[0] * F[id].P[1] * F[id].P[2];
         stage_cap = cap;
-        CUDA_TRY(cudaMalloc(&d_stage, sizeof(T) * 4 * cap));
-        CUDA_TRY(cudaMalloc(&d_flags, sizeof(int) * 4));
+        CUDA_TRY(cudaMalloc(&d_stage, sizeof(T) * 2 * OB_HALO_SLOTS * cap));
+        CUDA_TRY(cudaMalloc(&d_flags, sizeof(int) * 2 * OB_HALO_SLOTS));
         CUDA_TRY(cudaMalloc(&d_blockctr, sizeof(unsigned)));
-        CUDA_TRY(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * OB_HALO_SLOTS, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(d_blockctr, 0, sizeof(unsigned), ctx->stream));
         struct Pair { cudaIpcMemHandle_t s, f; };
         Pair mine;
@@ -995,17 +997,37 @@ struct ModelT : ob_model {
         p2p_halo = ok != 0;
         return OB_OK;
     }
-    int32_t exchange_x_halos_p2p(const XHaloBatch<T> &B, size_t total, long maxrows) {
+    // Staging buffers and flags form a ring of OB_HALO_SLOTS exchanges (slot = epoch mod OB_HALO_SLOTS).  An exchange is
+    // a PUSH (never blocks) and a WAIT+UNPACK; with `defer` the wait is queued and issued by finish_x_halos(), so that
+    // kernels which do not read x halos run while the slabs are in flight.  At most two exchanges are ever pending
+    // (prognostic fields, pHY'), and a slot is reused only after this rank has completed the wait of the exchange
+    // OB_HALO_SLOTS - 1 = 3 epochs later, which its neighbours can only have pushed after unpacking the slot's
+    // previous contents (their pushes are stream-ordered after their earlier unpacks, two pending at most).
+    struct PendingX { XHaloBatch<T> B; dim3 grid; int epoch; };
+    std::vector<PendingX> pending_x;
+    int32_t exchange_x_halos_p2p(const XHaloBatch<T> &B, size_t total, long maxrows, bool defer) {
         if (total > stage_cap) return fail(OB_ERR_INVALID, "halo staging buffer too small");
-        const int epoch = ++halo_epoch, par = epoch & 1;
-        // layout: stage[(par*2 + side)*cap], side 0 = west halo data, 1 = east halo data ; flags[par*2 + side]
-        auto stage = [&](T *base, int side) { return base + (size_t)(par * 2 + side) * stage_cap; };
+        if (pending_x.size() >= 2) return fail(OB_ERR_INVALID, "more than two deferred halo exchanges");
+        const int epoch = ++halo_epoch, slot = epoch % OB_HALO_SLOTS;
+        // layout: stage[(slot*2 + side)*cap], side 0 = west halo data, 1 = east halo data ; flags[slot*2 + side]
+        auto stage = [&](T *base, int side) { return base + (size_t)(slot * 2 + side) * stage_cap; };
         dim3 grid(nblk(maxrows * g.H[0], 256), B.count);
-        xhalo_push_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, stage(west_stage, 1), stage(east_stage, 0), west_flags + par * 2 + 1,
-                                                            east_flags + par * 2 + 0, d_blockctr, epoch);
-        xhalo_wait_unpack_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, stage(d_stage, 0), stage(d_stage, 1), d_flags + par * 2 + 0,
-                                                                   d_flags + par * 2 + 1, epoch);
-        launches += 2;
+        xhalo_push_kernel<T><<<grid, 256, 0, ctx->stream>>>(B, stage(west_stage, 1), stage(east_stage, 0), west_flags + slot * 2 + 1,
+                                                            east_flags + slot * 2 + 0, d_blockctr, epoch);
+        launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        pending_x.push_back(PendingX{B, grid, epoch});
+        return defer ? OB_OK : finish_x_halos();
+    }
+    int32_t finish_x_halos() {
+        for (const PendingX &p : pending_x) {
+            const int slot = p.epoch % OB_HALO_SLOTS;
+            xhalo_wait_unpack_kernel<T><<<p.grid, 256, 0, ctx->stream>>>(p.B, d_stage + (size_t)(slot * 2 + 0) * stage_cap,
+                                                                         d_stage + (size_t)(slot * 2 + 1) * stage_cap, d_flags + slot * 2 + 0,
+                                                                         d_flags + slot * 2 + 1, p.epoch);
+            launches += 1;
+        }
+        pending_x.clear();
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
@@ -1013,7 +1035,7 @@ struct ModelT : ob_model {
     // grouped Send/Recv pair per side carrying every field of the batch, ONE unpack launch.  Slabs span the full
     // parent extent in y and z (OneDBuffer, communication_buffers.jl:96-114), so corners stay consistent exactly as
     // with the local periodic copy.
-    int32_t exchange_x_halos(const std::vector<int> &ids) {
+    int32_t exchange_x_halos(const std::vector<int> &ids, bool defer = false) {
         XHaloBatch<T> B;
         B.count = 0; B.H = g.H[0]; B.N = g.N[0];
         size_t total = 0;
@@ -1030,7 +1052,7 @@ struct ModelT : ob_model {
         if (p2p_halo) {
             long mr = 0;
             for (int q = 0; q < B.count; q++) mr = std::max(mr, B.t[q].rows);
-            return exchange_x_halos_p2p(B, total, mr);
+            return exchange_x_halos_p2p(B, total, mr, defer);
         }
         if (4 * total > halo_buf_elems) {
             cudaFree(d_halo_buf);
@@ -1086,14 +1108,17 @@ struct ModelT : ob_model {
         return P;
     }
 
-    int32_t compute_tendencies() override {
+    int32_t compute_tendencies() override { return compute_tendencies_tiles(0, -1, false); }
+    // x tiles [tx_lo, tx_hi) of the marching kernel (tx_hi < 0: every tile), or with `invert` every tile except those
+    int32_t compute_tendencies_tiles(int tx_lo, int tx_hi, bool invert) {
         OB_TRY(need_all());
         PhaseScope ps(this, PH_TENDENCY);
         TendP<T> P = tend_params();
         const int kind = desc.advection_kind;
         const int nb = kind == OB_ADV_WENO ? (desc.advection_order + 1) / 2 : kind == OB_ADV_CENTERED ? desc.advection_order / 2 : 0;
         int nl = 0;
-        cudaError_t e = launch_tendency(P, kind, nb, desc.weno_division == OB_DIV_RCP_NEWTON, opt_tendency_kernel, ctx->stream, ctx->sm_count, &nl);
+        cudaError_t e = launch_tendency(P, kind, nb, desc.weno_division == OB_DIV_RCP_NEWTON, opt_tendency_kernel, ctx->stream, ctx->sm_count, &nl,
+                                        tx_lo, tx_hi, invert ? 1 : 0);
         if (e == cudaErrorNotSupported) return fail(OB_ERR_UNSUPPORTED, "advection scheme kind %d buffer %d has no tendency kernel", kind, nb);
         if (e != cudaSuccess) return fail(OB_ERR_CUDA, "tendency launch: %s", cudaGetErrorString(e));
         launches += nl;
@@ -1123,7 +1148,10 @@ struct ModelT : ob_model {
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
-    int32_t update_hydrostatic_pressure() override {
+    int32_t update_hydrostatic_pressure() override { return hydrostatic_pressure(false); }
+    // interior_x: only the columns i = 1 .. Nx (column-local scan: needs no x halo); the x-halo columns then come from
+    // the neighbours through the halo exchange of pHY', which overwrites them anyway
+    int32_t hydrostatic_pressure(bool interior_x) {
         if (!desc.has_hydrostatic_pressure || g.topo[2] == FLAT) return OB_OK;
         PhaseScope ps(this, PH_HYDRO);
         HydroP<T> P;
@@ -1137,6 +1165,7 @@ struct ModelT : ob_model {
         // surface_kernel_parameters: -H+2 : N+H-1 (interleave_communication_and_computation.jl:85-94); Flat => 1:1
         P.i0 = g.topo[0] == FLAT ? 1 : -g.H[0] + 2; P.i1 = g.topo[0] == FLAT ? 1 : g.N[0] + g.H[0] - 1;
         P.j0 = g.topo[1] == FLAT ? 1 : -g.H[1] + 2; P.j1 = g.topo[1] == FLAT ? 1 : g.N[1] + g.H[1] - 1;
+        if (interior_x) { P.i0 = 1; P.i1 = g.N[0]; }
         dim3 grid(nblk(P.i1 - P.i0 + 1, 64), P.j1 - P.j0 + 1);
         hydrostatic_pressure_kernel<T><<<grid, 64, 0, ctx->stream>>>(P);
         launches++;
@@ -1144,18 +1173,48 @@ struct ModelT : ob_model {
         return OB_OK;
     }
 
+    // Tiles of the marching tendency kernel that read no x halo: every x stencil of the scheme (buffer nb, and the +-1
+    // neighbours of the non-advective terms) of the cells i0 .. i0+30 and of the overlap lane stays inside 1 .. Nx.
+    bool interior_tiles(int &lo, int &hi) const {
+        const int kind = desc.advection_kind;
+        const int nb = std::max(1, kind == OB_ADV_WENO ? (desc.advection_order + 1) / 2 : kind == OB_ADV_CENTERED ? desc.advection_order / 2 : 1);
+        const int ntx = (g.N[0] + OB_TILE_X - 1) / OB_TILE_X;
+        lo = ntx; hi = 0;
+        for (int t = 0; t < ntx; t++) {
+            const int i0 = 1 + t * OB_TILE_X;
+            if (i0 - nb >= 1 && i0 + OB_TILE_X + nb <= g.N[0]) { lo = std::min(lo, t); hi = std::max(hi, t + 1); }
+        }
+        return hi > lo;
+    }
     int32_t update_state() override {
         OB_TRY(need_all());
         std::vector<int> prog = {OB_FIELD_U, OB_FIELD_V, OB_FIELD_W};
         for (int t = 0; t < ntr; t++) prog.push_back(OB_FIELD_TRACER0 + t);
-        OB_TRY(fill_halos(prog, false));
-        OB_TRY(compute_closure_fields());
-        OB_TRY(update_hydrostatic_pressure());
         std::vector<int> aux;
         for (int m = 0; m < ncl; m++) {
             if (F[OB_FIELD_NUE0 + m].exists) aux.push_back(OB_FIELD_NUE0 + m);
             for (int t = 0; t < ntr; t++) if (F[OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t].exists) aux.push_back(OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t);
         }
+        // Distributed, P2P halos, no closure fields: the x-slab pushes are issued first, the tiles that read no x halo are
+        // computed while the slabs cross NVLink, the waits + unpacks come next and the edge tiles last
+        // (interleave_communication_and_computation.jl:36-74, compute_nonhydrostatic_buffer_tendencies.jl)
+        int lo = 0, hi = 0;
+        if (dist && p2p_halo && opt_overlap && aux.empty() && opt_tendency_kernel != 1 && g.topo[0] == PERIODIC && interior_tiles(lo, hi)) {
+            OB_TRY(fill_halos(prog, false, true));
+            if (desc.has_hydrostatic_pressure) {
+                OB_TRY(hydrostatic_pressure(true));
+                OB_TRY(fill_halos({OB_FIELD_PHY}, true, true));
+            }
+            OB_TRY(compute_tendencies_tiles(lo, hi, false));
+            {
+                PhaseScope ps(this, PH_HALO);
+                OB_TRY(finish_x_halos());
+            }
+            return compute_tendencies_tiles(lo, hi, true);   // the edge tiles, one launch
+        }
+        OB_TRY(fill_halos(prog, false));
+        OB_TRY(compute_closure_fields());
+        OB_TRY(update_hydrostatic_pressure());
         if (desc.has_hydrostatic_pressure) aux.push_back(OB_FIELD_PHY);
         if (!aux.empty()) OB_TRY(fill_halos(aux, true));
         return compute_tendencies();
@@ -1408,6 +1467,7 @@ extern "C" int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t valu
     switch (option) {
         case OB_OPT_TENDENCY_KERNEL: m->opt_tendency_kernel = value; return OB_OK;
         case OB_OPT_FUSE_PROJECTION: m->opt_fuse = value; return OB_OK;
+        case OB_OPT_OVERLAP_HALO: m->opt_overlap = value; return OB_OK;
     }
     return fail(OB_ERR_INVALID, "unknown option %d", option);
 }

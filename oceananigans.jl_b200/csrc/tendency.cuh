@@ -9,6 +9,11 @@
 
 namespace ob {
 
+// x extent of the cells one CTA of the marching kernel produces (32 lanes, the last one is the flux-overlap lane); a
+// launch can be restricted to the x tiles [tx_lo, tx_hi) -- the distributed model computes the tiles that do not read
+// x halos while the halo exchange is in flight (interleave_communication_and_computation.jl:36-74)
+#define OB_TILE_X 31
+
 template <typename T>
 struct TendP {
     GridD<T> g;

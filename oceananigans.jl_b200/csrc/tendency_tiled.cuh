@@ -71,14 +71,16 @@ __device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int 
 }
 
 template <typename T, class S, bool FAST, int TY, int KC, int MINB>
-__global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc) {
+__global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc, int tx_lo, int ntx, int skip_lo, int skip_n) {
     __shared__ T sy[2][TY][32];
     __shared__ T sv[2][OB_SHARED_CL][TY][32];
     const int which = blockIdx.y;
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
-    const int ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+    const int nty = (Ny + TY - 2) / (TY - 1);   // x tiles tx_lo .. tx_lo + ntx - 1 of this launch (all of them unless split)
     const int b = blockIdx.x;
-    const int tile_x = b % ntx, tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
+    int tile_x = tx_lo + b % ntx;
+    if (tile_x >= skip_lo) tile_x += skip_n;   // complement launches: every tile except [skip_lo, skip_lo + skip_n)
+    const int tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
     const int i = 1 + tile_x * 31 + (int)threadIdx.x, j = 1 + tile_y * (TY - 1) + (int)threadIdx.y;
     // k-chunks: with a Bounded z and a WENO scheme of buffer nb the first and last chunk are the nb wall-adjacent
     // levels (general path with the fallback chain); every other chunk is interior and takes the fast path
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __g
 }
 
 template <typename T, class S, int TY, int KC, int MINB>
-static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch) {
+static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch, int tx_lo, int tx_hi, int invert) {
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
     int nb = 0;
     long nkc = (Nz + KC - 1) / KC;
@@ -119,11 +121,16 @@ static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, in
         nb = S::n;
         nkc = 2 + (Nz - 2 * nb + KC - 1) / KC;
     }
-    const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+    const long ntx_all = (Nx + OB_TILE_X - 1) / OB_TILE_X, nty = (Ny + TY - 2) / (TY - 1);
+    if (tx_hi < 0 || tx_hi > ntx_all) tx_hi = (int)ntx_all;
+    int skip_lo = 1 << 30, skip_n = 0;
+    long ntx = tx_hi - tx_lo;
+    if (invert) { skip_lo = tx_lo; skip_n = tx_hi - tx_lo; ntx = ntx_all - skip_n; tx_lo = 0; }
+    if (ntx <= 0) return cudaSuccess;
     if (ntx * nty * nkc > 2147483647L) return cudaErrorInvalidConfiguration;
     dim3 grid((unsigned)(ntx * nty * nkc), 3 + P.ntr), block(32, TY);
-    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc);
-    else tendency_march_kernel<T, S, false, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc);
+    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n);
+    else tendency_march_kernel<T, S, false, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n);
     *nlaunch += 1;
     return cudaGetLastError();
 }
@@ -131,16 +138,18 @@ static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, in
 // ---- TMA-staged variant (tendency_tma.cuh) ------------------------------------------------------------------------
 template <typename T, class S, bool FAST, int TY, int KC, int MINB>
 __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_tma_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M,
-                                                                          int nb, int nkc) {
+                                                                          int nb, int nkc, int tx_lo, int ntx, int skip_lo, int skip_n) {
     __shared__ T sy[2][TY][32];
     __shared__ T sv[2][OB_SHARED_CL][TY][32];
     __shared__ __align__(8) uint64_t bars[3];
     extern __shared__ __align__(128) unsigned char ring[];
     const int which = blockIdx.y;
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
-    const int ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+    const int nty = (Ny + TY - 2) / (TY - 1);   // x tiles tx_lo .. tx_lo + ntx - 1 of this launch (all of them unless split)
     const int b = blockIdx.x;
-    const int tile_x = b % ntx, tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
+    int tile_x = tx_lo + b % ntx;
+    if (tile_x >= skip_lo) tile_x += skip_n;   // complement launches: every tile except [skip_lo, skip_lo + skip_n)
+    const int tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
     const int i0 = 1 + tile_x * 31, j0 = 1 + tile_y * (TY - 1);
     const int i = i0 + (int)threadIdx.x, j = j0 + (int)threadIdx.y;
     int k0, k1;
@@ -199,7 +208,7 @@ static bool tma_applicable(const TendP<T> &P) {
 }
 
 template <typename T, class S, int TY, int KC, int MINB>
-static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch) {
+static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch, int tx_lo, int tx_hi, int invert) {
     if constexpr (S::kind != ADV_WENO) return cudaErrorNotSupported;
     else {
         using TT = TmaTile<T, S::n, TY>;
@@ -207,7 +216,12 @@ static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st
         int nb = 0;
         long nkc = (Nz + KC - 1) / KC;
         if (P.g.topo[2] == BOUNDED && Nz > 2 * S::n) { nb = S::n; nkc = 2 + (Nz - 2 * nb + KC - 1) / KC; }
-        const long ntx = (Nx + 30) / 31, nty = (Ny + TY - 2) / (TY - 1);
+        const long ntx_all = (Nx + OB_TILE_X - 1) / OB_TILE_X, nty = (Ny + TY - 2) / (TY - 1);
+        if (tx_hi < 0 || tx_hi > ntx_all) tx_hi = (int)ntx_all;
+        int skip_lo = 1 << 30, skip_n = 0;
+        long ntx = tx_hi - tx_lo;
+        if (invert) { skip_lo = tx_lo; skip_n = tx_hi - tx_lo; ntx = ntx_all - skip_n; tx_lo = 0; }
+        if (ntx <= 0) return cudaSuccess;
         if (ntx * nty * nkc > 2147483647L) return cudaErrorInvalidConfiguration;
         TmaMaps M;
         memset(&M, 0, sizeof(M));
@@ -231,12 +245,12 @@ static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st
             auto kern = tendency_march_tma_kernel<T, S, true, TY, KC, MINB>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT::SMEM_BYTES);
             if (e != cudaSuccess) return e;
-            kern<<<grid, block, TT::SMEM_BYTES, st>>>(P, M, nb, (int)nkc);
+            kern<<<grid, block, TT::SMEM_BYTES, st>>>(P, M, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n);
         } else {
             auto kern = tendency_march_tma_kernel<T, S, false, TY, KC, MINB>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT::SMEM_BYTES);
             if (e != cudaSuccess) return e;
-            kern<<<grid, block, TT::SMEM_BYTES, st>>>(P, M, nb, (int)nkc);
+            kern<<<grid, block, TT::SMEM_BYTES, st>>>(P, M, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n);
         }
         *nlaunch += 1;
         return cudaGetLastError();
@@ -245,22 +259,22 @@ static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st
 
 // mode: 0 auto, 1 generic, 2 marching (3.. = tuning variants when built with -DOB_TI_EXPERIMENT)
 template <typename T, class S>
-static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done) {
+static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done, int tx_lo, int tx_hi, int invert) {
     (void)sm_count;
     done = false;
     if (mode == 1) return cudaSuccess;
     done = true;
     if (mode == 3) {   // TMA-staged planes (falls back to the LDG marching kernel where TMA does not apply)
-        if (tma_applicable<T, S>(P)) return launch_march_tma<T, S, 8, 32, 4>(P, fast, st, nlaunch);
-        return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch);
+        if (tma_applicable<T, S>(P)) return launch_march_tma<T, S, 8, 32, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
+        return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
     }
 #ifdef OB_TI_EXPERIMENT
-    if (mode == 4) return launch_march<T, S, 4, 32, 8>(P, fast, st, nlaunch);
-    if (mode == 5) return launch_march<T, S, 16, 32, 2>(P, fast, st, nlaunch);
-    if (mode == 6) return launch_march<T, S, 8, 32, 3>(P, fast, st, nlaunch);
-    if (mode == 7) return launch_march<T, S, 8, 16, 4>(P, fast, st, nlaunch);
+    if (mode == 4) return launch_march<T, S, 4, 32, 8>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
+    if (mode == 5) return launch_march<T, S, 16, 32, 2>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
+    if (mode == 6) return launch_march<T, S, 8, 32, 3>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
+    if (mode == 7) return launch_march<T, S, 8, 16, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
 #endif
-    return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch);
+    return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
 }
 
 }  // namespace ob
