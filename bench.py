@@ -31,9 +31,11 @@ TWO_PI = 2 * np.pi
 DT = 1e-3
 
 
-def workload_config(n, ft=np.float64, nx=None):
+def workload_config(n, ft=np.float64, nx=None, ny=None, nz=None):
+    """configs[1] of BASELINE.json on an nx x ny x nz grid of cubic cells (Δ = 2π/n)"""
     from helpers import Config
-    return Config((nx or n, n, n), ((0, TWO_PI * (nx or n) / n), (0, TWO_PI), (0, TWO_PI)), "PPP", advection=("weno", 5),
+    nx, ny, nz = nx or n, ny or n, nz or n
+    return Config((nx, ny, nz), ((0, TWO_PI * nx / n), (0, TWO_PI * ny / n), (0, TWO_PI * nz / n)), "PPP", advection=("weno", 5),
                   closure=[("scalar", 1e-3, 1e-3)], buoyancy=("tracer",), tracers=("b",), ft=ft)
 
 
@@ -132,6 +134,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", type=int, default=256, help="cells per side per GPU")
+    ap.add_argument("--ny", type=int, default=0, help="cells in y (default: --size); configs[4] is --size 256 --ny 2048 --nz 512 on 8 GPUs")
+    ap.add_argument("--nz", type=int, default=0, help="cells in z (default: --size)")
     ap.add_argument("--ref-size", type=int, default=96)
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
@@ -162,16 +166,17 @@ def main():
         arch = ob.B200(local)
     ft = np.float32 if args.f32 else np.float64
     n = args.size
-    cfg = workload_config(n, ft=ft, nx=n if args.strong else n * world)
+    ny, nz = args.ny or n, args.nz or n
+    cfg = workload_config(n, ft=ft, nx=n if args.strong else n * world, ny=ny, nz=nz)
     nx_local = n // world if args.strong else n
     model = cfg.b200_model(arch)
     if args.overlap:
         model.set_option(_abi.OB_OPT_OVERLAP_HALO, 1)
-    ic = cfg.initial_conditions(2)
-    if world > 1:
-        ic = {k: v[:, :, rank * nx_local:(rank + 1) * nx_local] for k, v in ic.items()}
+    # synthetic random-perturbation initial conditions, generated per rank at the local size (a global array of
+    # configs[4] would be 17 GB per field)
+    ic = workload_config(n, ft=ft, nx=nx_local, ny=ny, nz=nz).initial_conditions(2 + rank)
     ob.set(model, **ic)
-    cells_local = nx_local * n * n
+    cells_local = nx_local * ny * nz
     cells_total = cells_local * world
 
     def barrier():
@@ -340,7 +345,8 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                 "dtype": "f32" if args.f32 else "f64", "data": "synthetic",
                 "config": {"workload": "3D triply-periodic NonhydrostaticModel, WENO-5, BuoyancyTracer, ScalarDiffusivity, %dx%dx%d %s "
-                                       "(BASELINE.json configs[1]; %dx%dx%d per GPU, slab-x)" % (nx_local * world, n, n, "Float32" if args.f32 else "Float64", nx_local, n, n),
+                                       "(BASELINE.json configs[1]%s; %dx%dx%d per GPU, slab-x)" % (nx_local * world, ny, nz, "Float32" if args.f32 else "Float64",
+                                                                                              " on the grid of configs[4]" if (ny, nz) != (n, n) else "", nx_local, ny, nz),
                            "timestepper": "RK3 (3 stages, 3 pressure solves per step)", "dt": DT, "halo": 3,
                            "l2": "inputs larger than L2: every kernel streams >= 4 parent arrays of %.0f MB" % (model.velocities["u"].nbytes / 1e6),
                            "parallelism": "slab-x%d" % world},

@@ -257,13 +257,15 @@ static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st
     }
 }
 
-// mode: 0 auto, 1 generic, 2 marching (3.. = tuning variants when built with -DOB_TI_EXPERIMENT)
+// mode: 0 auto, 1 generic, 2 marching (LDG), 3 marching with TMA-staged planes (4.. = tuning variants when built with -DOB_TI_EXPERIMENT)
 template <typename T, class S>
 static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done, int tx_lo, int tx_hi, int invert) {
     (void)sm_count;
     done = false;
     if (mode == 1) return cudaSuccess;
     done = true;
+    // auto: Float32 takes the TMA-staged variant (measured 4.5 % faster at 256^3), Float64 the LDG one (2 % faster)
+    if (mode == 0 && sizeof(T) == 4 && S::kind == ADV_WENO) mode = 3;
     if (mode == 3) {   // TMA-staged planes (falls back to the LDG marching kernel where TMA does not apply)
         if (tma_applicable<T, S>(P)) return launch_march_tma<T, S, 8, 32, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
         return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
