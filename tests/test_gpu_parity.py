@@ -171,6 +171,38 @@ def test_one_step_f64(arch, name):
     _compare(om, bm, 1e-11, p_factor=P_ILL_CONDITIONED.get(name, 1.0))
 
 
+def _golden_cases():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import GOLDEN
+    return [(n, s) for n, (dt, snaps) in sorted(GOLDEN.items()) for s in snaps]
+
+
+@pytest.mark.parametrize("name,steps", _golden_cases())
+def test_against_golden_vectors(arch, name, steps):
+    """the CUDA path against the frozen vectors of tests/golden/ (oracle outputs committed with their generator): sampled
+    interior points to the north-star tolerance (1e-11 after 1 step, 1e-9 after 10), interior sums as a whole-array check"""
+    import os
+    import ocean_b200 as ob
+    from make_golden import GOLDEN, SEED
+    dt, _ = GOLDEN[name]
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg = CONFIGS[name]
+    bm = cfg.b200_model(arch)
+    ob.set(bm, **cfg.initial_conditions(SEED))
+    for _ in range(steps):
+        ob.time_step(bm, dt)
+    tol = 1e-11 if steps == 1 else 1e-9
+    fields = dict(bm.velocities); fields["pNHS"] = bm.pressures["pNHS"]; fields.update(bm.tracers)
+    for fname, f in fields.items():
+        a = f.interior().astype(np.float64)
+        t = tol * (P_ILL_CONDITIONED.get(name, 1.0) if fname == "pNHS" else 1.0)
+        ref = g["s%d__%s__sub" % (steps, fname)]
+        assert rel_l2(a[::2, ::2, ::2], ref) <= t, (name, fname, rel_l2(a[::2, ::2, ::2], ref))
+        sums = g["s%d__%s__sum" % (steps, fname)]
+        assert abs((a * a).sum() - sums[1]) <= 1e-8 * max(sums[1], 1e-300) + 1e-300, (name, fname, "sum of squares")
+
+
 @pytest.mark.parametrize("name", ["ppp_weno5", "les_amd", "stretched", "readme_2d"])
 def test_ten_steps_f64(arch, name):
     import ocean_b200 as ob
