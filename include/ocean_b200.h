@@ -107,6 +107,8 @@ typedef struct {
     double Cnu;             /* AMD Poincaré constants */
     double Ckappa[OB_MAX_TRACERS];
     int32_t amd_has_cb;
+    int32_t vertically_implicit; /* ScalarDiffusivity(VerticallyImplicitTimeDiscretization(); ...) (scalar_diffusivity.jl:113-137):
+                                  * z-Bounded grids only; the substeps then run implicit_step! on every prognostic field */
 } ob_closure_desc;
 
 /* NonhydrostaticModel(grid; advection, closure, buoyancy, coriolis, tracers, timestepper)

@@ -65,6 +65,7 @@ struct ClosureD {
     T Cnu;
     T Ckappa[OB_MAXTR];
     int amd_has_cb;
+    int vi;   // VerticallyImplicitTimeDiscretization: interior vertical fluxes are elided from the explicit tendencies
 };
 
 template <typename T>

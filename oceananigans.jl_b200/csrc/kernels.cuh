@@ -167,6 +167,113 @@ __global__ void __launch_bounds__(256) xhalo_wait_unpack_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// implicit_step! of every prognostic field (vertically_implicit_diffusion_solver.jl:60-136,196-225): the tridiagonal
+// system (1 - Δτ ∂z κ ∂z) ϕ = ϕ★ of each column, coefficients from the ivd_* functions (periphery-aware), solved in
+// place by the sweep of solve_batched_tridiagonal_system_z! (batched_tridiagonal_solver.jl:211-243).  One thread per
+// column, x fastest (coalesced); blockIdx.y = field.  inactive_cell / inactive_node / peripheral_node:
+// src/Grids/inactive_node.jl:43-165.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct IvdP {
+    GridD<T> g;
+    int nfields, ntr, nvi;
+    Fld<T> f[3 + OB_MAXTR];
+    T nu[OB_MAXCL];                 // the vertically-implicit closures only, in closure order
+    T kappa[OB_MAXCL][OB_MAXTR];
+    T dt;
+    T *scratch;                     // nfields x (Nz+1) x Ny x Nx
+};
+template <typename T>
+struct IvdCol {
+    const IvdP<T> &P;
+    int which, lx, ly, lz, i, j;
+    __device__ __forceinline__ bool inactive_cell(int a, int b, int c) const {
+        const GridD<T> &g = P.g;
+        return ((g.topo[0] == BOUNDED) & ((a < 1) | (a > g.N[0]))) | ((g.topo[1] == BOUNDED) & ((b < 1) | (b > g.N[1]))) |
+               ((g.topo[2] == BOUNDED) & ((c < 1) | (c > g.N[2])));
+    }
+    // any: peripheral_node (OR over the cells around the node); !any: inactive_node (AND)
+    __device__ __forceinline__ bool node(int k, int fz, bool any) const {
+        bool r = !any;
+        for (int a = 0; a <= lx; a++)
+            for (int b = 0; b <= ly; b++)
+                for (int c = 0; c <= fz; c++) {
+                    const bool v = inactive_cell(i - a, j - b, k - c);
+                    r = any ? (r | v) : (r & v);
+                }
+        return r;
+    }
+    __device__ __forceinline__ T coef(int m) const { return which < 3 ? P.nu[m] : P.kappa[m][which - 3]; }
+    __device__ __forceinline__ T upper(int k) const {
+        T sum = 0;
+        for (int m = 0; m < P.nvi; m++) {
+            T d;
+            if (!lz) {
+                const T kap = node(k + 1, 1, false) ? T(0) : coef(m);
+                d = -P.dt * kap * (P.g.rdzC(k) * P.g.rdzF(k + 1));
+                if (node(k + 1, 1, true)) d = 0;
+            } else {
+                const T nu = node(k, 0, false) ? T(0) : coef(m);
+                d = -P.dt * nu * (P.g.rdzC(k) * P.g.rdzF(k));
+                if (node(k, 0, true)) d = 0;
+            }
+            sum = m == 0 ? d : sum + d;
+        }
+        return sum;
+    }
+    __device__ __forceinline__ T lower(int kk) const {
+        T sum = 0;
+        for (int m = 0; m < P.nvi; m++) {
+            T d;
+            if (!lz) {
+                const int k = kk + 1;
+                const T kap = node(k, 1, false) ? T(0) : coef(m);
+                d = -P.dt * kap * (P.g.rdzC(k) * P.g.rdzF(k));
+            } else {
+                const int kp = kk + 2;
+                const T nu = node(kp - 1, 0, false) ? T(0) : coef(m);
+                d = -P.dt * nu * (P.g.rdzC(kp) * P.g.rdzF(kp - 1));
+            }
+            if (node(kk, 0, true)) d = 0;
+            sum = m == 0 ? d : sum + d;
+        }
+        return sum;
+    }
+    __device__ __forceinline__ T diag(int k) const { return T(1) - P.dt * T(0) - upper(k) - lower(k - 1); }
+};
+template <typename T>
+__global__ void __launch_bounds__(128) ivd_solve_kernel(const __grid_constant__ IvdP<T> P) {
+    const int n = blockIdx.y;
+    const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
+    const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= (long)Nx * Ny) return;
+    const int i = 1 + (int)(col % Nx), j = 1 + (int)(col / Nx);
+    const int which = n < 3 ? n : 3 + (n - 3);
+    const IvdCol<T> C{P, which, which == 0, which == 1, which == 2, i, j};
+    const Fld<T> &f = P.f[n];
+    T *t = P.scratch + (size_t)n * (Nz + 1) * Ny * Nx + col;   // t[k] at t[k * Nx*Ny]
+    const size_t ts = (size_t)Nx * Ny;
+    const T tiny = 10 * (sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-07));
+    T beta = C.diag(1);
+    T prev = f(i, j, 1) / beta;
+    f(i, j, 1) = prev;
+    for (int k = 2; k <= Nz; k++) {
+        const T cm = C.upper(k - 1), bk = C.diag(k), am = C.lower(k - 1);
+        const T tk = cm / beta;
+        t[k * ts] = tk;
+        beta = sub_rn(bk, mul_rn(am, tk));
+        const T fk = f(i, j, k);
+        const T cand = sub_rn(fk, mul_rn(am, prev)) / beta;
+        prev = fabs(beta) > tiny ? cand : fk;
+        f(i, j, k) = prev;
+    }
+    for (int k = Nz - 1; k >= 1; k--) {
+        prev = sub_rn(f(i, j, k), mul_rn(t[(k + 1) * ts], prev));
+        f(i, j, k) = prev;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K7: constant-flux boundary contributions (compute_flux_bcs.jl:113-162): Gc[1] += flux*A/V ; Gc[N] -= flux*A/V
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>

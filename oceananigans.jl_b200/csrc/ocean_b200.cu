@@ -778,7 +778,7 @@ struct ModelT : ob_model {
             cudaIpcCloseMemHandle(west_stage); cudaIpcCloseMemHandle(west_flags);
             if (east != west) { cudaIpcCloseMemHandle(east_stage); cudaIpcCloseMemHandle(east_flags); }
         }
-        cudaFree(d_stage); cudaFree(d_flags); cudaFree(d_blockctr);
+        cudaFree(d_stage); cudaFree(d_flags); cudaFree(d_blockctr); cudaFree(d_ivd);
         delete solver;
         for (auto e : pool) cudaEventDestroy(e);
     }
@@ -862,6 +862,13 @@ struct ModelT : ob_model {
             if (g.topo[k] != FLAT && g.H[k] < 1) return fail(OB_ERR_INVALID, "halo must be >= 1");
             if (g.topo[k] == PERIODIC && g.N[k] < g.H[k]) return fail(OB_ERR_INVALID, "periodic size smaller than halo");
         }
+        for (int m = 0; m < d->n_closures; m++)
+            if (d->closures[m].vertically_implicit) {
+                if (d->closures[m].kind != OB_CLOSURE_SCALAR_DIFFUSIVITY)
+                    return fail(OB_ERR_UNSUPPORTED, "VerticallyImplicitTimeDiscretization is implemented for ScalarDiffusivity only");
+                if (g.topo[2] != BOUNDED)
+                    return fail(OB_ERR_INVALID, "VerticallyImplicitTimeDiscretization can only be specified on grids that are Bounded in the z-direction");
+            }
         setup_field(OB_FIELD_U, 1, 0, 0, d->bcs_u);
         setup_field(OB_FIELD_V, 0, 1, 0, d->bcs_v);
         setup_field(OB_FIELD_W, 0, 0, 1, d->bcs_w);
@@ -1097,6 +1104,7 @@ struct ModelT : ob_model {
         for (int m = 0; m < ncl; m++) {
             const ob_closure_desc &c = desc.closures[m];
             ClosureD<T> &o = P.cl[m];
+            o.vi = c.vertically_implicit ? 1 : 0;
             o.kind = c.kind; o.nu = (T)c.nu; o.cs = (T)c.cs; o.cb = (T)c.cb; o.lilly = c.lilly; o.Cnu = (T)c.Cnu; o.amd_has_cb = c.amd_has_cb;
             for (int t = 0; t < OB_MAXTR; t++) { o.kappa[t] = (T)c.kappa[t]; o.Pr[t] = (T)c.Pr[t]; o.Ckappa[t] = (T)c.Ckappa[t]; }
             if (c.kind != OB_CLOSURE_SCALAR_DIFFUSIVITY) P.nue[m] = fld(OB_FIELD_NUE0 + m);
@@ -1313,18 +1321,47 @@ struct ModelT : ob_model {
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
+    // implicit_step! of every prognostic field after its explicit update (nonhydrostatic_rk3_substep.jl:47-56,
+    // nonhydrostatic_ab2_step.jl:41-50): one launch, blockIdx.y = field (the solves are column-local and independent)
+    T *d_ivd = nullptr;
+    int32_t implicit_step(double dtau) {
+        int nvi = 0;
+        for (int m = 0; m < ncl; m++) nvi += desc.closures[m].vertically_implicit ? 1 : 0;
+        if (nvi == 0) return OB_OK;
+        PhaseScope ps(this, PH_UPDATE);
+        IvdP<T> P;
+        memset(&P, 0, sizeof(P));
+        P.g = g; P.nfields = 3 + ntr; P.ntr = ntr; P.nvi = 0; P.dt = (T)dtau;
+        for (int m = 0; m < ncl; m++) {
+            if (!desc.closures[m].vertically_implicit) continue;
+            P.nu[P.nvi] = (T)desc.closures[m].nu;
+            for (int t = 0; t < OB_MAXTR; t++) P.kappa[P.nvi][t] = (T)desc.closures[m].kappa[t];
+            P.nvi++;
+        }
+        for (int n = 0; n < P.nfields; n++) P.f[n] = fld(n < 3 ? n : OB_FIELD_TRACER0 + (n - 3));
+        const size_t cols = (size_t)g.N[0] * g.N[1];
+        if (!d_ivd) CUDA_TRY(cudaMalloc(&d_ivd, sizeof(T) * (size_t)P.nfields * (g.N[2] + 1) * cols));
+        P.scratch = d_ivd;
+        dim3 grid(nblk((long)cols, 128), P.nfields);
+        ivd_solve_kernel<T><<<grid, 128, 0, ctx->stream>>>(P);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
     int32_t rk3_substep(double dt, double gamma, double zeta, int has_zeta, bool cache) override {
         OB_TRY(need_all());
         OB_TRY(launch_update(has_zeta ? 1 : 0, dt, gamma, zeta, 0, cache));
         // Δτ = convert(FT, Δt * (γ + ζ)) with γ, ζ of the grid float type (runge_kutta_3.jl:186-187)
         T gz = has_zeta ? (T)((T)gamma + (T)zeta) : (T)gamma;
         double dtau = (double)(T)(dt * (double)gz);
+        OB_TRY(implicit_step(dtau));
         return project(dtau);
     }
     int32_t ab2_step(double dt, double chi, bool cache) override {
         OB_TRY(need_all());
         OB_TRY(launch_update(2, dt, 0, 0, chi, cache));
         double dtau = (double)(T)dt;
+        OB_TRY(implicit_step(dtau));
         return project(dtau);
     }
     int32_t cache_tendencies() override {

@@ -136,13 +136,25 @@ template <typename T> struct VFlux {
     __device__ VFlux(const TendP<T> &P_, int m) : P(P_), G{P_}, nu{P_, m} {}
     __device__ __forceinline__ T ux(int i, int j, int k) const { return (DYC * DZC(k)) * (-2 * (nu.ccc(i, j, k) * G.S11(i, j, k))); }
     __device__ __forceinline__ T uy(int i, int j, int k) const { return (DXF * DZC(k)) * (-2 * (nu.ffc(i, j, k) * G.S12(i, j, k))); }
-    __device__ __forceinline__ T uz(int i, int j, int k) const { return (DXF * DYC) * (-2 * (nu.fcf(i, j, k) * G.S13(i, j, k))); }
+    // VerticallyImplicitTimeDiscretization on a z-Bounded grid (abstract_scalar_diffusivity_closure.jl:270-312): away from the
+    // boundary faces k = 1, Nz+1 only the part the tridiagonal solve does not contain stays explicit
+    __device__ __forceinline__ bool elide(int k) const { return P.cl[nu.m].vi && P.g.topo[2] == BOUNDED && !((k == 1) | (k == P.g.N[2] + 1)); }
+    __device__ __forceinline__ T uz(int i, int j, int k) const {
+        if (elide(k)) return (DXF * DYC) * (-(nu.fcf(i, j, k) * G.dx_w(i, j, k)));
+        return (DXF * DYC) * (-2 * (nu.fcf(i, j, k) * G.S13(i, j, k)));
+    }
     __device__ __forceinline__ T vx(int i, int j, int k) const { return (DYF * DZC(k)) * (-2 * (nu.ffc(i, j, k) * G.S12(i, j, k))); }
     __device__ __forceinline__ T vy(int i, int j, int k) const { return (DXC * DZC(k)) * (-2 * (nu.ccc(i, j, k) * G.S22(i, j, k))); }
-    __device__ __forceinline__ T vz(int i, int j, int k) const { return (DXC * DYF) * (-2 * (nu.cff(i, j, k) * G.S23(i, j, k))); }
+    __device__ __forceinline__ T vz(int i, int j, int k) const {
+        if (elide(k)) return (DXC * DYF) * (-(nu.cff(i, j, k) * G.dy_w(i, j, k)));
+        return (DXC * DYF) * (-2 * (nu.cff(i, j, k) * G.S23(i, j, k)));
+    }
     __device__ __forceinline__ T wx(int i, int j, int k) const { return (DYC * DZF(k)) * (-2 * (nu.fcf(i, j, k) * G.S13(i, j, k))); }
     __device__ __forceinline__ T wy(int i, int j, int k) const { return (DXC * DZF(k)) * (-2 * (nu.cff(i, j, k) * G.S23(i, j, k))); }
-    __device__ __forceinline__ T wz(int i, int j, int k) const { return (DXC * DYC) * (-2 * (nu.ccc(i, j, k) * G.S33(i, j, k))); }
+    __device__ __forceinline__ T wz(int i, int j, int k) const {
+        if (elide(k)) return T(0);
+        return (DXC * DYC) * (-2 * (nu.ccc(i, j, k) * G.S33(i, j, k)));
+    }
 };
 
 #define DELTA_(hi, lo, d) (P.g.topo[d] == FLAT ? T(0) : ((hi) - (lo)))
@@ -179,6 +191,7 @@ template <typename T, int D> __device__ __forceinline__ T qflux(const TendP<T> &
     shift<D>(a, b, cc, -1);
     T rd = D == 0 ? P.g.rdx : D == 1 ? P.g.rdy : P.g.rdzF(k);
     T A = D == 0 ? DYC * DZC(k) : D == 1 ? DXC * DZC(k) : DXC * DYC;
+    if (D == 2 && P.cl[m].vi && P.g.topo[2] == BOUNDED && !((k == 1) | (k == P.g.N[2] + 1))) return T(0);   // diffusive_flux_z(::VITD)
     T dc = (P.g.topo[D] == FLAT ? T(0) : c.ld(i, j, k) - c.ld(a, b, cc)) * rd;
     return A * (-kap<T, D>(P, m, t, i, j, k) * dc);
 }

@@ -346,6 +346,7 @@ template <typename T, int N>
 __device__ __forceinline__ bool fast_path_ok(const TendP<T> &P, int k0, int k1) {
     const GridD<T> &g = P.g;
     if (g.topo[0] != PERIODIC || g.topo[1] != PERIODIC) return false;
+    for (int m = 0; m < P.ncl; m++) if (P.cl[m].vi) return false;   // vertically-implicit closures: generic flux functions
     if (P.u.sz * (long)(g.N[2] + 2 * g.H[2] + 1) >= 2147483647L) return false;  // 32-bit element offsets
     if (g.topo[2] == PERIODIC) return true;
     if (g.topo[2] == FLAT) return false;

@@ -106,7 +106,7 @@ end
 struct ObBcDesc; kind::NTuple{6, Int32}; value::NTuple{6, Float64}; end
 struct ObClosureDesc
     kind::Int32; nu::Float64; kappa::NTuple{8, Float64}; cs::Float64; lilly::Int32; cb::Float64; Pr::NTuple{8, Float64}
-    Cnu::Float64; Ckappa::NTuple{8, Float64}; amd_has_cb::Int32
+    Cnu::Float64; Ckappa::NTuple{8, Float64}; amd_has_cb::Int32; vertically_implicit::Int32
 end
 struct ObModelDesc
     grid::ObGridDesc
@@ -161,17 +161,18 @@ bc_desc(::Nothing) = ObBcDesc(ntuple(_ -> Int32(0), 6), ntuple(_ -> 0.0, 6))
 pad8(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, 8)
 closure_desc(c::ScalarDiffusivity, names) =
     (c.ν isa Number && all(κ -> κ isa Number, values(c.κ))) ?
-        ObClosureDesc(1, Float64(c.ν), pad8(values(c.κ)), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0) : unsupported("a function-valued diffusivity")
+        ObClosureDesc(1, Float64(c.ν), pad8(values(c.κ)), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0,
+                      Int32(Oceananigans.TimeSteppers.time_discretization(c) isa VerticallyImplicitTimeDiscretization)) : unsupported("a function-valued diffusivity")
 function closure_desc(c::Smagorinsky, names)
     coeff = c.coefficient
     lilly = !(coeff isa Number)
     cs = lilly ? coeff.smagorinsky : coeff
     cb = lilly ? coeff.reduction_factor : 0.0
     (cs isa Number) || unsupported("DynamicSmagorinsky")
-    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0)
+    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0, 0)
 end
 closure_desc(c::AnisotropicMinimumDissipation, names) =
-    ObClosureDesc(3, 0.0, pad8(()), 0.0, 0, c.Cb === nothing ? 0.0 : Float64(c.Cb), pad8(()), Float64(c.Cν), pad8(values(c.Cκ)), Int32(c.Cb !== nothing))
+    ObClosureDesc(3, 0.0, pad8(()), 0.0, 0, c.Cb === nothing ? 0.0 : Float64(c.Cb), pad8(()), Float64(c.Cν), pad8(values(c.Cκ)), Int32(c.Cb !== nothing), 0)
 closure_desc(c, names) = unsupported("closure $(typeof(c))")
 
 function model_desc(model::NonhydrostaticModel)

@@ -38,8 +38,25 @@ class WENO:
         self.weight_computation = weight_computation
 
 
+class ExplicitTimeDiscretization:
+    pass
+
+
+class VerticallyImplicitTimeDiscretization:
+    """ScalarDiffusivity(VerticallyImplicitTimeDiscretization(), ν=..., κ=...): vertical diffusion is taken out of the
+    explicit tendencies and solved implicitly after every substep (vertically_implicit_diffusion_solver.jl)"""
+
+
 class ScalarDiffusivity:
-    def __init__(self, nu=0.0, kappa=0.0, ν=None, κ=None):
+    """ScalarDiffusivity([time_discretization,] ν, κ) (scalar_diffusivity.jl:113-137)"""
+
+    def __init__(self, time_discretization=None, nu=0.0, kappa=0.0, ν=None, κ=None):
+        if isinstance(time_discretization, type):
+            time_discretization = time_discretization()
+        if time_discretization is not None and not isinstance(time_discretization, (ExplicitTimeDiscretization, VerticallyImplicitTimeDiscretization)):
+            raise TypeError("time_discretization must be ExplicitTimeDiscretization() or VerticallyImplicitTimeDiscretization()")
+        self.time_discretization = time_discretization or ExplicitTimeDiscretization()
+        self.vertically_implicit = isinstance(self.time_discretization, VerticallyImplicitTimeDiscretization)
         self.nu = nu if ν is None else ν
         self.kappa = kappa if κ is None else κ
         self.required_halo = 1
@@ -185,6 +202,9 @@ class NonhydrostaticModel:
             cd = d.closures[m]
             if isinstance(c, ScalarDiffusivity):
                 cd.kind, cd.nu = _abi.OB_CLOSURE_SCALAR_DIFFUSIVITY, float(FT(c.nu))
+                cd.vertically_implicit = int(c.vertically_implicit)
+                if c.vertically_implicit and g.topo[2] != _abi.OB_BOUNDED:
+                    raise ValueError("VerticallyImplicitTimeDiscretization can only be specified on grids that are Bounded in the z-direction.")
                 for t in range(nt):
                     kv = _per_tracer(c.kappa, self.tracer_names, t)
                     if callable(kv) or callable(c.nu):

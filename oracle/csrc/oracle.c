@@ -97,6 +97,8 @@ typedef struct {
     int has_pHY;
     ofield pHY;
     ofield Gu, Gv, Gw, Gc[MAXTR];
+    /* VerticallyImplicitTimeDiscretization per closure (abstract_scalar_diffusivity_closure.jl:265-312) */
+    int closure_vi[MAXCL];
 } oparams;
 
 typedef const oparams *P;
@@ -428,13 +430,26 @@ static FT nu_cff(P g, int m, int i, int j, int k) { return g->closure_kind[m] ==
 /* Ax_q(viscous_flux): area * (-2 ν Σ)  (closure_kernel_operators.jl:20-40; abstract_scalar...:214-226) */
 static FT F_ux(P g, int m, int i, int j, int k) { return (dyc(j) * dzc(k)) * (-2 * (nu_ccc(g, m, i, j, k) * S11(g, i, j, k))); }
 static FT F_uy(P g, int m, int i, int j, int k) { return (dxf(i) * dzc(k)) * (-2 * (nu_ffc(g, m, i, j, k) * S12(g, i, j, k))); }
-static FT F_uz(P g, int m, int i, int j, int k) { return (dxf(i) * dyc(j)) * (-2 * (nu_fcf(g, m, i, j, k) * S13(g, i, j, k))); }
+/* VerticallyImplicitTimeDiscretization on a z-Bounded grid (abstract_scalar_diffusivity_closure.jl:270-312): away from the
+ * boundary faces k = 1, Nz+1 the explicit vertical fluxes keep only what the tridiagonal solve does not contain:
+ * uz = -nu dx(w), vz = -nu dy(w), wz = 0, q_z = 0 */
+static int vi_elide(P g, int m, int k) { return g->closure_vi[m] && g->topo[2] == BOUNDED && !((k == 1) | (k == g->N[2] + 1)); }
+static FT F_uz(P g, int m, int i, int j, int k) {
+    if (vi_elide(g, m, k)) return (dxf(i) * dyc(j)) * (-(nu_fcf(g, m, i, j, k) * dx_w(g, i, j, k)));
+    return (dxf(i) * dyc(j)) * (-2 * (nu_fcf(g, m, i, j, k) * S13(g, i, j, k)));
+}
 static FT F_vx(P g, int m, int i, int j, int k) { return (dyf(j) * dzc(k)) * (-2 * (nu_ffc(g, m, i, j, k) * S12(g, i, j, k))); }
 static FT F_vy(P g, int m, int i, int j, int k) { return (dxc(i) * dzc(k)) * (-2 * (nu_ccc(g, m, i, j, k) * S22(g, i, j, k))); }
-static FT F_vz(P g, int m, int i, int j, int k) { return (dxc(i) * dyf(j)) * (-2 * (nu_cff(g, m, i, j, k) * S23(g, i, j, k))); }
+static FT F_vz(P g, int m, int i, int j, int k) {
+    if (vi_elide(g, m, k)) return (dxc(i) * dyf(j)) * (-(nu_cff(g, m, i, j, k) * dy_w(g, i, j, k)));
+    return (dxc(i) * dyf(j)) * (-2 * (nu_cff(g, m, i, j, k) * S23(g, i, j, k)));
+}
 static FT F_wx(P g, int m, int i, int j, int k) { return (dyc(j) * dzf(k)) * (-2 * (nu_fcf(g, m, i, j, k) * S13(g, i, j, k))); }
 static FT F_wy(P g, int m, int i, int j, int k) { return (dxc(i) * dzf(k)) * (-2 * (nu_cff(g, m, i, j, k) * S23(g, i, j, k))); }
-static FT F_wz(P g, int m, int i, int j, int k) { return (dxc(i) * dyc(j)) * (-2 * (nu_ccc(g, m, i, j, k) * S33(g, i, j, k))); }
+static FT F_wz(P g, int m, int i, int j, int k) {
+    if (vi_elide(g, m, k)) return (dxc(i) * dyc(j)) * (FT)0;
+    return (dxc(i) * dyc(j)) * (-2 * (nu_ccc(g, m, i, j, k) * S33(g, i, j, k)));
+}
 
 static FT div_tau1(P g, int m, int i, int j, int k) {
     FT Vi = 1 / ((dxf(i) * dyc(j)) * dzc(k));
@@ -472,6 +487,7 @@ static FT Q_y(P g, int m, int t, int i, int j, int k) {
 }
 static FT Q_z(P g, int m, int t, int i, int j, int k) {
     const ofield *c = &g->c[t];
+    if (vi_elide(g, m, k)) return (dxc(i) * dyc(j)) * (FT)0;
     FT dc = (FLATZ ? 0 : at(c, i, j, k) - at(c, i, j, k - 1)) * (1 / dzf(k));
     return (dxc(i) * dyc(j)) * (-kap(g, m, t, 2, i, j, k) * dc);
 }
@@ -558,6 +574,100 @@ static FT Gc_point(P g, int t, int i, int j, int k) {
 }
 
 /* one "kernel launch" per tendency over size(grid) (compute_nonhydrostatic_tendencies.jl:67-97) */
+/* ------------------------------------------------------------------------------------------
+ * implicit_step! (src/TurbulenceClosures/vertically_implicit_diffusion_solver.jl:60-136,196-225) through
+ * solve_batched_tridiagonal_system_z! (src/Solvers/batched_tridiagonal_solver.jl:211-243), in place on the field.
+ * which: 0 u (f,c,c), 1 v (c,f,c), 2 w (c,c,f), 3+t tracer t (c,c,c).  t_scratch: Nz+1 values per column.
+ * inactive_cell / inactive_node / peripheral_node: src/Grids/inactive_node.jl:43-165.
+ * ------------------------------------------------------------------------------------------ */
+static int inactive_cell(P g, int i, int j, int k) {
+    return ((g->topo[0] == BOUNDED) & ((i < 1) | (i > g->N[0]))) | ((g->topo[1] == BOUNDED) & ((j < 1) | (j > g->N[1]))) |
+           ((g->topo[2] == BOUNDED) & ((k < 1) | (k > g->N[2])));
+}
+/* any = 1: peripheral_node (OR over the cells around the node), any = 0: inactive_node (AND) */
+static int node_test(P g, int i, int j, int k, int fx, int fy, int fz, int any) {
+    int r = any ? 0 : 1;
+    for (int a = 0; a <= fx; a++)
+        for (int b = 0; b <= fy; b++)
+            for (int c = 0; c <= fz; c++) {
+                int v = inactive_cell(g, i - a, j - b, k - c);
+                r = any ? (r | v) : (r & v);
+            }
+    return r;
+}
+static FT strong(FT x, int keep) { return keep ? x : (FT)0; } /* x * Bool */
+static FT ivd_coefficient(P g, int m, int which) { return which < 3 ? g->nu[m] : g->kappa[m][which - 3]; }
+static FT ivd_upper(P g, int which, int lx, int ly, int lz, int i, int j, int k, FT dt) {
+    FT sum = 0;
+    int first = 1;
+    for (int m = 0; m < g->nclosures; m++) {
+        if (!g->closure_vi[m]) continue;
+        FT d;
+        if (!lz) {
+            FT kap = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, k + 1, lx, ly, 1, 0));
+            d = -dt * kap * ((1 / dzc(k)) * (1 / dzf(k + 1)));
+            d = strong(d, !node_test(g, i, j, k + 1, lx, ly, 1, 1));
+        } else {
+            FT nu = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, k, lx, ly, 0, 0));
+            d = -dt * nu * ((1 / dzc(k)) * (1 / dzf(k)));
+            d = strong(d, !node_test(g, i, j, k, lx, ly, 0, 1));
+        }
+        sum = first ? d : sum + d;
+        first = 0;
+    }
+    return sum;
+}
+static FT ivd_lower(P g, int which, int lx, int ly, int lz, int i, int j, int kk, FT dt) {
+    FT sum = 0;
+    int first = 1;
+    for (int m = 0; m < g->nclosures; m++) {
+        if (!g->closure_vi[m]) continue;
+        FT d;
+        if (!lz) {
+            int k = kk + 1;
+            FT kap = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, k, lx, ly, 1, 0));
+            d = -dt * kap * ((1 / dzc(k)) * (1 / dzf(k)));
+            d = strong(d, !node_test(g, i, j, kk, lx, ly, 0, 1));
+        } else {
+            int kp = kk + 2;
+            FT nu = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, kp - 1, lx, ly, 0, 0));
+            d = -dt * nu * ((1 / dzc(kp)) * (1 / dzf(kp - 1)));
+            d = strong(d, !node_test(g, i, j, kk, lx, ly, 0, 1));
+        }
+        sum = first ? d : sum + d;
+        first = 0;
+    }
+    return sum;
+}
+static FT ivd_diag(P g, int which, int lx, int ly, int lz, int i, int j, int k, FT dt) {
+    return (FT)1 - dt * (FT)0 - ivd_upper(g, which, lx, ly, lz, i, j, k, dt) - ivd_lower(g, which, lx, ly, lz, i, j, k - 1, dt);
+}
+void SUF(orc_implicit_step)(const oparams *g, int which, ofield *phi, FT dt, FT *t) {
+    const int lx = which == 0, ly = which == 1, lz = which == 2;
+    const int Nz = g->N[2];
+#ifdef ORACLE_F32
+    const FT tiny = 10 * 1.1920929e-07f;
+#else
+    const FT tiny = 10 * 2.220446049250313e-16;
+#endif
+    for (int j = 1; j <= g->N[1]; j++)
+        for (int i = 1; i <= g->N[0]; i++) {
+            FT beta = ivd_diag(g, which, lx, ly, lz, i, j, 1, dt);
+            *ref(phi, i, j, 1) = at(phi, i, j, 1) / beta;
+            for (int k = 2; k <= Nz; k++) {
+                FT cm = ivd_upper(g, which, lx, ly, lz, i, j, k - 1, dt);
+                FT bk = ivd_diag(g, which, lx, ly, lz, i, j, k, dt);
+                FT am = ivd_lower(g, which, lx, ly, lz, i, j, k - 1, dt);
+                t[k] = cm / beta;
+                beta = bk - am * t[k];
+                FT fk = at(phi, i, j, k);
+                FT cand = (fk - am * at(phi, i, j, k - 1)) / beta;
+                if (FABS(beta) > tiny) *ref(phi, i, j, k) = cand;
+            }
+            for (int k = Nz - 1; k >= 1; k--) *ref(phi, i, j, k) -= t[k + 1] * at(phi, i, j, k + 1);
+        }
+}
+
 void SUF(orc_compute_tendencies)(const oparams *g) {
     build_chains();
     const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];

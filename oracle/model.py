@@ -69,6 +69,7 @@ def _mkstructs(ft):
             ("u", OField), ("v", OField), ("w", OField), ("c", OField * MAXTR),
             ("has_pHY", C.c_int), ("pHY", OField),
             ("Gu", OField), ("Gv", OField), ("Gw", OField), ("Gc", OField * MAXTR),
+            ("closure_vi", C.c_int * MAXCL),
         ]
 
     return cft, P, OField, OParams
@@ -418,8 +419,11 @@ class FourierTridiagonalPoissonSolver:
 # Model
 # ---------------------------------------------------------------------------------------------
 class ScalarDiffusivity:
-    def __init__(self, nu=0.0, kappa=0.0):
-        self.nu, self.kappa = nu, kappa
+    """ScalarDiffusivity(time_discretization, ν, κ): vertically_implicit = VerticallyImplicitTimeDiscretization()
+    (scalar_diffusivity.jl:113-137)"""
+
+    def __init__(self, nu=0.0, kappa=0.0, vertically_implicit=False):
+        self.nu, self.kappa, self.vertically_implicit = nu, kappa, bool(vertically_implicit)
 
 
 class Smagorinsky:
@@ -515,6 +519,7 @@ class Model:
         for m, c in enumerate(self.closures):
             if isinstance(c, ScalarDiffusivity):
                 p.closure_kind[m] = 1
+                p.closure_vi[m] = int(c.vertically_implicit)
                 p.nu[m] = ft(c.nu)
                 for t in range(nt):
                     p.kappa[m][t] = ft(_per_tracer(c.kappa, self.tracer_names, t))
@@ -712,7 +717,26 @@ class Model:
                 U += dt * (ft(gamma) * Gn + ft(zeta) * Gm)
         # Δτ = convert(FT, stage_Δt(Δt, γ, ζ)) with stage_Δt = Δt * (γ + ζ) (runge_kutta_3.jl:186-187)
         gz = ft(gamma) if zeta is None else ft(ft(gamma) + ft(zeta))
-        self.pressure_correct(ft(self._dt_user * float(gz)))
+        dtau = ft(self._dt_user * float(gz))
+        # the reference interleaves (explicit update, implicit_step!) field by field; both are column-local per field
+        self.implicit_step(dtau)
+        self.pressure_correct(dtau)
+
+    def implicit_step(self, dtau):
+        """implicit_step! of every prognostic field (nonhydrostatic_rk3_substep.jl:47-56, nonhydrostatic_ab2_step.jl:41-50)"""
+        if not any(getattr(c, "vertically_implicit", False) for c in self.closures):
+            return
+        if self.grid.topo[2] != BOUNDED:
+            raise ValueError("VerticallyImplicitTimeDiscretization can only be specified on grids that are Bounded in the z-direction.")
+        ft = self.grid.ft
+        p = self.params()
+        scratch = np.zeros(self.grid.N[2] + 2, dtype=ft)
+        fn = self._fn("orc_implicit_step")
+        fn.restype = None
+        cft = structs(ft)[0]
+        for n, f in enumerate(self.prognostic):
+            of = f.ofield()
+            fn(C.byref(p), C.c_int(n), C.byref(of), cft(float(dtau)), scratch.ctypes.data_as(C.c_void_p))
 
     def ab2_step(self, dt, chi):
         ft = self.grid.ft
@@ -728,6 +752,7 @@ class Model:
             # `β * G⁻ * not_euler`: a false Bool is a strong zero in Julia (kills leftover NaNs in G⁻)
             Gu = alpha * Gn - beta * Gm if not_euler else alpha * Gn - ft(0)
             U += dt * Gu
+        self.implicit_step(dt)
         self.pressure_correct(dt)
 
     def divergence(self):

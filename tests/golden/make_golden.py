@@ -1,4 +1,4 @@
-"""Regenerate tests/golden/*.npz:  python tests/golden/make_golden.py
+"""Regenerate tests/golden/*.npz:  python tests/golden/make_golden.py [name ...]
 
 The reference itself cannot run in this image (no Julia), so these are NOT reference outputs: they are outputs of the CPU
 oracle (oracle/, the restatement of the reference CPU() path) frozen at the commit that introduced them.  They pin (i) the
@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = {  # name -> (dt, steps)
     "readme_2d": (1e-3, (1, 10)), "ppp_weno5": (1e-3, (1, 10)), "les_amd": (0.5, (1, 10)), "stretched": (0.5, (1, 10)),
     "lilly_bbb": (1e-3, (1,)), "smag_pbp": (1e-3, (1,)), "weno7": (1e-3, (1,)), "centered2_value": (1e-3, (1,)),
+    "vi_ppb": (0.05, (1, 10)),
 }
 SEED = 7
 
@@ -37,7 +38,10 @@ def summarize(om):
 
 def main():
     from test_gpu_parity import CONFIGS
+    only = sys.argv[1:]   # python tests/golden/make_golden.py [name ...]: regenerate a subset
     for name, (dt, snaps) in GOLDEN.items():
+        if only and name not in only:
+            continue
         cfg = CONFIGS[name]
         om = cfg.oracle_model()
         om.set(**cfg.initial_conditions(SEED))

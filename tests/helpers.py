@@ -42,6 +42,8 @@ class Config:
         for c in self.closure:
             if c[0] == "scalar":
                 cl.append(M.ScalarDiffusivity(nu=c[1], kappa=c[2]))
+            elif c[0] == "vi_scalar":
+                cl.append(M.ScalarDiffusivity(nu=c[1], kappa=c[2], vertically_implicit=True))
             elif c[0] == "smag":
                 cl.append(M.Smagorinsky(coefficient=c[1], Pr=c[2]))
             elif c[0] == "lilly":
@@ -74,6 +76,8 @@ class Config:
         for c in self.closure:
             if c[0] == "scalar":
                 cl.append(ob.ScalarDiffusivity(nu=c[1], kappa=c[2]))
+            elif c[0] == "vi_scalar":
+                cl.append(ob.ScalarDiffusivity(ob.VerticallyImplicitTimeDiscretization(), nu=c[1], kappa=c[2]))
             elif c[0] == "smag":
                 cl.append(ob.Smagorinsky(coefficient=c[1], Pr=c[2]))
             elif c[0] == "lilly":

@@ -50,6 +50,13 @@ CONFIGS = {
                        buoyancy=("tracer",), tracers=("b",)),
     "wide_stretched": Config((66, 9, 14), ((0, 6.6), (0, 0.9), stretched_faces(14, 1.4)), "PPB", advection=("weno", 5),
                              closure=[("lilly", 0.16, 1.0, 1.0)], buoyancy=("tracer",), tracers=("b", "c")),
+    # VerticallyImplicitTimeDiscretization: interior vertical diffusion leaves the explicit tendencies and is solved per
+    # column after every substep; alone, in a tuple with an explicit closure, on walls in x/y, stretched z
+    "vi_ppb": Config((16, 12, 14), ((0, 1.6), (0, 1.2), (-1.4, 0.0)), "PPB", advection=("weno", 5), closure=[("vi_scalar", 2e-2, 1e-2)],
+                     buoyancy=("tracer",), coriolis_f=0.3, tracers=("b", "c"),
+                     bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 2e-4), "bottom": ("Gradient", 0.5)}, "c": {"bottom": ("Value", 1.0)}}),
+    "vi_tuple_bbb": Config((12, 10, 12), ((0, 1.0), (0, 1.0), stretched_faces(12, 1.0)), "BBB", advection=("centered", 4),
+                           closure=[("scalar", 1e-3, 2e-3), ("vi_scalar", 3e-2, 2e-2)], buoyancy=("tracer",), tracers=("b",)),
     # Flat x and Flat y (2-D vertical slices)
     "flat_x": Config((1, 16, 12), (None, (0, 1.0), (-1.0, 0.0)), "FPB", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
                      buoyancy=("tracer",), tracers=("b",)),
@@ -58,7 +65,7 @@ CONFIGS = {
     "amd_cb": Config((12, 12, 10), ((0, 12.0), (0, 12.0), (-10.0, 0.0)), "PPB", advection=("weno", 5),
                      closure=[("amd", 1.0)], buoyancy=("tracer",), tracers=("b",)),
 }
-AB2 = {k: Config(**{**CONFIGS[k].__dict__, "timestepper": "ab2"}) for k in ("ppp_weno5", "les_amd")}
+AB2 = {k: Config(**{**CONFIGS[k].__dict__, "timestepper": "ab2"}) for k in ("ppp_weno5", "les_amd", "vi_ppb")}
 
 
 def _cfg32(cfg):
@@ -203,12 +210,12 @@ def test_against_golden_vectors(arch, name, steps):
         assert abs((a * a).sum() - sums[1]) <= 1e-8 * max(sums[1], 1e-300) + 1e-300, (name, fname, "sum of squares")
 
 
-@pytest.mark.parametrize("name", ["ppp_weno5", "les_amd", "stretched", "readme_2d"])
+@pytest.mark.parametrize("name", ["ppp_weno5", "les_amd", "stretched", "readme_2d", "vi_ppb", "vi_tuple_bbb"])
 def test_ten_steps_f64(arch, name):
     import ocean_b200 as ob
     cfg = CONFIGS[name]
     om, bm = pair(cfg, arch, seed=4)
-    dt = 1e-3 if name in ("ppp_weno5", "readme_2d") else 0.5
+    dt = 1e-3 if name in ("ppp_weno5", "readme_2d") else 0.05 if name.startswith("vi_") else 0.5
     for _ in range(10):
         om.time_step(dt)
         ob.time_step(bm, dt)
@@ -231,7 +238,7 @@ def test_one_step_f32(arch, name):
     import ocean_b200 as ob
     cfg = _cfg32(CONFIGS[name])
     om, bm = pair(cfg, arch, seed=6)
-    dt = 1e-3 if name in ("ppp_weno5", "readme_2d") else 0.5
+    dt = 1e-3 if name in ("ppp_weno5", "readme_2d") else 0.05 if name.startswith("vi_") else 0.5
     om.time_step(dt)
     ob.time_step(bm, dt)
     # pNHS in Float32 is a near-cancelling quantity (∇·u* of a projected field); hold it to a looser bound

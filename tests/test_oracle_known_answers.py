@@ -241,3 +241,34 @@ def test_oracle_batched_tridiagonal_matches_dense():
     for q in range(8, -1, -1):
         phi[q] -= t[q + 1] * phi[q + 1]
     assert np.allclose(phi, np.linalg.solve(A, f), rtol=1e-11)
+
+
+def test_oracle_vertically_implicit_diffusion_is_backward_euler():
+    """VerticallyImplicitTimeDiscretization (vertically_implicit_diffusion_solver.jl; test_implicit_diffusion in the
+    reference's test_time_stepping.jl compares implicit and explicit diffusion of a smooth profile): with no advection,
+    one forward-Euler step of a z-only profile must equal the dense backward-Euler solve of (I - Δt κ ∂z²) c = c⁰ with
+    no-flux walls, for a tracer and -- same operator, same boundary treatment -- for u"""
+    Nz, kap, dt = 16, 0.05, 0.01
+    g = M.Grid((4, 4, Nz), ((0, 1.0), (0, 1.0), (-1.0, 0.0)), topology=("P", "P", "B"), halo=(3, 3, 3))
+    zc = -1.0 + (np.arange(Nz) + 0.5) / Nz
+    prof = np.cos(np.pi * zc) + 0.3 * np.cos(3 * np.pi * zc)
+    c0 = np.broadcast_to(prof[:, None, None], (Nz, 4, 4)).copy()
+    m = M.Model(g, advection=None, closure=[M.ScalarDiffusivity(nu=kap, kappa=kap, vertically_implicit=True)], tracers=("c",), timestepper="ab2")
+    m.set(c=c0, u=c0)
+    m.time_step(dt, euler=True)
+    dz = 1.0 / Nz
+    A = np.eye(Nz)
+    for k in range(Nz):
+        for q in (k - 1, k + 1):
+            if 0 <= q < Nz:
+                A[k, q] -= dt * kap / dz ** 2
+                A[k, k] += dt * kap / dz ** 2
+    want = np.linalg.solve(A, prof)
+    assert np.allclose(m.tracers[0].interior[:, 1, 2], want, rtol=1e-12, atol=1e-14)
+    assert np.allclose(m.u.interior[:, 1, 2], want, rtol=1e-12, atol=1e-14)
+    # and it differs from the explicit step by O(Δt²): the implicit path is really taken
+    e = M.Model(g, advection=None, closure=[M.ScalarDiffusivity(nu=kap, kappa=kap)], tracers=("c",), timestepper="ab2")
+    e.set(c=c0)
+    e.time_step(dt, euler=True)
+    d = np.abs(e.tracers[0].interior[:, 1, 2] - want).max()
+    assert 1e-7 < d < 1e-3
