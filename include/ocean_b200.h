@@ -170,6 +170,13 @@ int32_t ob_cell_advection_timescale(ob_model *m, double *tau);
 int32_t ob_model_create(ob_ctx *ctx, const ob_model_desc *desc, ob_model **model);
 int32_t ob_model_destroy(ob_model *m);
 int32_t ob_model_bind_field(ob_model *m, int32_t field_id, void *device_ptr);
+/* Array-valued boundary condition (BoundaryCondition with an AbstractArray condition: getbc(bc, i, j, ...) = condition[i, j],
+ * src/BoundaryConditions/boundary_condition.jl): `values` is a device array (ob_malloc) of the field's interior extent in
+ * the two tangential dimensions of `side` (0 west .. 5 top), the lower dimension fastest, in the grid float type; it
+ * replaces the constant of the Flux / Value / Gradient condition declared for that side.  NULL restores the constant.
+ * The caller keeps ownership.  This is also how the Julia shim passes time-independent boundary FUNCTIONS: tabulated once
+ * on the host. */
+int32_t ob_model_set_bc_array(ob_model *m, int32_t field_id, int32_t side, const void *values);
 /* fill_halo_regions!(field) -- src/BoundaryConditions/fill_halo_regions.jl:20-38 */
 int32_t ob_fill_halo(ob_model *m, int32_t field_id, int32_t fill_normal_flow_bcs);
 /* update_state!(model) -- update_nonhydrostatic_model_state.jl:22-62 (halos, closure fields, pHY′, tendencies) */

@@ -20,6 +20,7 @@ struct HaloTask {
     int face;      // field is Face-located along `dir`
     int bc_lo, bc_hi;
     T v_lo, v_hi;  // constant value / gradient
+    const T *a_lo, *a_hi;  // array-valued condition over the interior extent of the tangential dims (n[da] fastest), or nullptr
     T d_lo, d_hi;  // Δ at the boundary (flipped location) for Value/Gradient
 };
 #define OB_MAX_HALO_TASKS 24
@@ -56,21 +57,24 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloB
         return;
     }
     q = t.p + (a + B.Hother[da]) * sa + (b + B.Hother[db]) * sb;  // interior window of the tangential dims
+    // getbc(condition::AbstractArray, i, j, ...) = condition[i, j] (boundary_condition.jl)
+    const T v_lo = t.a_lo ? __ldg(t.a_lo + a + (long)b * A) : t.v_lo;
+    const T v_hi = t.a_hi ? __ldg(t.a_hi + a + (long)b * A) : t.v_hi;
     // logical index l along d -> parent index l - 1 + H
 #define AT(l) q[((l) - 1 + H) * sd]
     // low side
     switch (t.bc_lo) {
         case BC_FLUX: AT(0) = AT(1); break;
         case BC_IMPENETRABLE: if (B.fill_normal) AT(1) = T(0); break;
-        case BC_GRADIENT: { T c = AT(1); AT(0) = add_rn(c, mul_rn(t.v_lo, -t.d_lo)); } break;
-        case BC_VALUE: { T c = AT(1); T g = (c - t.v_lo) / (t.d_lo / 2); AT(0) = add_rn(c, mul_rn(g, -t.d_lo)); } break;
+        case BC_GRADIENT: { T c = AT(1); AT(0) = add_rn(c, mul_rn(v_lo, -t.d_lo)); } break;
+        case BC_VALUE: { T c = AT(1); T g = (c - v_lo) / (t.d_lo / 2); AT(0) = add_rn(c, mul_rn(g, -t.d_lo)); } break;
         default: break;
     }
     switch (t.bc_hi) {
         case BC_FLUX: AT(N + 1) = AT(N); break;
         case BC_IMPENETRABLE: if (B.fill_normal) AT(N + 1) = T(0); break;
-        case BC_GRADIENT: { T c = AT(N); AT(N + 1) = add_rn(c, mul_rn(t.v_hi, t.d_hi)); } break;
-        case BC_VALUE: { T c = AT(N); T g = (t.v_hi - c) / (t.d_hi / 2); AT(N + 1) = add_rn(c, mul_rn(g, t.d_hi)); } break;
+        case BC_GRADIENT: { T c = AT(N); AT(N + 1) = add_rn(c, mul_rn(v_hi, t.d_hi)); } break;
+        case BC_VALUE: { T c = AT(N); T g = (v_hi - c) / (t.d_hi / 2); AT(N + 1) = add_rn(c, mul_rn(g, t.d_hi)); } break;
         default: break;
     }
 #undef AT
@@ -282,6 +286,8 @@ struct FluxBcTask {
     int dir, side;   // side 0 = low (+=), 1 = high (-=)
     int loc[3];      // 1 = face, 0 = center
     T flux;
+    const T *arr;    // array-valued flux over the field's tangential interior extent (row length `row`), or nullptr
+    int row;
 };
 template <typename T>
 __global__ void flux_bc_kernel(GridD<T> g, FluxBcTask<T> t) {
@@ -305,7 +311,8 @@ __global__ void flux_bc_kernel(GridD<T> g, FluxBcTask<T> t) {
     (void)n_face;
     T area = sa * sb;  // Ax = Δy*Δz ; Ay = Δx*Δz ; Az = Δx*Δy  (da < db always)
     T vol = d == 0 ? (sn * sa) * sb : d == 1 ? (sa * sn) * sb : (sa * sb) * sn;  // V = (Δx*Δy)*Δz
-    T term = t.flux * area / vol;
+    const T flux = t.arr ? __ldg(t.arr + a + (long)b * t.row) : t.flux;
+    T term = flux * area / vol;
     T &G = t.G(idx[0], idx[1], idx[2]);
     G = t.side == 0 ? G + term : G - term;
 }

@@ -685,6 +685,7 @@ struct FieldInfo {
     int loc[3] = {0, 0, 0};  // 1 = Face
     int P[3] = {1, 1, 1}, n[3] = {1, 1, 1}, o[3] = {0, 0, 0};
     ob_bc_desc bc;
+    const void *bc_array[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // ob_model_set_bc_array
     bool exists = false;
     long count() const { return (long)P[0] * P[1] * P[2]; }
 };
@@ -710,6 +711,7 @@ struct ob_model {
     virtual int32_t compute_tendencies() = 0;
     virtual int32_t compute_closure_fields() = 0;
     virtual int32_t update_hydrostatic_pressure() = 0;
+    virtual int32_t set_bc_array(int id, int side, const void *p) = 0;
     virtual int32_t rk3_substep(double dt, double gamma, double zeta, int has_zeta, bool cache) = 0;
     virtual int32_t ab2_step(double dt, double chi, bool cache) = 0;
     virtual int32_t cache_tendencies() = 0;
@@ -899,6 +901,15 @@ struct ModelT : ob_model {
         F[id].ptr = p;
         return OB_OK;
     }
+    int32_t set_bc_array(int id, int side, const void *p) override {
+        if (id < 0 || id >= 128 || !F[id].exists) return fail(OB_ERR_INVALID, "unknown field id %d", id);
+        if (side < 0 || side >= 6) return fail(OB_ERR_INVALID, "side %d out of range", side);
+        const int k = F[id].bc.kind[side];
+        if (p && k != OB_BC_FLUX && k != OB_BC_VALUE && k != OB_BC_GRADIENT)
+            return fail(OB_ERR_INVALID, "array-valued conditions need a Flux, Value or Gradient boundary condition on that side");
+        F[id].bc_array[side] = p;
+        return OB_OK;
+    }
     int32_t need(int id) const {
         if (!F[id].exists || !F[id].ptr) return fail(OB_ERR_UNBOUND, "field id %d is not bound (ob_model_bind_field)", id);
         return OB_OK;
@@ -939,6 +950,7 @@ struct ModelT : ob_model {
                         t.face = f.loc[d];
                         t.bc_lo = lo; t.bc_hi = hi;
                         t.v_lo = (T)f.bc.value[2 * d]; t.v_hi = (T)f.bc.value[2 * d + 1];
+                        t.a_lo = (const T *)f.bc_array[2 * d]; t.a_hi = (const T *)f.bc_array[2 * d + 1];
                         // Δ at flip(loc) at the boundary index (fill_halo_regions_value_gradient.jl:35-119)
                         auto sp = [&](int idx) -> T {
                             if (d == 0) return g.dx;
@@ -1236,13 +1248,14 @@ struct ModelT : ob_model {
                 const int fid = n < 3 ? n : OB_FIELD_TRACER0 + (n - 3);
                 const FieldInfo &f = F[fid];
                 for (int side = 0; side < 2; side++) {
-                    if (f.bc.kind[2 * d + side] != OB_BC_FLUX || f.bc.value[2 * d + side] == 0.0) continue;
+                    if (f.bc.kind[2 * d + side] != OB_BC_FLUX || (f.bc.value[2 * d + side] == 0.0 && !f.bc_array[2 * d + side])) continue;
                     FluxBcTask<T> t;
                     t.G = fld(OB_FIELD_GN0 + n);
                     t.dir = d; t.side = side;
                     for (int k = 0; k < 3; k++) t.loc[k] = f.loc[k];
                     t.flux = (T)f.bc.value[2 * d + side];
                     const int da = d == 0 ? 1 : 0, db = d == 2 ? 1 : 2;
+                    t.arr = (const T *)f.bc_array[2 * d + side]; t.row = f.n[da];
                     dim3 grid(nblk(g.N[da], 128), g.N[db]);
                     flux_bc_kernel<T><<<grid, 128, 0, ctx->stream>>>(g, t);
                     launches++;
@@ -1486,6 +1499,10 @@ extern "C" int32_t ob_model_destroy(ob_model *m) {
     CUDA_TRY(cudaSetDevice(m->ctx->device));      \
     return (expr);
 extern "C" int32_t ob_model_bind_field(ob_model *m, int32_t id, void *p) { MCALL(m->bind(id, p)) }
+extern "C" int32_t ob_model_set_bc_array(ob_model *m, int32_t id, int32_t side, const void *p) {
+    if (!m) return fail(OB_ERR_INVALID, "null model");
+    MCALL(m->set_bc_array(id, side, p))
+}
 extern "C" int32_t ob_fill_halo(ob_model *m, int32_t id, int32_t fn) { MCALL(m->fill_halo(id, fn)) }
 extern "C" int32_t ob_update_state(ob_model *m) { MCALL(m->update_state()) }
 extern "C" int32_t ob_compute_tendencies(ob_model *m) { MCALL(m->compute_tendencies()) }

@@ -22,6 +22,8 @@ class BoundaryCondition:
 
 
 def FluxBoundaryCondition(value):
+    """`value`: a number, or an array over the boundary plane -- numpy shape (n_slow, n_fast) of the field's interior extent in
+    the two tangential dimensions, e.g. (ny, nx) for top/bottom (BoundaryCondition with an AbstractArray condition)"""
     return BoundaryCondition("Flux", value)
 
 
@@ -92,7 +94,7 @@ def bc_desc(bcs):
             d.kind[s], d.value[s] = _abi.OB_BC_NONE, 0.0
         else:
             d.kind[s] = _KIND[bc.kind]
-            d.value[s] = 0.0 if bc.value is None else float(bc.value)
+            d.value[s] = 0.0 if (bc.value is None or isinstance(bc.value, np.ndarray)) else float(bc.value)   # arrays: ob_model_set_bc_array
     return d
 
 

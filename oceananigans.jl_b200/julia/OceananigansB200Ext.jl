@@ -144,8 +144,9 @@ function bc_kind(bc::BoundaryCondition)
     c = bc.classification
     c isa PBC && return (Int32(1), 0.0)
     v = bc.condition
-    (v isa Number || v === nothing) || unsupported("a function- or array-valued boundary condition")
-    val = v === nothing ? 0.0 : Float64(v)
+    # arrays (and time-independent boundary functions tabulated by the user into arrays) go through ob_model_set_bc_array
+    (v isa Number || v === nothing || v isa AbstractArray) || unsupported("a function-valued boundary condition (tabulate it into an array)")
+    val = (v === nothing || v isa AbstractArray) ? 0.0 : Float64(v)
     c isa Flux     && return (Int32(2), val)
     c isa Value    && return (Int32(3), val)
     c isa Gradient && return (Int32(4), val)
@@ -233,6 +234,14 @@ function create_handle(model)
         bind!(h, 64 + m - 1, K.νₑ)
         if c isa AnisotropicMinimumDissipation
             for (t, κ) in enumerate(K.κₑ); bind!(h, 80 + (m - 1) * 8 + t - 1, κ); end
+        end
+    end
+    # array-valued conditions: condition[i, j] over the boundary plane, already a device array (on_architecture(::B200, ...))
+    for (id, f) in ((0, model.velocities.u), (1, model.velocities.v), (2, model.velocities.w), ((16 + t - 1, c) for (t, c) in enumerate(model.tracers))...)
+        bcs = f.boundary_conditions
+        for (side, bc) in enumerate((bcs.west, bcs.east, bcs.south, bcs.north, bcs.bottom, bcs.top))
+            (bc isa BoundaryCondition && bc.condition isa AbstractArray) || continue
+            @ob ob_model_set_bc_array (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}) h Int32(id) Int32(side - 1) pointer(bc.condition)
         end
     end
     finalizer(_ -> ccall((:ob_model_destroy, lib), Int32, (Ptr{Cvoid},), h), model.timestepper)

@@ -263,6 +263,7 @@ class NonhydrostaticModel:
         _abi.call("ob_model_create", arch.ctx, C.byref(d), C.byref(h))
         self.handle = h
         self._bind_all()
+        self._upload_bc_arrays()
         self.update_state()
 
     # ---------------------------------------------------------------------------------------------------------
@@ -285,11 +286,39 @@ class NonhydrostaticModel:
             for t, f in enumerate(cf.get("kappae", [])):
                 self._bind(A.OB_FIELD_KAPPAE0 + m * A.OB_MAX_TRACERS + t, f)
 
+    def _upload_bc_arrays(self):
+        """array-valued boundary conditions: device copies registered with ob_model_set_bc_array (kept alive here)"""
+        from .fields import SIDES
+        A = _abi
+        self._bc_arrays = []
+        ids = {"u": A.OB_FIELD_U, "v": A.OB_FIELD_V, "w": A.OB_FIELD_W}
+        ids.update({n: A.OB_FIELD_TRACER0 + t for t, n in enumerate(self.tracer_names)})
+        for name, f in self.prognostic_fields.items():
+            for s, side in enumerate(SIDES):
+                bc = f.boundary_conditions[side]
+                if bc is None or not isinstance(bc.value, np.ndarray):
+                    continue
+                d = s // 2
+                da, db = (1 if d == 0 else 0), (1 if d == 2 else 2)
+                want = (f.n[db], f.n[da])
+                arr = np.ascontiguousarray(bc.value, dtype=self.grid.FT)
+                if arr.shape != want:
+                    raise ValueError("%s boundary condition of %s: array shape %r, expected %r (n_slow, n_fast)" % (side, name, arr.shape, want))
+                p = C.c_void_p()
+                _abi.call("ob_malloc", self.architecture.ctx, arr.nbytes, C.byref(p))
+                _abi.call("ob_memcpy_h2d", self.architecture.ctx, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+                _abi.call("ob_sync", self.architecture.ctx)
+                _abi.call("ob_model_set_bc_array", self.handle, ids[name], s, p)
+                self._bc_arrays.append(p)
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):
                 _abi.lib().ob_model_destroy(self.handle)
                 self.handle = None
+            for p in getattr(self, "_bc_arrays", []):
+                _abi.lib().ob_free(self.architecture.ctx, p)
+            self._bc_arrays = []
         except Exception:
             pass
 

@@ -285,7 +285,8 @@ def _fill_side_pair(f, d, bc_lo, bc_hi, fill_normal_flow_bcs):
                 A[plane(1 if side == "lo" else N + 1)] = 0
         elif kind in ("value", "gradient"):
             ft = g.ft
-            val = ft(bc[1])
+            # a number, or an array over the boundary plane: getbc(condition::AbstractArray, i, j, ...) = condition[i, j]
+            val = np.asarray(bc[1], dtype=ft) if isinstance(bc[1], np.ndarray) else ft(bc[1])
             iB = 1 if side == "lo" else N + 1
             iI = 1 if side == "lo" else N
             iH = 0 if side == "lo" else N + 1
@@ -639,7 +640,12 @@ class Model:
                     bc = f.bcs[name]
                     if bc is None or bc[0] != "flux" or bc[1] is None:
                         continue
-                    self._add_flux(f, G, d, side, ft(bc[1]))
+                    if isinstance(bc[1], np.ndarray):   # array-valued flux over the field's tangential extent; kernel over size(grid)
+                        t0, t1 = [dd for dd in range(3) if dd != d]
+                        flux = np.expand_dims(np.asarray(bc[1], dtype=ft)[:g.N[t1], :g.N[t0]], axis=2 - d)
+                    else:
+                        flux = ft(bc[1])
+                    self._add_flux(f, G, d, side, flux)
 
     def _add_flux(self, f, G, d, side, flux):
         g = self.grid

@@ -57,6 +57,15 @@ CONFIGS = {
                      bcs={"u": {"top": ("Flux", -1e-3)}, "b": {"top": ("Flux", 2e-4), "bottom": ("Gradient", 0.5)}, "c": {"bottom": ("Value", 1.0)}}),
     "vi_tuple_bbb": Config((12, 10, 12), ((0, 1.0), (0, 1.0), stretched_faces(12, 1.0)), "BBB", advection=("centered", 4),
                            closure=[("scalar", 1e-3, 2e-3), ("vi_scalar", 3e-2, 2e-2)], buoyancy=("tracer",), tracers=("b",)),
+    # array-valued boundary conditions (surface flux maps, tabulated boundary functions): Flux / Gradient / Value arrays on z
+    # and x sides
+    "array_bcs": Config((12, 10, 8), ((0, 1.2), (0, 1.0), (-0.8, 0.0)), "BPB", advection=("weno", 5), closure=[("scalar", 1e-2, 2e-2)],
+                        buoyancy=("tracer",), tracers=("b", "c"),
+                        bcs={"u": {"top": ("Flux", 1e-3 * np.random.default_rng(1).standard_normal((10, 13)))},
+                             "b": {"top": ("Flux", 1e-4 * np.random.default_rng(2).standard_normal((10, 12))),
+                                   "bottom": ("Gradient", 0.5 + 0.1 * np.random.default_rng(3).standard_normal((10, 12)))},
+                             "c": {"west": ("Value", 1.0 + 0.2 * np.random.default_rng(4).standard_normal((8, 10))),
+                                   "top": ("Value", np.random.default_rng(5).standard_normal((10, 12)))}}),
     # Flat x and Flat y (2-D vertical slices)
     "flat_x": Config((1, 16, 12), (None, (0, 1.0), (-1.0, 0.0)), "FPB", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
                      buoyancy=("tracer",), tracers=("b",)),

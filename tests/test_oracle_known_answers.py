@@ -272,3 +272,19 @@ def test_oracle_vertically_implicit_diffusion_is_backward_euler():
     e.time_step(dt, euler=True)
     d = np.abs(e.tracers[0].interior[:, 1, 2] - want).max()
     assert 1e-7 < d < 1e-3
+
+
+def test_oracle_array_valued_boundary_conditions_reduce_to_constants():
+    """getbc(condition::AbstractArray, i, j, ...) = condition[i, j]: a constant array must reproduce the constant condition
+    bit for bit (Flux through compute_flux_bc_tendencies!, Value / Gradient through the halo fill)"""
+    base = dict(size=(12, 10, 8), extent=((0, 1.2), (0, 1.0), (-0.8, 0.0)), topology="BPB", advection=("weno", 5),
+                closure=[("scalar", 1e-2, 2e-2)], tracers=("c",))
+    c1 = Config(**base, bcs={"c": {"top": ("Flux", 0.3), "bottom": ("Value", 0.7), "west": ("Gradient", -0.2)}})
+    c2 = Config(**base, bcs={"c": {"top": ("Flux", np.full((10, 12), 0.3)), "bottom": ("Value", np.full((10, 12), 0.7)),
+                                   "west": ("Gradient", np.full((8, 10), -0.2))}})
+    a, b = c1.oracle_model(), c2.oracle_model()
+    ic = c1.initial_conditions(3)
+    a.set(**ic); b.set(**ic)
+    for _ in range(2):
+        a.time_step(1e-3); b.time_step(1e-3)
+    assert all(np.array_equal(x.data, y.data) for x, y in zip(a.prognostic, b.prognostic))
