@@ -22,3 +22,4 @@ from .simulations import (Simulation, run, Callback, IterationInterval, TimeInte
 from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver, solve  # noqa: F401
 from .distributed import Distributed, partition_x, neighbors, gather_x, all_reduce_scalar  # noqa: F401
 from .streaming import HostStreamedStepper, HostMember  # noqa: F401
+from .checkpoint import checkpoint, restore  # noqa: F401

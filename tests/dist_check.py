@@ -29,6 +29,9 @@ CASES = {
     "wide_overlap_ppb": (Config((192, 10, 12), ((0, 6.0), (0, 1.0), (-1.2, 0.0)), "PPB", advection=("weno", 5), closure=[("scalar", 1e-3, 2e-3)],
                                 buoyancy=("tracer",), coriolis_f=0.5, tracers=("b", "c"),
                                 bcs={"u": {"top": ("Flux", -2e-3)}, "b": {"top": ("Flux", 5e-4)}}), 1e-3),
+    # vertically-implicit diffusion: the column solves are rank-local
+    "vi_scalar_ppb": (Config((32, 12, 10), ((0, 3.2), (0, 1.2), (-1.0, 0.0)), "PPB", advection=("weno", 5), closure=[("vi_scalar", 2e-2, 1e-2)],
+                             buoyancy=("tracer",), tracers=("b",), bcs={"b": {"top": ("Flux", 2e-4)}}), 0.05),
     "les_amd_dct": (Config((32, 16, 12), ((0, 32.0), (0, 16.0), (-12.0, 0.0)), "PPB", advection=("weno", 5),
                            closure=[("amd",), ("scalar", 1.05e-6, 1.46e-7)], buoyancy=("seawater", 9.80665, 2e-4, 8e-4),
                            coriolis_f=1e-4, tracers=("T", "S"),

@@ -230,3 +230,26 @@ def test_host_streamed_stepper_matches_resident_stepping(arch):
             got = np.frombuffer((C.c_char * nb).from_address(p.value), dtype=r.dtype).reshape(r.shape)
             assert np.array_equal(got, r), f.name
         mem.free()
+
+
+@pytest.mark.parametrize("ts", ["rk3", "ab2"])
+def test_checkpoint_restore_continues_bit_identically(arch, ts, tmp_path):
+    """checkpoint (parents of the prognostic fields, G⁻, clock) -> fresh model -> restore -> same trajectory, bit for bit
+    (checkpointer.jl; test_checkpointer.jl compares a restored run with an uninterrupted one)"""
+    import ocean_b200 as ob
+    cfg = Config((16, 12, 10), ((0, 1.6), (0, 1.2), (-1.0, 0.0)), "PPB", advection=("weno", 5), closure=[("lilly", 0.16, 1.0, 1.0)],
+                 buoyancy=("tracer",), coriolis_f=0.2, tracers=("b", "c"), timestepper=ts, bcs={"b": {"top": ("Flux", 1e-4)}})
+    a = cfg.b200_model(arch)
+    ob.set(a, **cfg.initial_conditions(12))
+    for _ in range(3):
+        ob.time_step(a, 1e-2)
+    path = ob.checkpoint(a, str(tmp_path / "ckpt.npz"))
+    for _ in range(3):
+        ob.time_step(a, 1e-2)
+    b = cfg.b200_model(arch)
+    ob.restore(b, path)
+    assert b.clock.iteration == 3 and b.clock.time == pytest.approx(3e-2)
+    for _ in range(3):
+        ob.time_step(b, 1e-2)
+    for (n, fa), fb in zip(a.prognostic_fields.items(), b.prognostic_fields.values()):
+        assert np.array_equal(fa.parent(), fb.parent()), n
