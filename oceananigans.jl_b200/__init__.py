@@ -18,7 +18,7 @@ from .models import (NonhydrostaticModel, Centered, WENO, ScalarDiffusivity, Sma
                      VerticallyImplicitTimeDiscretization, BuoyancyTracer, SeawaterBuoyancy, LinearEquationOfState, FPlane,
                      time_step, set, update_state)
 from .simulations import (Simulation, run, Callback, IterationInterval, TimeInterval, TimeStepWizard,  # noqa: F401
-                          conjure_time_step_wizard, NaNChecker)
+                          conjure_time_step_wizard, NaNChecker, NPZOutputWriter, Checkpointer)
 from .solvers import FFTBasedPoissonSolver, FourierTridiagonalPoissonSolver, BatchedTridiagonalSolver, solve  # noqa: F401
 from .distributed import Distributed, partition_x, neighbors, gather_x, all_reduce_scalar  # noqa: F401
 from .streaming import HostStreamedStepper, HostMember  # noqa: F401

@@ -77,6 +77,7 @@ class Simulation:
         self.stop_iteration, self.stop_time, self.wall_time_limit = stop_iteration, stop_time, wall_time_limit
         self.callbacks = {}
         self.callbacks["nan_checker"] = Callback(NaNChecker({"u": model.velocities["u"]}), IterationInterval(100))
+        self.output_writers = {}   # name -> NPZOutputWriter / Checkpointer (simulation.output_writers[:name] = ...)
         self.running = False
         self.initialized = False
         self.run_wall_time = 0.0
@@ -84,6 +85,38 @@ class Simulation:
 
     def add_callback(self, name, func, schedule=None):
         self.callbacks[name] = Callback(func, schedule)
+
+
+class NPZOutputWriter:
+    """Host-side output writer: the interiors of the named fields, copied device -> host when `schedule` fires and written
+    as <prefix>_iteration<N>.npz with the clock (the role of JLD2Writer / NetCDFWriter, src/OutputWriters/: every writer
+    starts with fetch_output's on_architecture(CPU(), ...) copy, fetch_output.jl:22).  `fields`: dict name -> Field."""
+
+    def __init__(self, model, fields, schedule, prefix="output", with_halos=False):
+        self.fields, self.schedule, self.prefix, self.with_halos = dict(fields), schedule, prefix, with_halos
+        self.written = []
+
+    def write(self, model):
+        import numpy as np
+        out = {n: (f.parent() if self.with_halos else np.ascontiguousarray(f.interior())) for n, f in self.fields.items()}
+        out["time"], out["iteration"] = np.float64(model.clock.time), np.int64(model.clock.iteration)
+        path = "%s_iteration%d.npz" % (self.prefix, model.clock.iteration)
+        np.savez(path, **out)
+        self.written.append(path)
+        return path
+
+
+class Checkpointer:
+    """Checkpointer(model, schedule; prefix): writes restartable states (checkpoint.py); `restore(model, path)` resumes"""
+
+    def __init__(self, model, schedule, prefix="checkpoint"):
+        self.schedule, self.prefix, self.written = schedule, prefix, []
+
+    def write(self, model):
+        from .checkpoint import checkpoint
+        path = checkpoint(model, "%s_iteration%d.npz" % (self.prefix, model.clock.iteration))
+        self.written.append(path)
+        return path
 
 
 def conjure_time_step_wizard(sim, schedule=None, **kw):
@@ -121,11 +154,17 @@ def time_step_simulation(sim):
         for cb in sim.callbacks.values():
             if cb.schedule(sim.model):
                 cb.func(sim)
+        for w in sim.output_writers.values():   # initialize!(sim): writers fire at iteration 0 too (run.jl:258-300)
+            if w.schedule(sim.model):
+                w.write(sim.model)
     dt = _aligned_time_step(sim, sim.dt)
     _models.time_step(sim.model, dt)
     for cb in sim.callbacks.values():
         if cb.schedule(sim.model):
             cb.func(sim)
+    for w in sim.output_writers.values():
+        if w.schedule(sim.model):
+            w.write(sim.model)
     sim.run_wall_time += _time.time() - t0
 
 

@@ -253,3 +253,24 @@ def test_checkpoint_restore_continues_bit_identically(arch, ts, tmp_path):
         ob.time_step(b, 1e-2)
     for (n, fa), fb in zip(a.prognostic_fields.items(), b.prognostic_fields.values()):
         assert np.array_equal(fa.parent(), fb.parent()), n
+
+
+def test_simulation_output_writer_and_checkpointer(arch, tmp_path):
+    """run!(simulation) with an output writer and a checkpointer (host plumbing: device -> host copies on a schedule)"""
+    import ocean_b200 as ob
+    cfg = Config((16, 16, 8), ((0, 1.0), (0, 1.0), (-0.5, 0.0)), "PPB", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
+                 buoyancy=("tracer",), tracers=("b",))
+    m = cfg.b200_model(arch)
+    ob.set(m, **cfg.initial_conditions(2))
+    sim = ob.Simulation(m, Δt=1e-3, stop_iteration=6)
+    sim.output_writers["fields"] = ob.NPZOutputWriter(m, {"u": m.velocities["u"], "b": m.tracers["b"]}, ob.IterationInterval(3),
+                                                      prefix=str(tmp_path / "out"))
+    sim.output_writers["ckpt"] = ob.Checkpointer(m, ob.IterationInterval(6), prefix=str(tmp_path / "ckpt"))
+    ob.run(sim)
+    w = sim.output_writers["fields"].written
+    assert [p.split("iteration")[-1] for p in w] == ["0.npz", "3.npz", "6.npz"]
+    z = np.load(w[-1])
+    assert z["u"].shape == (8, 16, 16) and int(z["iteration"]) == 6 and np.array_equal(z["b"], m.tracers["b"].interior())
+    m2 = cfg.b200_model(arch)
+    ob.restore(m2, sim.output_writers["ckpt"].written[-1])
+    assert m2.clock.iteration == 6 and np.array_equal(m2.velocities["u"].parent(), m.velocities["u"].parent())
