@@ -1,4 +1,4 @@
-"""Print per-field parity errors (B200 vs oracle) for a named test configuration: python tools/debug_parity.py les_amd"""
+"""Print per-field parity errors (B200 vs oracle) for a named test configuration: python tests/debug_parity.py les_amd"""
 import os
 import sys
 
