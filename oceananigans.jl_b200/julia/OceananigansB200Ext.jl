@@ -12,7 +12,7 @@ using Oceananigans.Grids: RectilinearGrid, topology, Periodic, Bounded, Flat, ha
 using Oceananigans.Models.NonhydrostaticModels: NonhydrostaticModel
 using Oceananigans.TimeSteppers: RungeKutta3TimeStepper, QuasiAdamsBashforth2TimeStepper, tick!, Clock
 using Oceananigans.Advection: WENO, Centered
-using Oceananigans.TurbulenceClosures: ScalarDiffusivity, Smagorinsky, AnisotropicMinimumDissipation
+using Oceananigans.TurbulenceClosures: ScalarDiffusivity, Smagorinsky, AnisotropicMinimumDissipation, VerticallyImplicitTimeDiscretization
 using Oceananigans.BoundaryConditions: FieldBoundaryConditions, BoundaryCondition, Flux, Value, Gradient, Open, Periodic as PBC
 import Oceananigans.Architectures as AC
 import Oceananigans.TimeSteppers: time_step!, update_state!, cache_previous_tendencies!
