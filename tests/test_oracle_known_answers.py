@@ -288,3 +288,143 @@ def test_oracle_array_valued_boundary_conditions_reduce_to_constants():
     for _ in range(2):
         a.time_step(1e-3); b.time_step(1e-3)
     assert all(np.array_equal(x.data, y.data) for x, y in zip(a.prognostic, b.prognostic))
+
+
+# ---- more of test/test_dynamics.jl, restated on the oracle: these have analytic answers, so they pin the restatement ----
+def _fld(om, name):
+    return {"u": om.u, "v": om.v, "w": om.w}.get(name) or om.tracers[om.tracer_names.index(name)]
+
+
+@pytest.mark.parametrize("vi", [False, True], ids=["explicit", "vertically_implicit"])
+@pytest.mark.parametrize("ts", ["rk3", "ab2"])
+@pytest.mark.parametrize("fieldname", ["u", "v", "c"])
+def test_oracle_diffusion_simple(fieldname, ts, vi):
+    """test_diffusion_simple (test_dynamics.jl:15-30): a constant field stays constant under ScalarDiffusivity(ν=1, κ=1),
+    Δt = 1, 10 steps, on a (1, 1, 16) grid -- explicit and vertically implicit"""
+    g = M.Grid((1, 1, 16), ((0, 1.0), (0, 1.0), (-1.0, 0.0)), topology=("P", "P", "B"), halo=(1, 1, 1))
+    om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=1.0, kappa=1.0, vertically_implicit=vi)], tracers=("c",), timestepper=ts)
+    f = _fld(om, fieldname)
+    f.interior[...] = np.pi
+    om.update_state()
+    for _ in range(10):
+        om.time_step(1.0)
+    assert np.allclose(_fld(om, fieldname).interior, np.pi, rtol=1e-8)
+
+
+@pytest.mark.parametrize("vi", [False, True], ids=["explicit", "vertically_implicit"])
+@pytest.mark.parametrize("direction,fieldnames", [(0, ("v", "w", "c")), (1, ("u", "w", "c")), (2, ("u", "v", "c"))])
+def test_oracle_diffusion_of_a_cosine(direction, fieldnames, vi):
+    """test_diffusion_cosine (test_dynamics.jl:63-85, 485-560): cos(2ξ) on a Bounded direction of length π/2, N = 128, decays as
+    exp(-κ m² t) (κ = 1, m = 2, 5 steps of Δt = 1e-6 L²); atol = rtol = 1e-6.  VerticallyImplicit only matters along z."""
+    N, L = 128, np.pi / 2
+    size, ext, topo = [1, 1, 1], [(0, 1.0)] * 3, ["P", "P", "P"]
+    size[direction], ext[direction], topo[direction] = N, (0, L), "B"
+    if vi and direction != 2:
+        pytest.skip("VerticallyImplicitTimeDiscretization needs a Bounded z (reference: error)")
+    g = M.Grid(tuple(size), tuple(ext), topology=tuple(topo), halo=(1, 1, 1))
+    for name in fieldnames:
+        om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=1.0, kappa=1.0, vertically_implicit=vi)], tracers=("c",))
+        f = _fld(om, name)
+        xi = g.nodes(direction, "c")
+        shape = [1, 1, 1]
+        shape[2 - direction] = N
+        f.interior[...] = np.cos(2 * xi).reshape(shape)
+        om.update_state()
+        dt = 1e-6 * L ** 2
+        for _ in range(5):
+            om.time_step(dt)
+        want = np.exp(-4 * 5 * dt) * np.cos(2 * xi).reshape(shape)
+        assert np.allclose(_fld(om, name).interior, want, atol=1e-6, rtol=1e-6), (direction, name)
+
+
+@pytest.mark.parametrize("topology", ["PPP", "PPB", "BBB"])
+@pytest.mark.parametrize("fieldname", ["u", "v", "w", "c"])
+def test_oracle_scalar_diffusivity_budget(fieldname, topology):
+    """test_ScalarDiffusivity_budget (test_dynamics.jl:32-54, 410-453): the mean of a randomly initialised field is conserved
+    by isotropic diffusion (10 steps of Δt = 1e-4 Δ²/κ)"""
+    if fieldname == "w" and topology != "PPP" or fieldname in ("u", "v") and topology == "BBB":
+        pytest.skip("the reference tests the budget of wall-normal velocities only on periodic directions")
+    N = 8
+    g = M.Grid((N, N, N), ((0, 1.0),) * 3, topology=tuple(topology), halo=(1, 1, 1))
+    om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=1.0, kappa=1.0)], tracers=("c",))
+    f = _fld(om, fieldname)
+    f.interior[...] = np.random.default_rng(3).uniform(0, 1, f.interior.shape)
+    m0 = f.interior.mean()
+    om.update_state()
+    dt = 1e-4 * (1.0 / N) ** 2
+    for _ in range(10):
+        om.time_step(dt)
+    assert np.isclose(_fld(om, fieldname).interior.mean(), m0, rtol=1e-8)
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched_faces"])
+def test_oracle_internal_wave(stretched):
+    """internal_wave_dynamics_test with NonhydrostaticModel (test_internal_wave_dynamics.jl; test_dynamics.jl:624-691): a
+    Gaussian internal-wave packet (k = 1, m = 16, f = 0.2, N = 1) on 128 x 1 x 128, (Periodic, Periodic, Bounded), 10 steps of
+    Δt = 0.01/σ: mean((u - u_exact)²)/mean(u_exact²) < 1e-4.  Pins buoyancy, Coriolis, the hydrostatic/nonhydrostatic
+    pressure split and the time stepper together."""
+    Nx = Nz = 128
+    L = 2 * np.pi
+    nu, z0, delta, a0, m, k, f, NN = 1e-9, -L / 3, L / 20, 1e-3, 16, 1, 0.2, 1.0
+    sigma = np.sqrt((NN ** 2 * k ** 2 + f ** 2 * m ** 2) / (k ** 2 + m ** 2))
+    dt = 0.01 / sigma
+    cg = m * sigma / (k ** 2 + m ** 2) * (f ** 2 / sigma ** 2 - 1)
+    U = a0 * k * sigma / (sigma ** 2 - f ** 2)
+    V = a0 * k * f / (sigma ** 2 - f ** 2)
+    W = a0 * m * sigma / (sigma ** 2 - NN ** 2)
+    B = a0 * m * NN ** 2 / (sigma ** 2 - NN ** 2)
+    a = lambda x, z, t: np.exp(-(z - cg * t - z0) ** 2 / (2 * delta) ** 2)
+    u = lambda x, z, t: a(x, z, t) * U * np.cos(k * x + m * z - sigma * t)
+    v = lambda x, z, t: a(x, z, t) * V * np.sin(k * x + m * z - sigma * t)
+    w = lambda x, z, t: a(x, z, t) * W * np.cos(k * x + m * z - sigma * t)
+    b = lambda x, z, t: a(x, z, t) * B * np.sin(k * x + m * z - sigma * t) + NN ** 2 * z
+    zext = np.linspace(-L, 0, Nz + 1) if stretched else (-L, 0.0)   # "regularly spaced vertically stretched grid": explicit faces
+    g = M.Grid((Nx, 1, Nz), ((0, L), (0, L), zext), topology=("P", "P", "B"), halo=(1, 1, 1))
+    om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=nu, kappa=nu)], buoyancy=("tracer",), coriolis_f=f, tracers=("b",))
+    X = lambda loc: g.nodes(0, loc)[None, None, :]
+    Z = lambda loc: g.nodes(2, loc)[:, None, None]
+    om.set(u=u(X("f"), Z("c"), 0), v=v(X("c"), Z("c"), 0), w=w(X("c"), Z("f"), 0), b=b(X("c"), Z("c"), 0))
+    for _ in range(10):
+        om.time_step(dt)
+    ua = u(X("f"), Z("c"), 10 * dt) * np.ones_like(om.u.interior)
+    err = np.mean((om.u.interior - ua) ** 2) / np.mean(ua ** 2)
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("vi", [False, True], ids=["explicit", "vertically_implicit"])
+def test_oracle_taylor_green_reference_size(vi):
+    """taylor_green_vortex_test exactly as in the reference (test_dynamics.jl:214-259): 64 x 64 x 2, extent 1, ν = 1, AB2,
+    Δt = Δx²/(10π ν), 10 steps; max relative error of u and v < 5e-6 -- explicit and VerticallyImplicitTimeDiscretization"""
+    N = 64
+    g = M.Grid((N, N, 2), ((0, 1.0), (0, 1.0), (-1.0, 0.0)), topology=("P", "P", "B"), halo=(1, 1, 1))
+    om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=1.0, kappa=0.0, vertically_implicit=vi)], timestepper="ab2")
+    yc, xc = g.nodes(1, "c")[None, :, None], g.nodes(0, "c")[None, None, :]
+    ones = np.ones((2, 1, 1))
+    om.set(u=-np.sin(2 * np.pi * yc) * np.ones((1, 1, N)) * ones, v=np.sin(2 * np.pi * xc) * np.ones((1, N, 1)) * ones)
+    dt = (1 / (10 * np.pi)) * (1.0 / N) ** 2
+    for _ in range(10):
+        om.time_step(dt)
+    t = 10 * dt
+    ua = -np.sin(2 * np.pi * yc) * np.exp(-4 * np.pi ** 2 * t) * np.ones((1, 1, N)) * ones
+    va = np.sin(2 * np.pi * xc) * np.exp(-4 * np.pi ** 2 * t) * np.ones((1, N, 1)) * ones
+    assert np.abs((om.u.interior - ua) / ua).max() < 5e-6
+    assert np.abs((om.v.interior - va) / va).max() < 5e-6
+
+
+def test_oracle_passive_tracer_advection():
+    """passive_tracer_advection_test (test_dynamics.jl:175-206, 617-622): a Gaussian of T advected by (U, V) = (0.5, 0.8) on
+    128 x 128 x 2, QuasiAdamsBashforth2, 100 steps, SeawaterBuoyancy with T, S: relative error < 1e-4"""
+    N, kap, Nt = 128, 1e-12, 100
+    L, U, V = 1.0, 0.5, 0.8
+    d, x0, y0 = L / 15, L / 2, L / 2
+    dt = 0.05 * L / N / np.sqrt(U * U + V * V)
+    T = lambda x, y, t: np.exp(-((x - U * t - x0) ** 2 + (y - V * t - y0) ** 2) / (2 * d ** 2))
+    g = M.Grid((N, N, 2), ((0, L), (0, L), (-L, 0.0)), topology=("P", "P", "B"), halo=(1, 1, 1))
+    om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=kap, kappa=kap)],
+                 buoyancy=("seawater", 9.80665, 1.67e-4, 7.8e-4), tracers=("T", "S"), timestepper="ab2")
+    xc, yc, one = g.nodes(0, "c")[None, None, :], g.nodes(1, "c")[None, :, None], np.ones((2, 1, 1))
+    om.set(u=U * np.ones((2, N, N)), v=V * np.ones((2, N, N)), T=T(xc, yc, 0) * one)
+    for _ in range(Nt):
+        om.time_step(dt)
+    Ta = T(xc, yc, Nt * dt) * one
+    assert np.mean((om.tracers[0].interior - Ta) ** 2) / np.mean(Ta ** 2) < 1e-4
