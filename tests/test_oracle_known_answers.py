@@ -428,3 +428,22 @@ def test_oracle_passive_tracer_advection():
         om.time_step(dt)
     Ta = T(xc, yc, Nt * dt) * one
     assert np.mean((om.tracers[0].interior - Ta) ** 2) / np.mean(Ta ** 2) < 1e-4
+
+
+@pytest.mark.parametrize("topology,names,sides", [
+    ("PBB", ("u", "c"), ("north", "south", "top", "bottom")),
+    ("BPB", ("v", "c"), ("east", "west", "top", "bottom")),
+    ("BBP", ("w", "c"), ("east", "west", "north", "south")),
+])
+def test_oracle_flux_boundary_condition_budget(topology, names, sides):
+    """test_nonhydrostatic_flux_budget (test_boundary_conditions_integration.jl:32-56, 672-721): a 2 x 2 x 2 model with a Flux
+    boundary condition of +-π on one side, field zero, one step of Δt = 1 (default RK3, Centered(2)): mean(ϕ) = π t / L"""
+    Ls = {"east": 0.3, "west": 0.3, "north": 0.4, "south": 0.4, "top": 0.5, "bottom": 0.5}
+    for name in names:
+        for side in sides:
+            direction = 1 if side in ("west", "south", "bottom") else -1
+            g = M.Grid((2, 2, 2), ((0, 0.3), (0, 0.4), (0, 0.5)), topology=tuple(topology), halo=(1, 1, 1))
+            om = M.Model(g, advection=("centered", 2), tracers=("c",), boundary_conditions={name: {side: ("flux", np.pi * direction)}})
+            om.update_state()
+            om.time_step(1.0)
+            assert np.isclose(_fld(om, name).interior.mean(), np.pi * 1.0 / Ls[side], rtol=1e-10), (topology, name, side)
