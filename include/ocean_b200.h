@@ -79,7 +79,8 @@ enum {
 
 /* RectilinearGrid (src/Grids/rectilinear_grid.jl:3-24).  Spacing arrays are passed exactly as the host
  * constructed them (grid_generation.jl:34-156): for a stretched z, dzf has Nz+2Hz+1 entries with logical
- * index k at dzf[k+Hz]; dzc has Nz+2Hz(+1 if Bounded) entries with logical k at dzc[k+Hz-1].  NULL => regular. */
+ * index k at dzf[k+Hz]; dzc has Nz+2Hz entries (Bounded z; one fewer when z is Periodic) with logical k at
+ * dzc[k+Hz-1].  NULL => regular. */
 typedef struct {
     int32_t float_type;     /* ob_float_type */
     int32_t N[3], H[3];
