@@ -447,3 +447,40 @@ def test_oracle_flux_boundary_condition_budget(topology, names, sides):
             om.update_state()
             om.time_step(1.0)
             assert np.isclose(_fld(om, name).interior.mean(), np.pi * 1.0 / Ls[side], rtol=1e-10), (topology, name, side)
+
+
+def test_oracle_les_closures_on_uniform_shear():
+    """Analytic values of the eddy viscosities for u = S z (not in the reference's tests, which only check that LES closures
+    time-step): Smagorinsky νₑ = (cₛ Δ)² √(2 Σᵢⱼ Σᵢⱼ) = cₛ² (Δx Δy Δz)^{2/3} |S| (smagorinsky.jl:90-104), Lilly's stratification
+    factor √(1 - min(1, Cb N²/Σ²)) with N² from b = N² z (lilly_coefficient.jl:129-142), and AMD νₑ = 0 for a laminar shear
+    (r = -Δₖ² ∂ₖuᵢ ∂ₖuⱼ Σᵢⱼ = 0: anisotropic_minimum_dissipation.jl:247-290)."""
+    S, N2, cs, Cb = 0.7, 0.05, 0.16, 1.0
+    g = M.Grid((6, 6, 12), ((0, 1.2), (0, 0.6), (-1.8, 0.0)), topology=("P", "P", "B"), halo=(3, 3, 3))
+    zc = g.nodes(2, "c")[:, None, None]
+    d3 = (0.2 * 0.1 * 0.15)
+    cases = [(M.Smagorinsky(coefficient=cs, Pr=1.0), cs ** 2 * d3 ** (2 / 3) * S),
+             (M.SmagorinskyLilly(C=cs, Cb=Cb, Pr=1.0), cs ** 2 * np.sqrt(1 - min(1.0, Cb * N2 / (S ** 2 / 2))) * d3 ** (2 / 3) * S),
+             (M.AnisotropicMinimumDissipation(), 0.0)]
+    for closure, want in cases:
+        om = M.Model(g, advection=("centered", 2), closure=[closure], buoyancy=("tracer",), tracers=("b",))
+        om.u.interior[...] = S * zc * np.ones((1, 6, 6))
+        om.tracers[0].interior[...] = N2 * zc * np.ones((1, 6, 6))
+        om.update_state()
+        nue = om.nue[0].interior[2:-2]          # away from the walls (one-sided halo values there)
+        assert np.allclose(nue, want, rtol=1e-10, atol=1e-14), (type(closure).__name__, nue.mean(), want)
+
+
+@pytest.mark.parametrize("ts,tol", [("rk3", 1e-9), ("ab2", 2e-5)])
+def test_oracle_inertial_oscillation(ts, tol):
+    """A uniform flow on an f-plane rotates at the inertial frequency: u + i v = (u₀ + i v₀) e^{-i f t} (the z-axis case of
+    inertial_oscillations_work_with_rotation_in_different_axis, test_dynamics.jl:354-396; FPlane, coriolis_schemes.jl:67-68)."""
+    f, u0, dt, n = 1.3, 0.4, 1e-3, 50
+    g = M.Grid((4, 4, 4), ((0, 1.0),) * 3, topology=("P", "P", "P"), halo=(1, 1, 1))
+    om = M.Model(g, advection=("centered", 2), coriolis_f=f, timestepper=ts)
+    om.set(u=u0 * np.ones((4, 4, 4)))
+    for _ in range(n):
+        om.time_step(dt)
+    t = n * dt
+    assert np.allclose(om.u.interior, u0 * np.cos(f * t), rtol=0, atol=tol)
+    assert np.allclose(om.v.interior, -u0 * np.sin(f * t), rtol=0, atol=tol)
+    assert np.abs(om.w.interior).max() < 1e-15
