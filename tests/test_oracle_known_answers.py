@@ -484,3 +484,38 @@ def test_oracle_inertial_oscillation(ts, tol):
     assert np.allclose(om.u.interior, u0 * np.cos(f * t), rtol=0, atol=tol)
     assert np.allclose(om.v.interior, -u0 * np.sin(f * t), rtol=0, atol=tol)
     assert np.abs(om.w.interior).max() < 1e-15
+
+
+@pytest.mark.parametrize("stretched", [False, True])
+def test_oracle_stratified_fluid_remains_at_rest(stretched):
+    """b = N² z with zero velocity is an exact discrete steady state: the hydrostatic pressure anomaly balances buoyancy level by
+    level (update_hydrostatic_pressure.jl:11-39; the untilted case of stratified_fluid_remains_at_rest..., test_dynamics.jl:261-352)"""
+    N2 = 1e-5
+    zext = stretched_faces(16, 2000.0) if stretched else (-2000.0, 0.0)
+    g = M.Grid((8, 8, 16), ((0, 2000.0), (0, 2000.0), zext), topology=("P", "P", "B"), halo=(3, 3, 3))
+    om = M.Model(g, advection=("weno", 5), buoyancy=("tracer",), tracers=("b",))
+    b0 = N2 * g.nodes(2, "c")[:, None, None] * np.ones((1, 8, 8))
+    om.set(b=b0)
+    for _ in range(10):
+        om.time_step(10.0)
+    assert max(np.abs(f.interior).max() for f in (om.u, om.v, om.w)) < 1e-13
+    assert np.allclose(om.tracers[0].interior, b0, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("kind", ["value", "gradient"])
+def test_oracle_linear_profile_is_steady_under_value_and_gradient_bcs(kind):
+    """A linear profile c = c₀ + γ z is a steady state of diffusion when the boundaries prescribe its own values (Value) or its
+    own slope (Gradient): checks the halo extrapolation formulas of fill_halo_regions_value_gradient.jl:35-119 through the
+    diffusive flux at the walls"""
+    Nz, gam, c0 = 12, 0.8, 0.3
+    g = M.Grid((4, 4, Nz), ((0, 1.0), (0, 1.0), (-1.5, 0.0)), topology=("P", "P", "B"), halo=(1, 1, 1))
+    if kind == "value":
+        bcs = {"c": {"top": ("value", c0), "bottom": ("value", c0 - 1.5 * gam)}}
+    else:
+        bcs = {"c": {"top": ("gradient", gam), "bottom": ("gradient", gam)}}
+    om = M.Model(g, advection=("centered", 2), closure=[M.ScalarDiffusivity(nu=0.0, kappa=0.2)], tracers=("c",), boundary_conditions=bcs)
+    prof = (c0 + gam * g.nodes(2, "c"))[:, None, None] * np.ones((1, 4, 4))
+    om.set(c=prof)
+    for _ in range(5):
+        om.time_step(1e-2)
+    assert np.allclose(om.tracers[0].interior, prof, rtol=1e-13, atol=1e-14)
