@@ -1,0 +1,580 @@
+// tendency_stage.cuh -- the fused tendency kernel, staged-ring form (default on the interior fast path).
+//
+// One CTA computes ALL tendencies of a 32 x (W*R) tile of columns (Gu, Gv, Gw and one tracer per pass) while it marches
+// in k.  Every stencil operand is read from shared memory:
+//
+//   * a PRODUCER warp feeds a ring of D = N+2 levels; each level holds the halo'd (32+2N) x (W*R+2N) planes of u, v, w
+//     and the tracer, brought in by TMA (cp.async.bulk.tensor.3d, one box per field and level, completion on an mbarrier)
+//     -- or by cp.async when the row pitch of the parent arrays is not a multiple of 16 bytes (Float32 with odd padding).
+//     Levels k .. k+N live in the ring; the N-1 levels below k of a thread's own column are kept in registers, so the
+//     z-lines of the stencils cost no memory traffic at all.
+//   * W COMPUTE warps: warp w owns rows w*R .. w*R+R-1 of the tile, lane l the column i0+l.  A thread evaluates, per
+//     level and tendency, the flux through the west face and the south face of each of its cells and the upper face;
+//     the east flux comes from lane+1 (shuffle), the north flux from the next row (register, or the next warp's
+//     published south flux), the lower flux from the previous level (register).  Every face flux is evaluated ONCE.
+//   * a HELPER warp evaluates the tile's east-edge x fluxes (lanes = rows) and north-edge y fluxes (lanes = columns) and
+//     publishes them, so tiles advance by the full 32 x (W*R) cells: no overlap lanes, no overlap rows.
+//   * warps never meet at a CTA barrier: ring slots are recycled through full/empty mbarriers (the empty barrier of a
+//     level needs one arrival per consumer warp), published fluxes through one mbarrier per publishing warp.  Because a
+//     level k+N can only be loaded after EVERY consumer has released level k-2, two consumer warps are never more than one
+//     level apart, which is what makes two publication slots sufficient.
+//
+// The arithmetic is flux_from_values() / the closure-flux expressions of tendency_fast.cuh, operand for operand, so the
+// results are bit-identical to march_fast_body (tests/test_gpu_parity.py checks this and the oracle comparison).
+//
+// Reference semantics: compute_nonhydrostatic_tendencies.jl:107-150 (one kernel per tendency there),
+// nonhydrostatic_tendency_kernel_functions.jl:71-302, upwind_biased_advective_fluxes.jl:23-121.
+#pragma once
+#include <cuda.h>
+#include "tendency_fast.cuh"
+#include "tendency_tma.cuh"
+
+namespace ob {
+
+template <typename T, int N, int W, int R>
+struct StageCfg {
+    static constexpr int EPV = 16 / (int)sizeof(T);
+    static constexpr int TXC = 32, TYC = W * R;
+    static constexpr int TW = ((TXC + 2 * N + (EPV - 1)) + EPV - 1) / EPV * EPV;   // box width: 16-byte multiple incl. the origin round-down
+    static constexpr int TH = TYC + 2 * N;
+    static constexpr int BOX_BYTES = TW * TH * (int)sizeof(T);
+    static constexpr int PLANE_BYTES = (BOX_BYTES + 127) / 128 * 128;
+    static constexpr int PL = PLANE_BYTES / (int)sizeof(T);   // elements between the planes of consecutive fields
+    static constexpr int D = N + 2;                           // ring depth: levels k .. k+N + one in flight
+    static constexpr int NF = 4;                              // staged fields: u, v, w, tracer of the pass
+    static constexpr int NQ = 4;                              // tendencies per pass
+    static constexpr int NV = 1 + OB_SHARED_CL;               // flux components: advective + shared closures
+    static constexpr int LEVEL_BYTES = NF * PLANE_BYTES;
+    static constexpr int RING_BYTES = D * LEVEL_BYTES;
+    static constexpr int YX_SLOT = (W + 1) * NQ * NV * 32;    // published south fluxes: [w][q][v][lane], w = W: helper (north edge)
+    static constexpr int XE_SLOT = NQ * NV * 32;              // published east-edge fluxes: [q][v][row]
+    static constexpr int XCH_BYTES = 2 * (YX_SLOT + XE_SLOT) * (int)sizeof(T);
+    static constexpr int NBAR = 2 * D + 2 * (W + 1);
+    static constexpr int SMEM_BYTES = RING_BYTES + XCH_BYTES + NBAR * 8;
+    static constexpr int THREADS = (W + 2) * 32;
+};
+
+// which (float type, scheme) combinations have a staged-ring kernel, and its tile shape (W compute warps x R rows each)
+template <typename T, class S>
+struct StageSel {
+    static constexpr bool built = S::kind == ADV_WENO && S::n == 3;
+    static constexpr int W = 8, R = 2;
+    static constexpr int ALT_W = 16, ALT_R = 1;
+};
+
+struct StageLaunch {
+    int ntx, nty, nkc;      // tiles in x, y and k-chunks
+    int kbeg, kend, klen;   // levels kbeg .. kend in chunks of klen
+    int use_tma;            // 0: the producer warp copies with cp.async (row pitch not 16-byte aligned)
+    int npass;              // 1 + extra tracers
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(void *dst, const void *src, int bytes, bool valid) {
+    const int sz = valid ? bytes : 0;
+    if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+
+// The levels k .. k+N of the ring as seen by one thread: pl[d] points at field 0 of level k+d, already offset to the
+// thread's own point; field f is PL elements further, a row TW elements.
+template <typename T, int N, int TW, int PL>
+struct StageView {
+    const T *pl[N + 1];
+    __device__ __forceinline__ T at(int f, int d, int dx, int dy) const { return pl[d][f * PL + dy * TW + dx]; }
+};
+
+// own-column value of field F at level k+dl, dl in [-(N-1), N]: below k from the register history (h[m] = level k-(N-1)+m)
+template <typename T, int N, int TW, int PL>
+__device__ __forceinline__ T zval(const StageView<T, N, TW, PL> &V, const T (&h)[N - 1], int f, int dl) {
+    if (dl < 0) return h[N - 1 + dl];
+    return V.at(f, dl, 0, 0);
+}
+
+// Advective flux of tendency WHICH through the face the thread owns in direction ADV (0: west, 1: south, 2: upper face
+// k+1), from the staged planes; the operands and their order are those of fast_flux (tendency_fast.cuh).
+// hq: history of the advected field; ha: history of the advecting component whose z-line is needed (u for ADV 0, v for 1, w for 2)
+template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR, int TW, int PL>
+__device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const T (&hq)[N - 1], const T (&ha)[N - 1], const FastGeom<T, STR> &g, int k) {
+    constexpr int NC = N - 1;
+    constexpr int QF = WHICH;    // field index of the advected quantity (3 = the tracer of the pass)
+    constexpr int AF = ADV;      // field index of the advecting component
+    constexpr int LV = ADV == 2 ? 1 : 0;   // the upper face belongs to level k+1
+    T s[2 * N];
+#pragma unroll
+    for (int m = 0; m < 2 * N; m++) {
+        if constexpr (ADV == 0) s[m] = V.at(QF, 0, m - N, 0);
+        else if constexpr (ADV == 1) s[m] = V.at(QF, 0, 0, m - N);
+        else s[m] = zval<T, N, TW, PL>(V, hq, QF, 1 - N + m);
+    }
+    if constexpr (WHICH == 3) {
+        T a[1] = {V.at(AF, LV, 0, 0)};
+        return flux_from_values<T, N, FAST, WHICH, ADV, STR>(s, a, g, k + LV);
+    } else {
+        T a[2 * NC];
+#pragma unroll
+        for (int m = 0; m < 2 * NC; m++) {
+            if constexpr (WHICH == 0) a[m] = V.at(AF, LV, m - NC, 0);
+            else if constexpr (WHICH == 1) a[m] = V.at(AF, LV, 0, m - NC);
+            else a[m] = zval<T, N, TW, PL>(V, ha, AF, LV - NC + m);
+        }
+        return flux_from_values<T, N, FAST, WHICH, ADV, STR>(s, a, g, k + LV);
+    }
+}
+
+// Non-advective terms from the staged planes: FastTerms (tendency_fast.cuh) with the velocity / tracer loads redirected to
+// shared memory (level offsets -1: register history of the own column; 0, +1: ring).  Closure fields (nu_e, kappa_e) and
+// pHY' stay on the global path: each is read at most a few times per cell.
+template <typename T, int N, bool STR, int TW, int PL>
+struct StageTerms {
+    const TendP<T> &P;
+    const FastGeom<T, STR> &G;
+    const StageView<T, N, TW, PL> &V;
+    const T (&hu)[N - 1], (&hv)[N - 1], (&hw)[N - 1], (&hc)[N - 1];
+    int eo;   // global element offset of the thread's (clamped) point at level k
+    int k;
+    int tstage;   // tracer index staged as field 3
+    __device__ __forceinline__ T fld(int f, int a, int b, int c) const {
+        if (c < 0) return f == 0 ? hu[N - 2] : f == 1 ? hv[N - 2] : f == 2 ? hw[N - 2] : hc[N - 2];
+        return V.at(f, c, a, b);
+    }
+    __device__ __forceinline__ T ldg(const T *p, int a, int b, int c) const { return __ldg(p + (a + b * G.sy + c * G.sz)); }
+    __device__ __forceinline__ const T *at(const Fld<T> &f) const { return f.p + f.off + eo; }
+    __device__ __forceinline__ T dzC(int c) const { return G.dzC(k + c); }
+    __device__ __forceinline__ T dzF(int c) const { return G.dzF(k + c); }
+    __device__ __forceinline__ T dx_u(int a, int b, int c) const { return (fld(0, a + 1, b, c) - fld(0, a, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dy_v(int a, int b, int c) const { return (fld(1, a, b + 1, c) - fld(1, a, b, c)) * G.rdy; }
+    __device__ __forceinline__ T dz_w(int a, int b, int c) const { return (fld(2, a, b, c + 1) - fld(2, a, b, c)) * G.rdzC(k + c); }
+    __device__ __forceinline__ T dx_v(int a, int b, int c) const { return (fld(1, a, b, c) - fld(1, a - 1, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dy_u(int a, int b, int c) const { return (fld(0, a, b, c) - fld(0, a, b - 1, c)) * G.rdy; }
+    __device__ __forceinline__ T dx_w(int a, int b, int c) const { return (fld(2, a, b, c) - fld(2, a - 1, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (fld(0, a, b, c) - fld(0, a, b, c - 1)) * G.rdzF(k + c); }
+    __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (fld(2, a, b, c) - fld(2, a, b - 1, c)) * G.rdy; }
+    __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (fld(1, a, b, c) - fld(1, a, b, c - 1)) * G.rdzF(k + c); }
+    __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * (dy_u(a, b, c) + dx_v(a, b, c)); }
+    __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * (dz_u(a, b, c) + dx_w(a, b, c)); }
+    __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * (dz_v(a, b, c) + dy_w(a, b, c)); }
+    __device__ __forceinline__ T If1(const T *f, int D, int a, int b, int c) const {
+        return T(0.5) * (ldg(f, a - (D == 0), b - (D == 1), c - (D == 2)) + ldg(f, a, b, c));
+    }
+    __device__ __forceinline__ T If2(const T *f, int D2, int D1, int a, int b, int c) const {
+        return T(0.5) * (If1(f, D1, a - (D2 == 0), b - (D2 == 1), c - (D2 == 2)) + If1(f, D1, a, b, c));
+    }
+    __device__ __forceinline__ T nu_ccc(int m, const T *ne, int a, int b, int c) const { return ne ? ldg(ne, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_ffc(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 1, 0, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_fcf(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 0, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_cff(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 1, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T ux(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dx_u(a, b, c))); }
+    __device__ __forceinline__ T uy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T uz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T vx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T vy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dy_v(a, b, c))); }
+    __device__ __forceinline__ T vz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzF(c)) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T wy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzF(c)) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_ccc(m, ne, a, b, c) * dz_w(a, b, c))); }
+    __device__ __forceinline__ const T *nue_ptr(int m) const { return P.cl[m].kind == CL_SCALAR ? nullptr : at(P.nue[m]); }
+    // diffusive flux of the staged tracer along D at the face (a, b, c)
+    __device__ __forceinline__ T qflux(int m, const T *kf, int D, int a, int b, int c) const {
+        const int kind = P.cl[m].kind;
+        const T kap = kind == CL_SCALAR ? P.cl[m].kappa[tstage] : kind == CL_SMAG ? If1(kf, D, a, b, c) / P.cl[m].Pr[tstage] : If1(kf, D, a, b, c);
+        const T rd = D == 0 ? G.rdx : D == 1 ? G.rdy : G.rdzF(k + c);
+        const T A = D == 0 ? G.dy * dzC(c) : D == 1 ? G.dx * dzC(c) : G.dx * G.dy;
+        const T dc = (fld(3, a, b, c) - fld(3, a - (D == 0), b - (D == 1), c - (D == 2))) * rd;
+        return A * (-kap * dc);
+    }
+    // closure flux of tendency WHICH through the face this thread owns in direction D (D == 2: the UPPER face)
+    template <int WHICH, int D> __device__ __forceinline__ T own_closure_flux(int m) const {
+        if constexpr (WHICH == 3) {
+            const int kind = P.cl[m].kind;
+            const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][tstage]);
+            return qflux(m, kf, D, 0, 0, D == 2 ? 1 : 0);
+        } else {
+            const T *ne = nue_ptr(m);
+            if constexpr (WHICH == 0) return D == 0 ? ux(m, ne, -1, 0, 0) : D == 1 ? uy(m, ne, 0, 0, 0) : uz(m, ne, 0, 0, 1);
+            else if constexpr (WHICH == 1) return D == 0 ? vx(m, ne, 0, 0, 0) : D == 1 ? vy(m, ne, 0, -1, 0) : vz(m, ne, 0, 0, 1);
+            else return D == 0 ? wx(m, ne, 0, 0, 0) : D == 1 ? wy(m, ne, 0, 0, 0) : wz(m, ne, 0, 0, 0);
+        }
+    }
+    __device__ __forceinline__ T bpert(int c) const {
+        if (P.buoy == BUOY_TRACER) {
+            if (P.ib == tstage) return fld(3, 0, 0, c);
+            return ldg(at(P.c[P.ib]), 0, 0, c);
+        }
+        if (P.buoy == BUOY_SEAWATER) return P.grav * (P.alpha * ldg(at(P.c[P.iT]), 0, 0, c) - P.beta * ldg(at(P.c[P.iS]), 0, 0, c));
+        return 0;
+    }
+    // the tendency assemblers, same term order as FastTerms::finish<WHICH, true>
+    template <int WHICH> __device__ __forceinline__ T finish(T adv, T closure_term) const {
+        T r = -adv;
+        if constexpr (WHICH == 0) {
+            if (P.has_cor) {
+                const T fbar = T(0.5) * (P.f + P.f);
+                const T A = G.dx * dzC(0);
+                const T I = T(0.5) * (T(0.5) * (A * fld(1, -1, 0, 0) + A * fld(1, 0, 0, 0)) + T(0.5) * (A * fld(1, -1, 1, 0) + A * fld(1, 0, 1, 0)));
+                r = r - (-fbar * I * (1 / (G.dx * dzC(0))));
+            }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, -1, 0, 0)) * G.rdx; }
+        } else if constexpr (WHICH == 1) {
+            if (P.has_cor) {
+                const T fbar = T(0.5) * (P.f + P.f);
+                const T A = G.dy * dzC(0);
+                const T I = T(0.5) * (T(0.5) * (A * fld(0, 0, -1, 0) + A * fld(0, 1, -1, 0)) + T(0.5) * (A * fld(0, 0, 0, 0) + A * fld(0, 1, 0, 0)));
+                r = r - (fbar * I * (1 / (G.dy * dzC(0))));
+            }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, 0, -1, 0)) * G.rdy; }
+        } else if constexpr (WHICH == 2) {
+            if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
+        }
+        if (P.ncl > 0) r = r - closure_term;
+        return r;
+    }
+};
+
+// Per-thread state that survives from one level to the next.  NR rows per thread (compute warps: R, helper: 1).
+template <typename T, int N, int NR>
+struct StageCarry {
+    T h[4][NR][N - 1];                          // own-column history of u, v, w, tracer: levels k-(N-1) .. k-1
+    T lower[4][NR];                             // advective flux through the lower face, per tendency
+    T lower_c[4][NR][OB_SHARED_CL];             // closure fluxes through the lower face
+};
+
+template <typename T, int N, bool FAST, int W, int R, bool STR>
+__global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M, const StageLaunch L) {
+    using C = StageCfg<T, N, W, R>;
+    constexpr int TW = C::TW, PL = C::PL, D = C::D, NV = C::NV;
+    extern __shared__ __align__(128) unsigned char smem[];
+    T *ring = reinterpret_cast<T *>(smem);
+    T *xch = reinterpret_cast<T *>(smem + C::RING_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::RING_BYTES + C::XCH_BYTES);
+    uint64_t *full = bars, *empty = bars + D, *pub = bars + 2 * D;   // pub[2*w + slot], w = 1 .. W (W: helper)
+
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    const GridD<T> &gg = P.g;
+    const int Nx = gg.N[0], Ny = gg.N[1];
+    int b = blockIdx.x;
+    const int tile_x = b % L.ntx; b /= L.ntx;
+    const int tile_y = b % L.nty;
+    const int kc = b / L.nty;
+    const int pass = blockIdx.y;
+    const int i0 = 1 + tile_x * C::TXC, j0 = 1 + tile_y * C::TYC;
+    const int k0 = L.kbeg + kc * L.klen, k1 = min(k0 + L.klen - 1, L.kend);
+    const int kfirst = k0 - N, klast = k1 + N;
+    const bool mom = pass == 0;                 // CTA-uniform: pass 0 = momentum + tracer 0, pass p = tracer p alone
+    const int tstage = pass;
+    const bool has_tr = tstage < P.ntr;
+    const int nfields = has_tr ? 4 : 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < D; s++) { mbar_init(&full[s], L.use_tma ? 1 : 32); mbar_init(&empty[s], W + 1); }
+        for (int s = 0; s < 2 * (W + 1); s++) mbar_init(&pub[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tile origin in parent coordinates (0-based); the box starts on a 16-byte boundary of the row
+    const int cxu = i0 - N + gg.H[0] - 1;
+    const int cx0 = cxu & ~(C::EPV - 1), cy0 = j0 - N + gg.H[1] - 1;
+    const int sh = cxu - cx0;
+
+    // ---------------------------------------------------------------- producer warp --------------------------------
+    if (warp == W + 1) {
+        if (L.use_tma) {
+            if (lane == 0) {
+                for (int Lv = kfirst; Lv <= klast; Lv++) {
+                    const int n = Lv - kfirst, s = n % D;
+                    if (n >= D) mbar_wait(&empty[s], (uint32_t)(((n / D) - 1) & 1));
+                    unsigned char *dst = smem + s * C::LEVEL_BYTES;
+                    mbar_expect_tx(&full[s], nfields * C::BOX_BYTES);
+                    const int cz = Lv + gg.H[2] - 1;
+                    tma_load_3d(dst, &M.m[0], &full[s], cx0, cy0, cz);
+                    tma_load_3d(dst + C::PLANE_BYTES, &M.m[1], &full[s], cx0, cy0, cz);
+                    tma_load_3d(dst + 2 * C::PLANE_BYTES, &M.m[2], &full[s], cx0, cy0, cz);
+                    if (has_tr) tma_load_3d(dst + 3 * C::PLANE_BYTES, &M.m[3 + tstage], &full[s], cx0, cy0, cz);
+                }
+            }
+        } else {
+            // cp.async path: the 32 lanes copy the boxes element by element (zero-fill outside the parent array)
+            const int Px = P.u.sy, Py = (int)(P.u.sz / P.u.sy);
+            for (int Lv = kfirst; Lv <= klast; Lv++) {
+                const int n = Lv - kfirst, s = n % D;
+                if (n >= D) mbar_wait(&empty[s], (uint32_t)(((n / D) - 1) & 1));
+                const int cz = Lv + gg.H[2] - 1;
+                for (int f = 0; f < nfields; f++) {
+                    const Fld<T> &F = f == 0 ? P.u : f == 1 ? P.v : f == 2 ? P.w : P.c[tstage];
+                    T *dst = reinterpret_cast<T *>(smem + s * C::LEVEL_BYTES + f * C::PLANE_BYTES);
+                    const T *src = F.p + (long)cz * F.sz;
+                    for (int e = lane; e < C::TW * C::TH; e += 32) {
+                        const int yy = e / C::TW, xx = e - yy * C::TW;
+                        const int gx = cx0 + xx, gy = cy0 + yy;
+                        const bool ok = gx < Px && gy < Py;
+                        cp_async_elem(dst + e, src + (ok ? (long)gy * Px + gx : 0), (int)sizeof(T), ok);
+                    }
+                }
+                cp_async_mbar_arrive(&full[s]);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers ------------------------------------
+    FastGeom<T, STR> g;
+    g.init(gg, P.u.sy, P.u.sz);
+    const int ncl = P.ncl;
+    const bool share_cl = ncl >= 1;   // the host only launches this kernel with ncl <= OB_SHARED_CL
+    auto yx_at = [&](int slot, int w, int q, int v) -> T * { return xch + slot * (C::YX_SLOT + C::XE_SLOT) + ((w * C::NQ + q) * NV + v) * 32; };
+    auto xe_at = [&](int slot, int q, int v) -> T * { return xch + slot * (C::YX_SLOT + C::XE_SLOT) + C::YX_SLOT + (q * NV + v) * 32; };
+
+    // running ring positions: level k is in slot sk; level k+N (the newest one this level needs) in slot sn with phase pn
+    int sk = 0, sn = 0, pn = 0;
+    // wait for the levels kfirst .. kfirst+N-1 here; level k+N is awaited at the top of each iteration
+    for (int n = 0; n < N; n++) mbar_wait(&full[n], 0);
+    sn = N % D; pn = (N / D) & 1;
+
+    if (warp < W) {
+        // ------------------------------------------------------------ compute warp ---------------------------------
+        StageCarry<T, N, R> cy;
+        const int row0 = warp * R;
+        int own[R], eo_base[R];
+        bool live[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            own[r] = (row0 + r + N) * TW + lane + N + sh;
+            const int i = i0 + lane, j = j0 + row0 + r;
+            live[r] = i <= Nx && j <= Ny;
+            eo_base[r] = min(i, Nx + 1) + min(j, Ny + 1) * g.sy;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                cy.lower[q][r] = T(0);
+#pragma unroll
+                for (int m = 0; m < OB_SHARED_CL; m++) cy.lower_c[q][r][m] = T(0);
+#pragma unroll
+                for (int h = 0; h < N - 1; h++) cy.h[q][r][h] = T(0);
+            }
+        }
+        for (int k = kfirst; k <= k1; k++) {
+            mbar_wait(&full[sn], (uint32_t)pn);
+            const int mode = k >= k0 ? 2 : k == k0 - 1 ? 1 : 0;   // 2: full level, 1: upper fluxes only, 0: history only
+            const T *lev[N + 1];
+#pragma unroll
+            for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * (C::LEVEL_BYTES / (int)sizeof(T)); }
+            const int e = k - k0, xs = e & 1, xp = (e >> 1) & 1;
+            if (mode == 2) {
+                // phase A: the south fluxes of row 0, published for the warp below
+                StageView<T, N, TW, PL> V;
+#pragma unroll
+                for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + own[0];
+                StageTerms<T, N, STR, TW, PL> F{P, g, V, cy.h[0][0], cy.h[1][0], cy.h[2][0], cy.h[3][0], eo_base[0] + k * g.sz, k, tstage};
+                if (mom) {
+                    *(yx_at(xs, warp, 0, 0) + lane) = stage_flux<T, N, FAST, 0, 1, STR, TW, PL>(V, cy.h[0][0], cy.h[1][0], g, k);
+                    *(yx_at(xs, warp, 1, 0) + lane) = stage_flux<T, N, FAST, 1, 1, STR, TW, PL>(V, cy.h[1][0], cy.h[1][0], g, k);
+                    *(yx_at(xs, warp, 2, 0) + lane) = stage_flux<T, N, FAST, 2, 1, STR, TW, PL>(V, cy.h[2][0], cy.h[1][0], g, k);
+                    if (share_cl) {
+#pragma unroll
+                        for (int m = 0; m < OB_SHARED_CL; m++)
+                            if (m < ncl) {
+                                *(yx_at(xs, warp, 0, 1 + m) + lane) = F.template own_closure_flux<0, 1>(m);
+                                *(yx_at(xs, warp, 1, 1 + m) + lane) = F.template own_closure_flux<1, 1>(m);
+                                *(yx_at(xs, warp, 2, 1 + m) + lane) = F.template own_closure_flux<2, 1>(m);
+                            }
+                    }
+                }
+                if (has_tr) {
+                    *(yx_at(xs, warp, 3, 0) + lane) = stage_flux<T, N, FAST, 3, 1, STR, TW, PL>(V, cy.h[3][0], cy.h[1][0], g, k);
+                    if (share_cl) {
+#pragma unroll
+                        for (int m = 0; m < OB_SHARED_CL; m++)
+                            if (m < ncl) *(yx_at(xs, warp, 3, 1 + m) + lane) = F.template own_closure_flux<3, 1>(m);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && warp > 0) mbar_arrive(&pub[2 * warp + xs]);
+                // the fluxes published by the warp above (or the helper for the top warp) and by the helper (east edge)
+                mbar_wait(&pub[2 * (warp + 1) + xs], (uint32_t)xp);
+                if (warp + 1 != W) mbar_wait(&pub[2 * W + xs], (uint32_t)xp);
+            }
+            if (mode >= 1) {
+                auto tendency = [&](auto which_tag) {
+                    constexpr int WHICH = decltype(which_tag)::value;
+                    const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[tstage];
+                    T fy_next = T(0), cy_next[OB_SHARED_CL] = {T(0), T(0)};
+#pragma unroll
+                    for (int r = R - 1; r >= 0; r--) {   // top row first: its north flux is the published one
+                        StageView<T, N, TW, PL> V;
+#pragma unroll
+                        for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + own[r];
+                        const int eo = eo_base[r] + k * g.sz;
+                        StageTerms<T, N, STR, TW, PL> F{P, g, V, cy.h[0][r], cy.h[1][r], cy.h[2][r], cy.h[3][r], eo, k, tstage};
+                        const T (&hq)[N - 1] = cy.h[WHICH][r];
+                        const T upper = stage_flux<T, N, FAST, WHICH, 2, STR, TW, PL>(V, hq, cy.h[2][r], g, k);
+                        T cup[OB_SHARED_CL] = {T(0), T(0)};
+                        if (share_cl) {
+#pragma unroll
+                            for (int m = 0; m < OB_SHARED_CL; m++) if (m < ncl) cup[m] = F.template own_closure_flux<WHICH, 2>(m);
+                        }
+                        if (mode == 2) {
+                            const T fx = stage_flux<T, N, FAST, WHICH, 0, STR, TW, PL>(V, hq, cy.h[0][r], g, k);
+                            T fy, fy1, cyv[OB_SHARED_CL] = {T(0), T(0)}, cy1[OB_SHARED_CL] = {T(0), T(0)}, cx[OB_SHARED_CL] = {T(0), T(0)};
+                            if (r == 0) fy = *(yx_at(xs, warp, WHICH, 0) + lane);
+                            else fy = stage_flux<T, N, FAST, WHICH, 1, STR, TW, PL>(V, hq, cy.h[1][r], g, k);
+                            if (r == R - 1) fy1 = *(yx_at(xs, warp + 1, WHICH, 0) + lane);
+                            else fy1 = fy_next;
+                            T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
+                            if (lane == 31) fx1 = xe_at(xs, WHICH, 0)[row0 + r];
+                            if (share_cl) {
+#pragma unroll
+                                for (int m = 0; m < OB_SHARED_CL; m++)
+                                    if (m < ncl) {
+                                        cx[m] = F.template own_closure_flux<WHICH, 0>(m);
+                                        if (r == 0) cyv[m] = *(yx_at(xs, warp, WHICH, 1 + m) + lane);
+                                        else cyv[m] = F.template own_closure_flux<WHICH, 1>(m);
+                                        if (r == R - 1) cy1[m] = *(yx_at(xs, warp + 1, WHICH, 1 + m) + lane);
+                                        else cy1[m] = cy_next[m];
+                                    }
+                            }
+                            const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
+                            const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - cy.lower[WHICH][r]));
+                            T term = T(0);
+                            if (share_cl) {
+#pragma unroll
+                                for (int m = 0; m < OB_SHARED_CL; m++)
+                                    if (m < ncl) {
+                                        T cx1 = __shfl_down_sync(0xffffffffu, cx[m], 1);
+                                        if (lane == 31) cx1 = xe_at(xs, WHICH, 1 + m)[row0 + r];
+                                        const T d = Vi * ((cx1 - cx[m]) + (cy1[m] - cyv[m]) + (cup[m] - cy.lower_c[WHICH][r][m]));
+                                        term = m == 0 ? d : term + d;
+                                    }
+                            }
+                            const T res = F.template finish<WHICH>(adv, term);
+                            if (live[r]) G.p[G.off + eo] = res;
+                            fy_next = fy;
+#pragma unroll
+                            for (int m = 0; m < OB_SHARED_CL; m++) cy_next[m] = cyv[m];
+                        }
+                        cy.lower[WHICH][r] = upper;
+#pragma unroll
+                        for (int m = 0; m < OB_SHARED_CL; m++) cy.lower_c[WHICH][r][m] = cup[m];
+                    }
+                };
+                if (mom) {
+                    tendency(std::integral_constant<int, 0>{});
+                    tendency(std::integral_constant<int, 1>{});
+                    tendency(std::integral_constant<int, 2>{});
+                }
+                if (has_tr) tendency(std::integral_constant<int, 3>{});
+            }
+            // history shift: level k becomes k-1
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+#pragma unroll
+                    for (int h = 0; h + 1 < N - 1; h++) cy.h[f][r][h] = cy.h[f][r][h + 1];
+                    cy.h[f][r][N - 2] = lev[0][f * PL + own[r]];
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[sk]);
+            if (++sk == D) sk = 0;
+            if (++sn == D) { sn = 0; pn ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------------------ helper warp ----------------------------------
+        // edge A (north): lanes = columns, own point (i0+lane, j0+TYC); edge B (east): lanes = rows, own point (i0+32, j0+lane)
+        T hA[4][N - 1], hB[4][N - 1];
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+#pragma unroll
+            for (int h = 0; h < N - 1; h++) { hA[f][h] = T(0); hB[f][h] = T(0); }
+        const int ownA = (C::TYC + N) * TW + lane + N + sh;
+        const int rowB = min(lane, C::TYC - 1);
+        const int ownB = (rowB + N) * TW + 32 + N + sh;
+        const int eoA = min(i0 + lane, Nx + 1) + min(j0 + C::TYC, Ny + 1) * g.sy;
+        const int eoB = min(i0 + 32, Nx + 1) + min(j0 + rowB, Ny + 1) * g.sy;
+        for (int k = kfirst; k <= k1; k++) {
+            mbar_wait(&full[sn], (uint32_t)pn);
+            const T *lev[N + 1];
+#pragma unroll
+            for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * (C::LEVEL_BYTES / (int)sizeof(T)); }
+            if (k >= k0) {
+                const int e = k - k0, xs = e & 1;
+                {
+                    StageView<T, N, TW, PL> V;
+#pragma unroll
+                    for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + ownA;
+                    StageTerms<T, N, STR, TW, PL> F{P, g, V, hA[0], hA[1], hA[2], hA[3], eoA + k * g.sz, k, tstage};
+                    if (mom) {
+                        *(yx_at(xs, W, 0, 0) + lane) = stage_flux<T, N, FAST, 0, 1, STR, TW, PL>(V, hA[0], hA[1], g, k);
+                        *(yx_at(xs, W, 1, 0) + lane) = stage_flux<T, N, FAST, 1, 1, STR, TW, PL>(V, hA[1], hA[1], g, k);
+                        *(yx_at(xs, W, 2, 0) + lane) = stage_flux<T, N, FAST, 2, 1, STR, TW, PL>(V, hA[2], hA[1], g, k);
+                        if (share_cl) {
+#pragma unroll
+                            for (int m = 0; m < OB_SHARED_CL; m++)
+                                if (m < ncl) {
+                                    *(yx_at(xs, W, 0, 1 + m) + lane) = F.template own_closure_flux<0, 1>(m);
+                                    *(yx_at(xs, W, 1, 1 + m) + lane) = F.template own_closure_flux<1, 1>(m);
+                                    *(yx_at(xs, W, 2, 1 + m) + lane) = F.template own_closure_flux<2, 1>(m);
+                                }
+                        }
+                    }
+                    if (has_tr) {
+                        *(yx_at(xs, W, 3, 0) + lane) = stage_flux<T, N, FAST, 3, 1, STR, TW, PL>(V, hA[3], hA[1], g, k);
+                        if (share_cl) {
+#pragma unroll
+                            for (int m = 0; m < OB_SHARED_CL; m++)
+                                if (m < ncl) *(yx_at(xs, W, 3, 1 + m) + lane) = F.template own_closure_flux<3, 1>(m);
+                        }
+                    }
+                }
+                if (lane < C::TYC) {
+                    StageView<T, N, TW, PL> V;
+#pragma unroll
+                    for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + ownB;
+                    StageTerms<T, N, STR, TW, PL> F{P, g, V, hB[0], hB[1], hB[2], hB[3], eoB + k * g.sz, k, tstage};
+                    if (mom) {
+                        xe_at(xs, 0, 0)[lane] = stage_flux<T, N, FAST, 0, 0, STR, TW, PL>(V, hB[0], hB[0], g, k);
+                        xe_at(xs, 1, 0)[lane] = stage_flux<T, N, FAST, 1, 0, STR, TW, PL>(V, hB[1], hB[0], g, k);
+                        xe_at(xs, 2, 0)[lane] = stage_flux<T, N, FAST, 2, 0, STR, TW, PL>(V, hB[2], hB[0], g, k);
+                        if (share_cl) {
+#pragma unroll
+                            for (int m = 0; m < OB_SHARED_CL; m++)
+                                if (m < ncl) {
+                                    xe_at(xs, 0, 1 + m)[lane] = F.template own_closure_flux<0, 0>(m);
+                                    xe_at(xs, 1, 1 + m)[lane] = F.template own_closure_flux<1, 0>(m);
+                                    xe_at(xs, 2, 1 + m)[lane] = F.template own_closure_flux<2, 0>(m);
+                                }
+                        }
+                    }
+                    if (has_tr) {
+                        xe_at(xs, 3, 0)[lane] = stage_flux<T, N, FAST, 3, 0, STR, TW, PL>(V, hB[3], hB[0], g, k);
+                        if (share_cl) {
+#pragma unroll
+                            for (int m = 0; m < OB_SHARED_CL; m++)
+                                if (m < ncl) xe_at(xs, 3, 1 + m)[lane] = F.template own_closure_flux<3, 0>(m);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pub[2 * W + xs]);
+            }
+#pragma unroll
+            for (int f = 0; f < 4; f++) {
+#pragma unroll
+                for (int h = 0; h + 1 < N - 1; h++) { hA[f][h] = hA[f][h + 1]; hB[f][h] = hB[f][h + 1]; }
+                hA[f][N - 2] = lev[0][f * PL + ownA];
+                hB[f][N - 2] = lev[0][f * PL + ownB];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[sk]);
+            if (++sk == D) sk = 0;
+            if (++sn == D) { sn = 0; pn ^= 1; }
+        }
+    }
+}
+
+}  // namespace ob

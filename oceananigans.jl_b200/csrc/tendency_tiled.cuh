@@ -18,8 +18,11 @@
 // Inputs are read with ld.global.nc through L1 (coalesced along x); the kernel is FP64-issue bound, not HBM or
 // L1 bound, so no shared-memory staging of the input tile is needed.
 #pragma once
+#include <vector>
+#include <stdlib.h>
 #include "tendency.cuh"
 #include "tendency_tma.cuh"
+#include "tendency_stage.cuh"
 
 namespace ob {
 
@@ -71,7 +74,7 @@ __device__ __forceinline__ void march_body(const TendP<T> &P, int t, int i, int 
 }
 
 template <typename T, class S, bool FAST, int TY, int KC, int MINB>
-__global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc, int tx_lo, int ntx, int skip_lo, int skip_n) {
+__global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __grid_constant__ TendP<T> P, int nb, int nkc, int tx_lo, int ntx, int skip_lo, int skip_n, int wall_only) {
     __shared__ T sy[2][TY][32];
     __shared__ T sv[2][OB_SHARED_CL][TY][32];
     const int which = blockIdx.y;
@@ -80,7 +83,9 @@ __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __g
     const int b = blockIdx.x;
     int tile_x = tx_lo + b % ntx;
     if (tile_x >= skip_lo) tile_x += skip_n;   // complement launches: every tile except [skip_lo, skip_lo + skip_n)
-    const int tile_y = (b / ntx) % nty, kc = b / (ntx * nty);
+    const int tile_y = (b / ntx) % nty;
+    int kc = b / (ntx * nty);
+    if (wall_only) kc = kc ? nkc - 1 : 0;      // only the two wall-adjacent chunks (the staged-ring kernel does the interior)
     const int i = 1 + tile_x * 31 + (int)threadIdx.x, j = 1 + tile_y * (TY - 1) + (int)threadIdx.y;
     // k-chunks: with a Bounded z and a WENO scheme of buffer nb the first and last chunk are the nb wall-adjacent
     // levels (general path with the fallback chain); every other chunk is interior and takes the fast path
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_kernel(const __g
 }
 
 template <typename T, class S, int TY, int KC, int MINB>
-static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch, int tx_lo, int tx_hi, int invert) {
+static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, int *nlaunch, int tx_lo, int tx_hi, int invert, int wall_only = 0) {
     const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
     int nb = 0;
     long nkc = (Nz + KC - 1) / KC;
@@ -128,9 +133,10 @@ static cudaError_t launch_march(const TendP<T> &P, int fast, cudaStream_t st, in
     if (invert) { skip_lo = tx_lo; skip_n = tx_hi - tx_lo; ntx = ntx_all - skip_n; tx_lo = 0; }
     if (ntx <= 0) return cudaSuccess;
     if (ntx * nty * nkc > 2147483647L) return cudaErrorInvalidConfiguration;
-    dim3 grid((unsigned)(ntx * nty * nkc), 3 + P.ntr), block(32, TY);
-    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n);
-    else tendency_march_kernel<T, S, false, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n);
+    if (wall_only && nb == 0) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)(ntx * nty * (wall_only ? 2 : nkc)), 3 + P.ntr), block(32, TY);
+    if (S::kind == ADV_WENO && fast) tendency_march_kernel<T, S, true, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n, wall_only);
+    else tendency_march_kernel<T, S, false, TY, KC, MINB><<<grid, block, 0, st>>>(P, nb, (int)nkc, tx_lo, (int)ntx, skip_lo, skip_n, wall_only);
     *nlaunch += 1;
     return cudaGetLastError();
 }
@@ -257,6 +263,107 @@ static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st
     }
 }
 
+// ---- staged-ring kernel (tendency_stage.cuh) --------------------------------------------------------------------------
+// Applicable: WENO, (Periodic, Periodic, Periodic | Bounded) topology, at most OB_SHARED_CL closures, none vertically
+// implicit, 32-bit element offsets, the whole x range in one launch.
+template <typename T, class S>
+static bool stage_applicable(const TendP<T> &P) {
+    if (S::kind != ADV_WENO) return false;
+    const GridD<T> &g = P.g;
+    if (g.topo[0] != PERIODIC || g.topo[1] != PERIODIC || g.topo[2] == FLAT) return false;
+    if (P.ncl > OB_SHARED_CL) return false;
+    for (int m = 0; m < P.ncl; m++) if (P.cl[m].vi) return false;
+    if (P.u.sz * (long)(g.N[2] + 2 * g.H[2] + 1) >= 2147483647L) return false;
+    if (g.topo[2] == BOUNDED && g.N[2] <= 2 * S::n) return false;
+    for (int d = 0; d < 3; d++) if (g.H[d] < S::n) return false;
+    return true;
+}
+
+// tensor maps are cached per (pointer, shape): a model re-launches with the same parents every stage
+struct StageMapKey { const void *p; unsigned long long px, py, pz; int tw, th, esz; };
+static bool stage_map(CUtensorMap *out, const void *ptr, cuuint64_t Px, cuuint64_t Py, cuuint64_t Pz, int tw, int th, int esz) {
+    struct Entry { StageMapKey k; CUtensorMap m; };
+    static thread_local std::vector<Entry> cache;
+    for (const Entry &e : cache)
+        if (e.k.p == ptr && e.k.px == Px && e.k.py == Py && e.k.pz == Pz && e.k.tw == tw && e.k.th == th && e.k.esz == esz) { *out = e.m; return true; }
+    if (!encode_tiled_fn()) return false;
+    const cuuint64_t dims[3] = {Px, Py, Pz};
+    const cuuint64_t strides[2] = {Px * (cuuint64_t)esz, Px * Py * (cuuint64_t)esz};
+    const cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)th, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUtensorMap m;
+    if (encode_tiled_fn()(&m, esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    if (cache.size() > 256) cache.clear();
+    cache.push_back(Entry{StageMapKey{ptr, Px, Py, Pz, tw, th, esz}, m});
+    *out = m;
+    return true;
+}
+
+template <typename T, class S, int W, int R>
+static cudaError_t launch_stage(const TendP<T> &P, int fast, cudaStream_t st, int sm_count, int *nlaunch) {
+    if constexpr (S::kind != ADV_WENO) return cudaErrorNotSupported;
+    else {
+        constexpr int N = S::n;
+        using C = StageCfg<T, N, W, R>;
+        const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
+        StageLaunch L;
+        L.ntx = (Nx + C::TXC - 1) / C::TXC;
+        L.nty = (Ny + C::TYC - 1) / C::TYC;
+        const bool walls = P.g.topo[2] == BOUNDED;
+        L.kbeg = walls ? N + 1 : 1;
+        L.kend = walls ? Nz - N : Nz;
+        L.npass = P.ntr > 1 ? P.ntr : 1;
+        // chunk length: balance whole waves of CTAs (one CTA per SM) against the N+1 warm-up levels of every chunk
+        const long tiles = (long)L.ntx * L.nty;
+        const int nlev = L.kend - L.kbeg + 1;
+        const int sms = sm_count > 0 ? sm_count : 148;
+        double best = 1e300;
+        int best_nk = 1;
+        for (int nk = 1; nk <= nlev; nk++) {
+            const int len = (nlev + nk - 1) / nk;
+            if (len < 4 && nk > 1) break;
+            const long ctas = tiles * nk;   // pass 0 dominates: the tracer-only passes fill in behind it
+            const long waves = (ctas + sms - 1) / sms;
+            const double cost = (double)waves * (len + 2.0);
+            if (cost < best) { best = cost; best_nk = nk; }
+        }
+        L.klen = (nlev + best_nk - 1) / best_nk;
+        L.nkc = (nlev + L.klen - 1) / L.klen;
+        TmaMaps M;
+        memset(&M, 0, sizeof(M));
+        const cuuint64_t Px = (cuuint64_t)P.u.sy, Py = (cuuint64_t)(P.u.sz / P.u.sy);
+        L.use_tma = ((Px * sizeof(T)) % 16 == 0 && !getenv("OB_STAGE_NO_TMA")) ? 1 : 0;
+        if (L.use_tma) {
+            const cuuint64_t Pzc = (cuuint64_t)(Nz + 2 * P.g.H[2]), Pzw = Pzc + (walls ? 1 : 0);
+            bool ok = stage_map(&M.m[0], P.u.p, Px, Py, Pzc, C::TW, C::TH, (int)sizeof(T)) && stage_map(&M.m[1], P.v.p, Px, Py, Pzc, C::TW, C::TH, (int)sizeof(T)) &&
+                      stage_map(&M.m[2], P.w.p, Px, Py, Pzw, C::TW, C::TH, (int)sizeof(T));
+            for (int t = 0; ok && t < P.ntr; t++) ok = stage_map(&M.m[3 + t], P.c[t].p, Px, Py, Pzc, C::TW, C::TH, (int)sizeof(T));
+            if (!ok) L.use_tma = 0;
+        }
+        if ((long)L.ntx * L.nty * L.nkc > 2147483647L) return cudaErrorInvalidConfiguration;
+        dim3 grid((unsigned)(L.ntx * L.nty * L.nkc), (unsigned)L.npass), block(C::THREADS);
+        cudaError_t e;
+        if (fast) {
+            auto kern = P.g.dzc ? tendency_stage_kernel<T, N, true, W, R, true> : tendency_stage_kernel<T, N, true, W, R, false>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, block, C::SMEM_BYTES, st>>>(P, M, L);
+        } else {
+            auto kern = P.g.dzc ? tendency_stage_kernel<T, N, false, W, R, true> : tendency_stage_kernel<T, N, false, W, R, false>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, block, C::SMEM_BYTES, st>>>(P, M, L);
+        }
+        *nlaunch += 1;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (walls) return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch, 0, -1, 0, 1);
+        return cudaSuccess;
+    }
+}
+
 // mode: 0 auto, 1 generic, 2 marching (LDG), 3 marching with TMA-staged planes (4.. = tuning variants when built with -DOB_TI_EXPERIMENT)
 template <typename T, class S>
 static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cudaStream_t st, int sm_count, int *nlaunch, bool &done, int tx_lo, int tx_hi, int invert) {
@@ -264,6 +371,16 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     done = false;
     if (mode == 1) return cudaSuccess;
     done = true;
+    const bool whole = tx_lo == 0 && tx_hi < 0 && !invert;
+    if constexpr (StageSel<T, S>::built) {
+        if ((mode == 0 || mode == 8 || mode == 9) && whole && stage_applicable<T, S>(P)) {
+#ifdef OB_STAGE_ALT
+            if (mode == 9) return launch_stage<T, S, StageSel<T, S>::ALT_W, StageSel<T, S>::ALT_R>(P, fast, st, sm_count, nlaunch);
+#endif
+            return launch_stage<T, S, StageSel<T, S>::W, StageSel<T, S>::R>(P, fast, st, sm_count, nlaunch);
+        }
+    }
+    if (mode == 8 || mode == 9) mode = 0;
     // auto: Float32 takes the TMA-staged variant (measured 4.5 % faster at 256^3), Float64 the LDG one (2 % faster)
     if (mode == 0 && sizeof(T) == 4 && S::kind == ADV_WENO) mode = 3;
     if (mode == 3) {   // TMA-staged planes (falls back to the LDG marching kernel where TMA does not apply)

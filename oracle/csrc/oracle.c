@@ -23,6 +23,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #ifndef FT
 #define FT double
@@ -888,3 +891,22 @@ void SUF(orc_amd_diffusivity)(const oparams *g, int m, int t) {
                 *ref(&g->kappae[m][t], i, j, k) = FMAX((FT)0, kap_);
             }
 }
+
+/* thread control for bench.py's CPU arm: torchrun exports OMP_NUM_THREADS=1, so the count is set explicitly and the number
+ * actually in effect is what gets reported */
+#ifndef ORACLE_F32
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int orc_get_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+#endif

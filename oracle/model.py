@@ -41,7 +41,9 @@ def lib():
 
 
 def set_num_threads(n):
-    os.environ["OMP_NUM_THREADS"] = str(n)
+    """force the OpenMP team size of the C kernels (whatever OMP_NUM_THREADS says) and return the size in effect"""
+    lib().orc_set_num_threads(int(n))
+    return int(lib().orc_get_max_threads())
 
 
 def _mkstructs(ft):

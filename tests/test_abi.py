@@ -72,5 +72,4 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "oracle" not in txt.replace("the oracle", "").replace("oracle/", "").lower() or f == "__init__.py" or True
                 assert "from oracle" not in txt and "import oracle" not in txt, f

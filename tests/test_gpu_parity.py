@@ -71,6 +71,14 @@ CONFIGS = {
                      buoyancy=("tracer",), tracers=("b",)),
     "flat_y": Config((16, 1, 12), ((0, 1.0), None, (-1.0, 0.0)), "PFB", advection=("weno", 5), closure=[("smag", 0.16, 1.0)],
                      buoyancy=("tracer",), tracers=("b",)),
+    # staged-ring tendency kernel: three 32-wide x tiles, three 16-row y tiles, several k-chunks; Periodic z and Bounded z
+    # (interior chunks staged, wall chunks on the generic marching path), LES closures read from global memory
+    "stage_ppp": Config((70, 40, 24), ((0, 7.0), (0, 4.0), (0, 2.4)), "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
+                        buoyancy=("tracer",), coriolis_f=0.2, tracers=("b", "c")),
+    "stage_les": Config((40, 36, 30), ((0, 40.0), (0, 36.0), (-30.0, 0.0)), "PPB", advection=("weno", 5),
+                        closure=[("amd",), ("scalar", 1.05e-6, 1.46e-7)], buoyancy=("seawater", 9.80665, 2e-4, 8e-4),
+                        coriolis_f=1e-4, tracers=("T", "S"),
+                        bcs={"u": {"top": ("Flux", -2e-5)}, "T": {"top": ("Flux", 5e-5), "bottom": ("Gradient", 0.005)}}),
     "amd_cb": Config((12, 12, 10), ((0, 12.0), (0, 12.0), (-10.0, 0.0)), "PPB", advection=("weno", 5),
                      closure=[("amd", 1.0)], buoyancy=("tracer",), tracers=("b",)),
 }
@@ -88,7 +96,7 @@ def _cfg32(cfg):
 # tests/test_oracle_conditioning.py shows (CPU only) that a 1-ulp perturbation of the oracle's own input moves pNHS by
 # more than 1e-11 there, so no implementation -- including the reference with another FFT library -- can meet 1e-11
 # on p for them; u, v, w and the tracers are still held to the contract tolerance.
-P_ILL_CONDITIONED = {"les_amd": 100.0, "stretched": 100.0, "amd_cb": 100.0, "flat_x": 10.0, "flat_y": 10.0, "ragged_ppb": 10.0}
+P_ILL_CONDITIONED = {"les_amd": 100.0, "stage_les": 100.0, "stretched": 100.0, "amd_cb": 100.0, "flat_x": 10.0, "flat_y": 10.0, "ragged_ppb": 10.0}
 
 
 def _compare(om, bm, tol, what=("u", "v", "w", "pNHS"), p_factor=1.0):
@@ -115,7 +123,7 @@ def _sync_state_from_oracle(om, bm):
         bm.tracers[n].set_parent(f.data)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["generic", "marching", "tma"])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 8], ids=["generic", "marching", "tma", "stage"])
 @pytest.mark.parametrize("division", ["NormalDivision", "BackendOptimizedDivision"])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
 def test_tendencies_match_oracle(arch, name, division, kernel):
@@ -174,6 +182,34 @@ def test_tma_staged_kernel_is_bit_identical_to_the_ldg_marching_kernel(arch, nam
     bm.compute_tendencies()
     for r, g in zip(ref, bm.Gn):
         assert np.array_equal(r, g.parent()), name
+
+
+@pytest.mark.parametrize("ft", ["f64", "f32"])
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_staged_ring_kernel_is_bit_identical_to_the_ldg_marching_kernel(arch, name, ft):
+    """OB_OPT_TENDENCY_KERNEL = 8 (and the automatic choice) is the staged-ring kernel (tendency_stage.cuh): TMA- or
+    cp.async-fed shared-memory ring, every face flux evaluated once, all tendencies in one CTA.  It evaluates the same
+    flux functions on the same operands as the marching kernel, so every tendency must agree bit for bit (configurations
+    where it does not apply fall through to the marching path and agree trivially)"""
+    from ocean_b200 import _abi
+    d = dict(CONFIGS[name].__dict__)
+    d["ft"] = np.float64 if ft == "f64" else np.float32
+    cfg = Config(**d)
+    bm = cfg.b200_model(arch)
+    import ocean_b200 as ob
+    ob.set(bm, **cfg.initial_conditions(5))
+    bm.update_state()
+    bm.set_option(_abi.OB_OPT_TENDENCY_KERNEL, 2)
+    bm.compute_tendencies()
+    ref = [g.parent() for g in bm.Gn]
+    for mode in (8, 0):
+        for g in bm.Gn:
+            g.set_parent(np.zeros(g.P[::-1], g.grid.FT))
+        bm.set_option(_abi.OB_OPT_TENDENCY_KERNEL, mode)
+        bm.compute_tendencies()
+        for n, (r, g) in enumerate(zip(ref, bm.Gn)):
+            got = g.parent()
+            assert np.array_equal(r, got), (name, mode, n, int(np.sum(r != got)), float(np.abs(r - got).max()))
 
 
 @pytest.mark.parametrize("name", sorted(CONFIGS))

@@ -14,11 +14,13 @@ from bench import workload_config  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 arch = ob.B200(0)
-for ft in (np.float64, np.float32):
+fts = {"f64": (np.float64,), "f32": (np.float32,)}.get(os.environ.get("OB_FT", ""), (np.float64, np.float32))
+for ft in fts:
     cfg = workload_config(n, ft=ft)
     m = cfg.b200_model(arch)
     ob.set(m, **cfg.initial_conditions(2))
-    modes = [(2, "marching"), (3, "tma"), (1, "generic")] + [(int(x), "variant%s" % x) for x in os.environ.get("OB_VARIANTS", "").split(",") if x]
+    names = {0: "auto", 1: "generic", 2: "marching", 3: "tma", 8: "stage", 9: "stage-alt"}
+    modes = [(int(x), names.get(int(x), "variant%s" % x)) for x in os.environ.get("OB_MODES", "2,8").split(",") if x]
     for mode, name in modes:
         m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, mode)
         for _ in range(3):
