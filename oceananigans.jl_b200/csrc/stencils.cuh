@@ -10,6 +10,7 @@
 //   velocity_tracer_gradients.jl:6-42, Operators/*.jl
 #pragma once
 #include "common.cuh"
+#include "coef_literals.h"
 
 namespace ob {
 
@@ -91,11 +92,15 @@ __device__ __forceinline__ T centered_face(const G &get, int i, int j, int k) {
 // Z-WENO weights and reconstruction from the 2N-1 upwind-ordered values v[0..2N-2]
 // (v[m] = ψ[face - N + m] for LeftBias, ψ[face + N - 1 - m] for RightBias; the right-biased sub-stencils of
 // weno_interpolants.jl:448-471 are the left-biased ones on the mirrored stencil).
-template <typename T, int N, bool FAST>
+// LIT: every coefficient is a compile-time literal (coef_literals.h, the same values as the constant-bank tables) -- the
+// operations and their order are unchanged, only the operand kind differs (immediate / literal pool instead of LDC).
+template <typename T, int N, bool FAST, bool LIT = false>
 __device__ __forceinline__ T weno_from_values(const T (&v)[2 * N - 1]) {
     const auto &tab = Tab<T>::get();
     // smoothness coefficients (weno_interpolants.jl:169-192) come from the constant bank
     auto wb = [&](int r, int c) -> T {
+        if constexpr (LIT) return CoefLit<T, N>::beta(r, c);
+        else
 #ifdef OB_BETA_LITERALS  // OFF: literal operands let the compiler re-associate the ill-conditioned quadratic form (measured: 1e-8 on a tracer with a large mean)
         if constexpr (N == 3) {
             constexpr T tbl[3][6] = {{10, -31, 11, 25, -19, 4}, {4, -13, 5, 13, -13, 4}, {4, -19, 11, 25, -31, 10}};
@@ -141,17 +146,20 @@ __device__ __forceinline__ T weno_from_values(const T (&v)[2 * N - 1]) {
     T sum = 0;
 #pragma unroll
     for (int r = 0; r < N; r++) {
-        T q = div_<FAST>(tau, beta[r] + tab.weno_eps);
-        alpha[r] = tab.weno_cstar[N][r] * (1 + q * q);
+        T q, cs;
+        if constexpr (LIT) { q = div_<FAST>(tau, beta[r] + CoefLit<T, N>::eps()); cs = CoefLit<T, N>::cstar(r); }
+        else { q = div_<FAST>(tau, beta[r] + tab.weno_eps); cs = tab.weno_cstar[N][r]; }
+        alpha[r] = cs * (1 + q * q);
         sum = (r == 0) ? alpha[r] : sum + alpha[r];
     }
     T inv = FAST ? fast_rcp(sum) : 1 / sum;
     T res = 0;
 #pragma unroll
     for (int r = 0; r < N; r++) {
-        T p = tab.weno_coeff[N][r][0] * v[N - 1 - r];
+        auto wc = [&](int q) -> T { if constexpr (LIT) return CoefLit<T, N>::coeff(r, q); else return tab.weno_coeff[N][r][q]; };
+        T p = wc(0) * v[N - 1 - r];
 #pragma unroll
-        for (int q = 1; q < N; q++) p = p + tab.weno_coeff[N][r][q] * v[N - 1 - r + q];
+        for (int q = 1; q < N; q++) p = p + wc(q) * v[N - 1 - r + q];
         res = (r == 0) ? (alpha[r] * inv) * p : fma_(alpha[r] * inv, p, res);
     }
     return res;

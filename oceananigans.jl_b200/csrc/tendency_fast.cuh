@@ -14,22 +14,24 @@
 
 namespace ob {
 
-template <typename T, int NC>
+// LIT: coefficients of Centered(2 NC) = the advecting scheme of WENO(NC + 1) as literals (coef_literals.h)
+template <typename T, int NC, bool LIT = false>
 __device__ __forceinline__ T centered_vals(const T (&v)[2 * NC]) {
     const auto &tab = Tab<T>::get();
-    T acc = tab.cen_coeff[NC][0] * v[0];
+    auto cc = [&](int m) -> T { if constexpr (LIT) return CoefLit<T, NC + 1>::cen(m); else return tab.cen_coeff[NC][m]; };
+    T acc = cc(0) * v[0];
 #pragma unroll
-    for (int m = 1; m < 2 * NC; m++) acc = fma_(tab.cen_coeff[NC][m], v[m], acc);
+    for (int m = 1; m < 2 * NC; m++) acc = fma_(cc(m), v[m], acc);
     return acc;
 }
 
 // WENO(2N-1) from the 2N values s[m] = ψ[face - N + m]; LeftBias uses s[0 .. 2N-2], RightBias the mirror image
-template <typename T, int N, bool FAST>
+template <typename T, int N, bool FAST, bool LIT = false>
 __device__ __forceinline__ T weno_sel(const T (&s)[2 * N], bool left) {
     T v[2 * N - 1];
 #pragma unroll
     for (int m = 0; m < 2 * N - 1; m++) v[m] = left ? s[m] : s[2 * N - 1 - m];
-    return weno_from_values<T, N, FAST>(v);
+    return weno_from_values<T, N, FAST, LIT>(v);
 }
 
 // Geometry of the fast path.  STR = stretched z: metrics are read per level from the host-built arrays; otherwise every
@@ -68,12 +70,12 @@ __device__ __forceinline__ void load_line(const T *__restrict__ p, const FastGeo
 // velocity component ADV.
 // The flux from already-loaded stencil values: s[m] = q at offsets -N .. N-1 along ADV; a[] = the advecting component
 // at offsets -(N-1) .. N-2 along axis WHICH (momentum) or its single value at the face (tracer).
-template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR>
+template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR, bool LIT = false>
 __device__ __forceinline__ T flux_from_values(const T (&s)[2 * N], T (&a)[WHICH == 3 ? 1 : 2 * (N - 1)], const FastGeom<T, STR> &g, int kp) {
     if constexpr (WHICH == 3) {
         const T A = ADV == 0 ? g.dy * g.dzC(kp) : ADV == 1 ? g.dx * g.dzC(kp) : g.dx * g.dy;
         const T ut = a[0];
-        const T cr = weno_sel<T, N, FAST>(s, ut > 0);
+        const T cr = weno_sel<T, N, FAST, LIT>(s, ut > 0);
         return A * ut * cr;
     } else {
         constexpr int NC = N - 1;
@@ -84,8 +86,8 @@ __device__ __forceinline__ T flux_from_values(const T (&s)[2 * N], T (&a)[WHICH 
             const T A = ADV == 0 ? g.dy * g.dzC(kq) : ADV == 1 ? g.dx * g.dzC(kq) : g.dx * g.dy;
             a[m] = A * a[m];
         }
-        const T ut = centered_vals<T, NC>(a);
-        const T qr = weno_sel<T, N, FAST>(s, ut > 0);
+        const T ut = centered_vals<T, NC, LIT>(a);
+        const T qr = weno_sel<T, N, FAST, LIT>(s, ut > 0);
         return ut * qr;
     }
 }

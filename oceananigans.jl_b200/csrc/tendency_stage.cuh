@@ -1,19 +1,19 @@
 // tendency_stage.cuh -- the fused tendency kernel, staged-ring form (default on the interior fast path).
 //
-// One CTA computes ALL tendencies of a 32 x (W*R) tile of columns (Gu, Gv, Gw and one tracer per pass) while it marches
+// One CTA computes ALL tendencies of a 32 x W tile of columns (Gu, Gv, Gw and one tracer per pass) while it marches
 // in k.  Every stencil operand is read from shared memory:
 //
-//   * a PRODUCER warp feeds a ring of D = N+2 levels; each level holds the halo'd (32+2N) x (W*R+2N) planes of u, v, w
+//   * a PRODUCER warp feeds a ring of D = N+2 levels; each level holds the halo'd (32+2N) x (W+2N) planes of u, v, w
 //     and the tracer, brought in by TMA (cp.async.bulk.tensor.3d, one box per field and level, completion on an mbarrier)
 //     -- or by cp.async when the row pitch of the parent arrays is not a multiple of 16 bytes (Float32 with odd padding).
 //     Levels k .. k+N live in the ring; the N-1 levels below k of a thread's own column are kept in registers, so the
 //     z-lines of the stencils cost no memory traffic at all.
-//   * W COMPUTE warps: warp w owns rows w*R .. w*R+R-1 of the tile, lane l the column i0+l.  A thread evaluates, per
-//     level and tendency, the flux through the west face and the south face of each of its cells and the upper face;
-//     the east flux comes from lane+1 (shuffle), the north flux from the next row (register, or the next warp's
-//     published south flux), the lower flux from the previous level (register).  Every face flux is evaluated ONCE.
+//   * W COMPUTE warps: warp w owns row w of the tile, lane l the column i0+l.  A thread evaluates, per level and
+//     tendency, the flux through the west face and the south face of its cell and through the upper face; the east flux
+//     comes from lane+1 (shuffle), the north flux is the south flux the next warp published in shared memory, the lower
+//     flux is last level's upper flux (register).  Every face flux is evaluated ONCE.
 //   * a HELPER warp evaluates the tile's east-edge x fluxes (lanes = rows) and north-edge y fluxes (lanes = columns) and
-//     publishes them, so tiles advance by the full 32 x (W*R) cells: no overlap lanes, no overlap rows.
+//     publishes them, so tiles advance by the full 32 x W cells: no overlap lanes, no overlap rows.
 //   * warps never meet at a CTA barrier: ring slots are recycled through full/empty mbarriers (the empty barrier of a
 //     level needs one arrival per consumer warp), published fluxes through one mbarrier per publishing warp.  Because a
 //     level k+N can only be loaded after EVERY consumer has released level k-2, two consumer warps are never more than one
@@ -31,10 +31,10 @@
 
 namespace ob {
 
-template <typename T, int N, int W, int R>
+template <typename T, int N, int W, int NCL>
 struct StageCfg {
     static constexpr int EPV = 16 / (int)sizeof(T);
-    static constexpr int TXC = 32, TYC = W * R;
+    static constexpr int TXC = 32, TYC = W;
     static constexpr int TW = ((TXC + 2 * N + (EPV - 1)) + EPV - 1) / EPV * EPV;   // box width: 16-byte multiple incl. the origin round-down
     static constexpr int TH = TYC + 2 * N;
     static constexpr int BOX_BYTES = TW * TH * (int)sizeof(T);
@@ -43,23 +43,26 @@ struct StageCfg {
     static constexpr int D = N + 2;                           // ring depth: levels k .. k+N + one in flight
     static constexpr int NF = 4;                              // staged fields: u, v, w, tracer of the pass
     static constexpr int NQ = 4;                              // tendencies per pass
-    static constexpr int NV = 1 + OB_SHARED_CL;               // flux components: advective + shared closures
+    static constexpr int NV = 1 + NCL;                        // flux components: advective + one per closure
     static constexpr int LEVEL_BYTES = NF * PLANE_BYTES;
+    static constexpr int LEVEL = LEVEL_BYTES / (int)sizeof(T);
     static constexpr int RING_BYTES = D * LEVEL_BYTES;
     static constexpr int YX_SLOT = (W + 1) * NQ * NV * 32;    // published south fluxes: [w][q][v][lane], w = W: helper (north edge)
     static constexpr int XE_SLOT = NQ * NV * 32;              // published east-edge fluxes: [q][v][row]
-    static constexpr int XCH_BYTES = 2 * (YX_SLOT + XE_SLOT) * (int)sizeof(T);
+    static constexpr int XCH_SLOT = YX_SLOT + XE_SLOT;
+    static constexpr int XCH_BYTES = 2 * XCH_SLOT * (int)sizeof(T);
     static constexpr int NBAR = 2 * D + 2 * (W + 1);
     static constexpr int SMEM_BYTES = RING_BYTES + XCH_BYTES + NBAR * 8;
     static constexpr int THREADS = (W + 2) * 32;
+    static constexpr bool FITS = SMEM_BYTES <= 227 * 1024;
 };
 
-// which (float type, scheme) combinations have a staged-ring kernel, and its tile shape (W compute warps x R rows each)
+// which (float type, scheme) combinations have a staged-ring kernel, and its tile height (= compute warps) per closure count
 template <typename T, class S>
 struct StageSel {
     static constexpr bool built = S::kind == ADV_WENO && S::n == 3;
-    static constexpr int W = 8, R = 2;
-    static constexpr int ALT_W = 16, ALT_R = 1;
+    static constexpr int W01 = 16;   // no closure / one closure
+    static constexpr int W2 = 12;    // two closures: the published fluxes need a third component
 };
 
 struct StageLaunch {
@@ -72,6 +75,17 @@ struct StageLaunch {
 __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// wait with back-off: the producer spends its life here and must not compete for issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *b, uint32_t parity) {
+    const uint32_t a = smem_u32(b);
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void cp_async_elem(void *dst, const void *src, int bytes, bool valid) {
     const int sz = valid ? bytes : 0;
     if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
@@ -81,25 +95,25 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *b) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 
-// The levels k .. k+N of the ring as seen by one thread: pl[d] points at field 0 of level k+d, already offset to the
-// thread's own point; field f is PL elements further, a row TW elements.
+// The levels k .. k+N of the ring as seen from one point of the tile: pl[d] points at field 0 of level k+d, already
+// offset to that point; field f is PL elements further, a row TW elements.
 template <typename T, int N, int TW, int PL>
 struct StageView {
     const T *pl[N + 1];
     __device__ __forceinline__ T at(int f, int d, int dx, int dy) const { return pl[d][f * PL + dy * TW + dx]; }
 };
 
-// own-column value of field F at level k+dl, dl in [-(N-1), N]: below k from the register history (h[m] = level k-(N-1)+m)
+// own-column value of field f at level k+dl, dl in [-(N-1), N]: below k from the register history (h[m] = level k-(N-1)+m)
 template <typename T, int N, int TW, int PL>
 __device__ __forceinline__ T zval(const StageView<T, N, TW, PL> &V, const T (&h)[N - 1], int f, int dl) {
     if (dl < 0) return h[N - 1 + dl];
     return V.at(f, dl, 0, 0);
 }
 
-// Advective flux of tendency WHICH through the face the thread owns in direction ADV (0: west, 1: south, 2: upper face
-// k+1), from the staged planes; the operands and their order are those of fast_flux (tendency_fast.cuh).
+// Advective flux of tendency WHICH through the face owned in direction ADV (0: west, 1: south, 2: upper face k+1), from
+// the staged planes; the operands and their order are those of fast_flux (tendency_fast.cuh).
 // hq: history of the advected field; ha: history of the advecting component whose z-line is needed (u for ADV 0, v for 1, w for 2)
-template <typename T, int N, bool FAST, int WHICH, int ADV, bool STR, int TW, int PL>
+template <typename T, int N, int WHICH, int ADV, bool STR, int TW, int PL>
 __device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const T (&hq)[N - 1], const T (&ha)[N - 1], const FastGeom<T, STR> &g, int k) {
     constexpr int NC = N - 1;
     constexpr int QF = WHICH;    // field index of the advected quantity (3 = the tracer of the pass)
@@ -114,7 +128,7 @@ __device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const 
     }
     if constexpr (WHICH == 3) {
         T a[1] = {V.at(AF, LV, 0, 0)};
-        return flux_from_values<T, N, FAST, WHICH, ADV, STR>(s, a, g, k + LV);
+        return flux_from_values<T, N, true, WHICH, ADV, STR, true>(s, a, g, k + LV);
     } else {
         T a[2 * NC];
 #pragma unroll
@@ -123,20 +137,21 @@ __device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const 
             else if constexpr (WHICH == 1) a[m] = V.at(AF, LV, 0, m - NC);
             else a[m] = zval<T, N, TW, PL>(V, ha, AF, LV - NC + m);
         }
-        return flux_from_values<T, N, FAST, WHICH, ADV, STR>(s, a, g, k + LV);
+        return flux_from_values<T, N, true, WHICH, ADV, STR, true>(s, a, g, k + LV);
     }
 }
 
 // Non-advective terms from the staged planes: FastTerms (tendency_fast.cuh) with the velocity / tracer loads redirected to
-// shared memory (level offsets -1: register history of the own column; 0, +1: ring).  Closure fields (nu_e, kappa_e) and
-// pHY' stay on the global path: each is read at most a few times per cell.
-template <typename T, int N, bool STR, int TW, int PL>
+// shared memory (level offset -1: register history of the own column; 0, +1: ring).  Closure fields (nu_e, kappa_e) and
+// pHY' stay on the global path: each is read at most a few times per cell.  LES = false: every closure is a
+// ScalarDiffusivity (no closure fields), which removes the global path from the code altogether.
+template <typename T, int N, bool LES, bool STR, int TW, int PL>
 struct StageTerms {
     const TendP<T> &P;
     const FastGeom<T, STR> &G;
     const StageView<T, N, TW, PL> &V;
     const T (&hu)[N - 1], (&hv)[N - 1], (&hw)[N - 1], (&hc)[N - 1];
-    int eo;   // global element offset of the thread's (clamped) point at level k
+    int eo;   // global element offset of the (clamped) point at level k
     int k;
     int tstage;   // tracer index staged as field 3
     __device__ __forceinline__ T fld(int f, int a, int b, int c) const {
@@ -165,10 +180,10 @@ struct StageTerms {
     __device__ __forceinline__ T If2(const T *f, int D2, int D1, int a, int b, int c) const {
         return T(0.5) * (If1(f, D1, a - (D2 == 0), b - (D2 == 1), c - (D2 == 2)) + If1(f, D1, a, b, c));
     }
-    __device__ __forceinline__ T nu_ccc(int m, const T *ne, int a, int b, int c) const { return ne ? ldg(ne, a, b, c) : P.cl[m].nu; }
-    __device__ __forceinline__ T nu_ffc(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 1, 0, a, b, c) : P.cl[m].nu; }
-    __device__ __forceinline__ T nu_fcf(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 0, a, b, c) : P.cl[m].nu; }
-    __device__ __forceinline__ T nu_cff(int m, const T *ne, int a, int b, int c) const { return ne ? If2(ne, 2, 1, a, b, c) : P.cl[m].nu; }
+    __device__ __forceinline__ T nu_ccc(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? ldg(ne, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
+    __device__ __forceinline__ T nu_ffc(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? If2(ne, 1, 0, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
+    __device__ __forceinline__ T nu_fcf(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? If2(ne, 2, 0, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
+    __device__ __forceinline__ T nu_cff(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? If2(ne, 2, 1, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
     __device__ __forceinline__ T ux(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dx_u(a, b, c))); }
     __device__ __forceinline__ T uy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
     __device__ __forceinline__ T uz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
@@ -178,21 +193,32 @@ struct StageTerms {
     __device__ __forceinline__ T wx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzF(c)) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
     __device__ __forceinline__ T wy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzF(c)) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
     __device__ __forceinline__ T wz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_ccc(m, ne, a, b, c) * dz_w(a, b, c))); }
-    __device__ __forceinline__ const T *nue_ptr(int m) const { return P.cl[m].kind == CL_SCALAR ? nullptr : at(P.nue[m]); }
+    __device__ __forceinline__ const T *nue_ptr(int m) const {
+        if constexpr (LES) return P.cl[m].kind == CL_SCALAR ? nullptr : at(P.nue[m]);
+        else return nullptr;
+    }
     // diffusive flux of the staged tracer along D at the face (a, b, c)
     __device__ __forceinline__ T qflux(int m, const T *kf, int D, int a, int b, int c) const {
-        const int kind = P.cl[m].kind;
-        const T kap = kind == CL_SCALAR ? P.cl[m].kappa[tstage] : kind == CL_SMAG ? If1(kf, D, a, b, c) / P.cl[m].Pr[tstage] : If1(kf, D, a, b, c);
+        T kap;
+        if constexpr (LES) {
+            const int kind = P.cl[m].kind;
+            kap = kind == CL_SCALAR ? P.cl[m].kappa[tstage] : kind == CL_SMAG ? If1(kf, D, a, b, c) / P.cl[m].Pr[tstage] : If1(kf, D, a, b, c);
+        } else {
+            kap = P.cl[m].kappa[tstage];
+        }
         const T rd = D == 0 ? G.rdx : D == 1 ? G.rdy : G.rdzF(k + c);
         const T A = D == 0 ? G.dy * dzC(c) : D == 1 ? G.dx * dzC(c) : G.dx * G.dy;
         const T dc = (fld(3, a, b, c) - fld(3, a - (D == 0), b - (D == 1), c - (D == 2))) * rd;
         return A * (-kap * dc);
     }
-    // closure flux of tendency WHICH through the face this thread owns in direction D (D == 2: the UPPER face)
+    // closure flux of tendency WHICH through the owned face in direction D (D == 2: the UPPER face)
     template <int WHICH, int D> __device__ __forceinline__ T own_closure_flux(int m) const {
         if constexpr (WHICH == 3) {
-            const int kind = P.cl[m].kind;
-            const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][tstage]);
+            const T *kf = nullptr;
+            if constexpr (LES) {
+                const int kind = P.cl[m].kind;
+                kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][tstage]);
+            }
             return qflux(m, kf, D, 0, 0, D == 2 ? 1 : 0);
         } else {
             const T *ne = nue_ptr(m);
@@ -210,7 +236,7 @@ struct StageTerms {
         return 0;
     }
     // the tendency assemblers, same term order as FastTerms::finish<WHICH, true>
-    template <int WHICH> __device__ __forceinline__ T finish(T adv, T closure_term) const {
+    template <int WHICH, int NCL> __device__ __forceinline__ T finish(T adv, T closure_term) const {
         T r = -adv;
         if constexpr (WHICH == 0) {
             if (P.has_cor) {
@@ -231,23 +257,17 @@ struct StageTerms {
         } else if constexpr (WHICH == 2) {
             if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
         }
-        if (P.ncl > 0) r = r - closure_term;
+        if constexpr (NCL > 0) r = r - closure_term;
         return r;
     }
 };
 
-// Per-thread state that survives from one level to the next.  NR rows per thread (compute warps: R, helper: 1).
-template <typename T, int N, int NR>
-struct StageCarry {
-    T h[4][NR][N - 1];                          // own-column history of u, v, w, tracer: levels k-(N-1) .. k-1
-    T lower[4][NR];                             // advective flux through the lower face, per tendency
-    T lower_c[4][NR][OB_SHARED_CL];             // closure fluxes through the lower face
-};
-
-template <typename T, int N, bool FAST, int W, int R, bool STR>
+template <typename T, int N, int W, int NCL, bool LES, bool STR>
 __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M, const StageLaunch L) {
-    using C = StageCfg<T, N, W, R>;
+    using C = StageCfg<T, N, W, NCL>;
     constexpr int TW = C::TW, PL = C::PL, D = C::D, NV = C::NV;
+    using View = StageView<T, N, TW, PL>;
+    using Terms = StageTerms<T, N, LES, STR, TW, PL>;
     extern __shared__ __align__(128) unsigned char smem[];
     T *ring = reinterpret_cast<T *>(smem);
     T *xch = reinterpret_cast<T *>(smem + C::RING_BYTES);
@@ -288,7 +308,7 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
             if (lane == 0) {
                 for (int Lv = kfirst; Lv <= klast; Lv++) {
                     const int n = Lv - kfirst, s = n % D;
-                    if (n >= D) mbar_wait(&empty[s], (uint32_t)(((n / D) - 1) & 1));
+                    if (n >= D) mbar_wait_sleep(&empty[s], (uint32_t)(((n / D) - 1) & 1));
                     unsigned char *dst = smem + s * C::LEVEL_BYTES;
                     mbar_expect_tx(&full[s], nfields * C::BOX_BYTES);
                     const int cz = Lv + gg.H[2] - 1;
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
             const int Px = P.u.sy, Py = (int)(P.u.sz / P.u.sy);
             for (int Lv = kfirst; Lv <= klast; Lv++) {
                 const int n = Lv - kfirst, s = n % D;
-                if (n >= D) mbar_wait(&empty[s], (uint32_t)(((n / D) - 1) & 1));
+                if (n >= D) mbar_wait_sleep(&empty[s], (uint32_t)(((n / D) - 1) & 1));
                 const int cz = Lv + gg.H[2] - 1;
                 for (int f = 0; f < nfields; f++) {
                     const Fld<T> &F = f == 0 ? P.u : f == 1 ? P.v : f == 2 ? P.w : P.c[tstage];
@@ -324,256 +344,155 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
     }
 
     // ---------------------------------------------------------------- consumers ------------------------------------
+    // Compute warps (warp < W): own point (i0+lane, j0+warp), the same for every phase.  Helper (warp == W): its south-flux
+    // point is (i0+lane, j0+TYC) -- the tile's north edge, lanes = columns -- and its west-flux point (i0+32, j0+lane) --
+    // the east edge, lanes = rows.  Phase A (south fluxes) runs the same code in every consumer warp.
+    const bool helper = warp == W;
     FastGeom<T, STR> g;
     g.init(gg, P.u.sy, P.u.sz);
-    const int ncl = P.ncl;
-    const bool share_cl = ncl >= 1;   // the host only launches this kernel with ncl <= OB_SHARED_CL
-    auto yx_at = [&](int slot, int w, int q, int v) -> T * { return xch + slot * (C::YX_SLOT + C::XE_SLOT) + ((w * C::NQ + q) * NV + v) * 32; };
-    auto xe_at = [&](int slot, int q, int v) -> T * { return xch + slot * (C::YX_SLOT + C::XE_SLOT) + C::YX_SLOT + (q * NV + v) * 32; };
+    const int rowB = min(lane, C::TYC - 1);
+    const int ownY = (helper ? C::TYC + N : warp + N) * TW + lane + N + sh;
+    const int ownX = helper ? (rowB + N) * TW + 32 + N + sh : ownY;
+    const int gi = i0 + lane, gj = j0 + warp;
+    const int eoY = min(gi, Nx + 1) + min(helper ? j0 + C::TYC : gj, Ny + 1) * g.sy;
+    const int eoX = helper ? min(i0 + 32, Nx + 1) + min(j0 + rowB, Ny + 1) * g.sy : eoY;
+    const bool live = !helper && gi <= Nx && gj <= Ny;
+    auto yx_at = [&](int slot, int w, int q, int v) -> T * { return xch + slot * C::XCH_SLOT + ((w * C::NQ + q) * NV + v) * 32 + lane; };
+    auto xe_at = [&](int slot, int q, int v, int row) -> T * { return xch + slot * C::XCH_SLOT + C::YX_SLOT + (q * NV + v) * 32 + row; };
 
+    // register state carried from level to level: own-column history (helper: h[0] = u at its west-flux point, h[1] = v at its
+    // south-flux point), lower-face fluxes
+    T h[4][N - 1], lower[4], lower_c[4][NCL > 0 ? NCL : 1];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        lower[q] = T(0);
+#pragma unroll
+        for (int m = 0; m < (NCL > 0 ? NCL : 1); m++) lower_c[q][m] = T(0);
+#pragma unroll
+        for (int m = 0; m < N - 1; m++) h[q][m] = T(0);
+    }
     // running ring positions: level k is in slot sk; level k+N (the newest one this level needs) in slot sn with phase pn
-    int sk = 0, sn = 0, pn = 0;
-    // wait for the levels kfirst .. kfirst+N-1 here; level k+N is awaited at the top of each iteration
+    int sk = 0, sn = N % D, pn = (N / D) & 1;
     for (int n = 0; n < N; n++) mbar_wait(&full[n], 0);
-    sn = N % D; pn = (N / D) & 1;
 
-    if (warp < W) {
-        // ------------------------------------------------------------ compute warp ---------------------------------
-        StageCarry<T, N, R> cy;
-        const int row0 = warp * R;
-        int own[R], eo_base[R];
-        bool live[R];
+    for (int k = kfirst; k <= k1; k++) {
+        mbar_wait(&full[sn], (uint32_t)pn);
+        const T *lev[N + 1];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            own[r] = (row0 + r + N) * TW + lane + N + sh;
-            const int i = i0 + lane, j = j0 + row0 + r;
-            live[r] = i <= Nx && j <= Ny;
-            eo_base[r] = min(i, Nx + 1) + min(j, Ny + 1) * g.sy;
+        for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * C::LEVEL; }
+        const int e = k - k0, xs = e & 1, xp = (e >> 1) & 1;
+        const bool full_level = k >= k0;
+        View VY;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                cy.lower[q][r] = T(0);
+        for (int d = 0; d <= N; d++) VY.pl[d] = lev[d] + ownY;
+        const Terms FY{P, g, VY, h[0], h[1], h[2], h[3], eoY + k * g.sz, k, tstage};
+        if (full_level) {
+            // ---- phase A: south fluxes, published for the warp below (helper: the tile's north edge) ------------------
+            if (mom) {
+                *yx_at(xs, warp, 0, 0) = stage_flux<T, N, 0, 1, STR, TW, PL>(VY, h[0], h[1], g, k);
+                *yx_at(xs, warp, 1, 0) = stage_flux<T, N, 1, 1, STR, TW, PL>(VY, h[1], h[1], g, k);
+                *yx_at(xs, warp, 2, 0) = stage_flux<T, N, 2, 1, STR, TW, PL>(VY, h[2], h[1], g, k);
 #pragma unroll
-                for (int m = 0; m < OB_SHARED_CL; m++) cy.lower_c[q][r][m] = T(0);
-#pragma unroll
-                for (int h = 0; h < N - 1; h++) cy.h[q][r][h] = T(0);
+                for (int m = 0; m < NCL; m++) {
+                    *yx_at(xs, warp, 0, 1 + m) = FY.template own_closure_flux<0, 1>(m);
+                    *yx_at(xs, warp, 1, 1 + m) = FY.template own_closure_flux<1, 1>(m);
+                    *yx_at(xs, warp, 2, 1 + m) = FY.template own_closure_flux<2, 1>(m);
+                }
             }
-        }
-        for (int k = kfirst; k <= k1; k++) {
-            mbar_wait(&full[sn], (uint32_t)pn);
-            const int mode = k >= k0 ? 2 : k == k0 - 1 ? 1 : 0;   // 2: full level, 1: upper fluxes only, 0: history only
-            const T *lev[N + 1];
+            if (has_tr) {
+                *yx_at(xs, warp, 3, 0) = stage_flux<T, N, 3, 1, STR, TW, PL>(VY, h[3], h[1], g, k);
 #pragma unroll
-            for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * (C::LEVEL_BYTES / (int)sizeof(T)); }
-            const int e = k - k0, xs = e & 1, xp = (e >> 1) & 1;
-            if (mode == 2) {
-                // phase A: the south fluxes of row 0, published for the warp below
-                StageView<T, N, TW, PL> V;
-#pragma unroll
-                for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + own[0];
-                StageTerms<T, N, STR, TW, PL> F{P, g, V, cy.h[0][0], cy.h[1][0], cy.h[2][0], cy.h[3][0], eo_base[0] + k * g.sz, k, tstage};
-                if (mom) {
-                    *(yx_at(xs, warp, 0, 0) + lane) = stage_flux<T, N, FAST, 0, 1, STR, TW, PL>(V, cy.h[0][0], cy.h[1][0], g, k);
-                    *(yx_at(xs, warp, 1, 0) + lane) = stage_flux<T, N, FAST, 1, 1, STR, TW, PL>(V, cy.h[1][0], cy.h[1][0], g, k);
-                    *(yx_at(xs, warp, 2, 0) + lane) = stage_flux<T, N, FAST, 2, 1, STR, TW, PL>(V, cy.h[2][0], cy.h[1][0], g, k);
-                    if (share_cl) {
-#pragma unroll
-                        for (int m = 0; m < OB_SHARED_CL; m++)
-                            if (m < ncl) {
-                                *(yx_at(xs, warp, 0, 1 + m) + lane) = F.template own_closure_flux<0, 1>(m);
-                                *(yx_at(xs, warp, 1, 1 + m) + lane) = F.template own_closure_flux<1, 1>(m);
-                                *(yx_at(xs, warp, 2, 1 + m) + lane) = F.template own_closure_flux<2, 1>(m);
-                            }
-                    }
-                }
-                if (has_tr) {
-                    *(yx_at(xs, warp, 3, 0) + lane) = stage_flux<T, N, FAST, 3, 1, STR, TW, PL>(V, cy.h[3][0], cy.h[1][0], g, k);
-                    if (share_cl) {
-#pragma unroll
-                        for (int m = 0; m < OB_SHARED_CL; m++)
-                            if (m < ncl) *(yx_at(xs, warp, 3, 1 + m) + lane) = F.template own_closure_flux<3, 1>(m);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0 && warp > 0) mbar_arrive(&pub[2 * warp + xs]);
-                // the fluxes published by the warp above (or the helper for the top warp) and by the helper (east edge)
-                mbar_wait(&pub[2 * (warp + 1) + xs], (uint32_t)xp);
-                if (warp + 1 != W) mbar_wait(&pub[2 * W + xs], (uint32_t)xp);
+                for (int m = 0; m < NCL; m++) *yx_at(xs, warp, 3, 1 + m) = FY.template own_closure_flux<3, 1>(m);
             }
-            if (mode >= 1) {
-                auto tendency = [&](auto which_tag) {
-                    constexpr int WHICH = decltype(which_tag)::value;
-                    const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[tstage];
-                    T fy_next = T(0), cy_next[OB_SHARED_CL] = {T(0), T(0)};
+            if (helper) {
+                // ---- helper phase B: west fluxes at the tile's east edge, lanes = rows -----------------------------------
+                View VX;
 #pragma unroll
-                    for (int r = R - 1; r >= 0; r--) {   // top row first: its north flux is the published one
-                        StageView<T, N, TW, PL> V;
-#pragma unroll
-                        for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + own[r];
-                        const int eo = eo_base[r] + k * g.sz;
-                        StageTerms<T, N, STR, TW, PL> F{P, g, V, cy.h[0][r], cy.h[1][r], cy.h[2][r], cy.h[3][r], eo, k, tstage};
-                        const T (&hq)[N - 1] = cy.h[WHICH][r];
-                        const T upper = stage_flux<T, N, FAST, WHICH, 2, STR, TW, PL>(V, hq, cy.h[2][r], g, k);
-                        T cup[OB_SHARED_CL] = {T(0), T(0)};
-                        if (share_cl) {
-#pragma unroll
-                            for (int m = 0; m < OB_SHARED_CL; m++) if (m < ncl) cup[m] = F.template own_closure_flux<WHICH, 2>(m);
-                        }
-                        if (mode == 2) {
-                            const T fx = stage_flux<T, N, FAST, WHICH, 0, STR, TW, PL>(V, hq, cy.h[0][r], g, k);
-                            T fy, fy1, cyv[OB_SHARED_CL] = {T(0), T(0)}, cy1[OB_SHARED_CL] = {T(0), T(0)}, cx[OB_SHARED_CL] = {T(0), T(0)};
-                            if (r == 0) fy = *(yx_at(xs, warp, WHICH, 0) + lane);
-                            else fy = stage_flux<T, N, FAST, WHICH, 1, STR, TW, PL>(V, hq, cy.h[1][r], g, k);
-                            if (r == R - 1) fy1 = *(yx_at(xs, warp + 1, WHICH, 0) + lane);
-                            else fy1 = fy_next;
-                            T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
-                            if (lane == 31) fx1 = xe_at(xs, WHICH, 0)[row0 + r];
-                            if (share_cl) {
-#pragma unroll
-                                for (int m = 0; m < OB_SHARED_CL; m++)
-                                    if (m < ncl) {
-                                        cx[m] = F.template own_closure_flux<WHICH, 0>(m);
-                                        if (r == 0) cyv[m] = *(yx_at(xs, warp, WHICH, 1 + m) + lane);
-                                        else cyv[m] = F.template own_closure_flux<WHICH, 1>(m);
-                                        if (r == R - 1) cy1[m] = *(yx_at(xs, warp + 1, WHICH, 1 + m) + lane);
-                                        else cy1[m] = cy_next[m];
-                                    }
-                            }
-                            const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
-                            const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - cy.lower[WHICH][r]));
-                            T term = T(0);
-                            if (share_cl) {
-#pragma unroll
-                                for (int m = 0; m < OB_SHARED_CL; m++)
-                                    if (m < ncl) {
-                                        T cx1 = __shfl_down_sync(0xffffffffu, cx[m], 1);
-                                        if (lane == 31) cx1 = xe_at(xs, WHICH, 1 + m)[row0 + r];
-                                        const T d = Vi * ((cx1 - cx[m]) + (cy1[m] - cyv[m]) + (cup[m] - cy.lower_c[WHICH][r][m]));
-                                        term = m == 0 ? d : term + d;
-                                    }
-                            }
-                            const T res = F.template finish<WHICH>(adv, term);
-                            if (live[r]) G.p[G.off + eo] = res;
-                            fy_next = fy;
-#pragma unroll
-                            for (int m = 0; m < OB_SHARED_CL; m++) cy_next[m] = cyv[m];
-                        }
-                        cy.lower[WHICH][r] = upper;
-#pragma unroll
-                        for (int m = 0; m < OB_SHARED_CL; m++) cy.lower_c[WHICH][r][m] = cup[m];
-                    }
-                };
-                if (mom) {
-                    tendency(std::integral_constant<int, 0>{});
-                    tendency(std::integral_constant<int, 1>{});
-                    tendency(std::integral_constant<int, 2>{});
-                }
-                if (has_tr) tendency(std::integral_constant<int, 3>{});
-            }
-            // history shift: level k becomes k-1
-#pragma unroll
-            for (int r = 0; r < R; r++)
-#pragma unroll
-                for (int f = 0; f < 4; f++) {
-#pragma unroll
-                    for (int h = 0; h + 1 < N - 1; h++) cy.h[f][r][h] = cy.h[f][r][h + 1];
-                    cy.h[f][r][N - 2] = lev[0][f * PL + own[r]];
-                }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[sk]);
-            if (++sk == D) sk = 0;
-            if (++sn == D) { sn = 0; pn ^= 1; }
-        }
-    } else {
-        // ------------------------------------------------------------ helper warp ----------------------------------
-        // edge A (north): lanes = columns, own point (i0+lane, j0+TYC); edge B (east): lanes = rows, own point (i0+32, j0+lane)
-        T hA[4][N - 1], hB[4][N - 1];
-#pragma unroll
-        for (int f = 0; f < 4; f++)
-#pragma unroll
-            for (int h = 0; h < N - 1; h++) { hA[f][h] = T(0); hB[f][h] = T(0); }
-        const int ownA = (C::TYC + N) * TW + lane + N + sh;
-        const int rowB = min(lane, C::TYC - 1);
-        const int ownB = (rowB + N) * TW + 32 + N + sh;
-        const int eoA = min(i0 + lane, Nx + 1) + min(j0 + C::TYC, Ny + 1) * g.sy;
-        const int eoB = min(i0 + 32, Nx + 1) + min(j0 + rowB, Ny + 1) * g.sy;
-        for (int k = kfirst; k <= k1; k++) {
-            mbar_wait(&full[sn], (uint32_t)pn);
-            const T *lev[N + 1];
-#pragma unroll
-            for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * (C::LEVEL_BYTES / (int)sizeof(T)); }
-            if (k >= k0) {
-                const int e = k - k0, xs = e & 1;
-                {
-                    StageView<T, N, TW, PL> V;
-#pragma unroll
-                    for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + ownA;
-                    StageTerms<T, N, STR, TW, PL> F{P, g, V, hA[0], hA[1], hA[2], hA[3], eoA + k * g.sz, k, tstage};
-                    if (mom) {
-                        *(yx_at(xs, W, 0, 0) + lane) = stage_flux<T, N, FAST, 0, 1, STR, TW, PL>(V, hA[0], hA[1], g, k);
-                        *(yx_at(xs, W, 1, 0) + lane) = stage_flux<T, N, FAST, 1, 1, STR, TW, PL>(V, hA[1], hA[1], g, k);
-                        *(yx_at(xs, W, 2, 0) + lane) = stage_flux<T, N, FAST, 2, 1, STR, TW, PL>(V, hA[2], hA[1], g, k);
-                        if (share_cl) {
-#pragma unroll
-                            for (int m = 0; m < OB_SHARED_CL; m++)
-                                if (m < ncl) {
-                                    *(yx_at(xs, W, 0, 1 + m) + lane) = F.template own_closure_flux<0, 1>(m);
-                                    *(yx_at(xs, W, 1, 1 + m) + lane) = F.template own_closure_flux<1, 1>(m);
-                                    *(yx_at(xs, W, 2, 1 + m) + lane) = F.template own_closure_flux<2, 1>(m);
-                                }
-                        }
-                    }
-                    if (has_tr) {
-                        *(yx_at(xs, W, 3, 0) + lane) = stage_flux<T, N, FAST, 3, 1, STR, TW, PL>(V, hA[3], hA[1], g, k);
-                        if (share_cl) {
-#pragma unroll
-                            for (int m = 0; m < OB_SHARED_CL; m++)
-                                if (m < ncl) *(yx_at(xs, W, 3, 1 + m) + lane) = F.template own_closure_flux<3, 1>(m);
-                        }
-                    }
-                }
+                for (int d = 0; d <= N; d++) VX.pl[d] = lev[d] + ownX;
+                const Terms FX{P, g, VX, h[0], h[1], h[2], h[3], eoX + k * g.sz, k, tstage};
                 if (lane < C::TYC) {
-                    StageView<T, N, TW, PL> V;
-#pragma unroll
-                    for (int d = 0; d <= N; d++) V.pl[d] = lev[d] + ownB;
-                    StageTerms<T, N, STR, TW, PL> F{P, g, V, hB[0], hB[1], hB[2], hB[3], eoB + k * g.sz, k, tstage};
                     if (mom) {
-                        xe_at(xs, 0, 0)[lane] = stage_flux<T, N, FAST, 0, 0, STR, TW, PL>(V, hB[0], hB[0], g, k);
-                        xe_at(xs, 1, 0)[lane] = stage_flux<T, N, FAST, 1, 0, STR, TW, PL>(V, hB[1], hB[0], g, k);
-                        xe_at(xs, 2, 0)[lane] = stage_flux<T, N, FAST, 2, 0, STR, TW, PL>(V, hB[2], hB[0], g, k);
-                        if (share_cl) {
+                        *xe_at(xs, 0, 0, lane) = stage_flux<T, N, 0, 0, STR, TW, PL>(VX, h[0], h[0], g, k);
+                        *xe_at(xs, 1, 0, lane) = stage_flux<T, N, 1, 0, STR, TW, PL>(VX, h[1], h[0], g, k);
+                        *xe_at(xs, 2, 0, lane) = stage_flux<T, N, 2, 0, STR, TW, PL>(VX, h[2], h[0], g, k);
 #pragma unroll
-                            for (int m = 0; m < OB_SHARED_CL; m++)
-                                if (m < ncl) {
-                                    xe_at(xs, 0, 1 + m)[lane] = F.template own_closure_flux<0, 0>(m);
-                                    xe_at(xs, 1, 1 + m)[lane] = F.template own_closure_flux<1, 0>(m);
-                                    xe_at(xs, 2, 1 + m)[lane] = F.template own_closure_flux<2, 0>(m);
-                                }
+                        for (int m = 0; m < NCL; m++) {
+                            *xe_at(xs, 0, 1 + m, lane) = FX.template own_closure_flux<0, 0>(m);
+                            *xe_at(xs, 1, 1 + m, lane) = FX.template own_closure_flux<1, 0>(m);
+                            *xe_at(xs, 2, 1 + m, lane) = FX.template own_closure_flux<2, 0>(m);
                         }
                     }
                     if (has_tr) {
-                        xe_at(xs, 3, 0)[lane] = stage_flux<T, N, FAST, 3, 0, STR, TW, PL>(V, hB[3], hB[0], g, k);
-                        if (share_cl) {
+                        *xe_at(xs, 3, 0, lane) = stage_flux<T, N, 3, 0, STR, TW, PL>(VX, h[3], h[0], g, k);
 #pragma unroll
-                            for (int m = 0; m < OB_SHARED_CL; m++)
-                                if (m < ncl) xe_at(xs, 3, 1 + m)[lane] = F.template own_closure_flux<3, 0>(m);
-                        }
+                        for (int m = 0; m < NCL; m++) *xe_at(xs, 3, 1 + m, lane) = FX.template own_closure_flux<3, 0>(m);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pub[2 * W + xs]);
+            } else {
+                __syncwarp();
+                if (lane == 0 && warp > 0) mbar_arrive(&pub[2 * warp + xs]);
             }
-#pragma unroll
-            for (int f = 0; f < 4; f++) {
-#pragma unroll
-                for (int h = 0; h + 1 < N - 1; h++) { hA[f][h] = hA[f][h + 1]; hB[f][h] = hB[f][h + 1]; }
-                hA[f][N - 2] = lev[0][f * PL + ownA];
-                hB[f][N - 2] = lev[0][f * PL + ownB];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[sk]);
-            if (++sk == D) sk = 0;
-            if (++sn == D) { sn = 0; pn ^= 1; }
         }
+        if (!helper && k >= k0 - 1) {
+            // ---- phase C: upper fluxes; on full levels the west fluxes, the divergence and the tendency ----------------
+            if (full_level) {
+                mbar_wait(&pub[2 * (warp + 1) + xs], (uint32_t)xp);
+                if (warp + 1 != W) mbar_wait(&pub[2 * W + xs], (uint32_t)xp);
+            }
+            const int eo = eoY + k * g.sz;
+            auto tendency = [&](auto which_tag) {
+                constexpr int WHICH = decltype(which_tag)::value;
+                const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[tstage];
+                const T upper = stage_flux<T, N, WHICH, 2, STR, TW, PL>(VY, h[WHICH], h[2], g, k);
+                T cup[NCL > 0 ? NCL : 1];
+#pragma unroll
+                for (int m = 0; m < NCL; m++) cup[m] = FY.template own_closure_flux<WHICH, 2>(m);
+                if (full_level) {
+                    const T fx = stage_flux<T, N, WHICH, 0, STR, TW, PL>(VY, h[WHICH], h[0], g, k);
+                    const T fy = *yx_at(xs, warp, WHICH, 0);
+                    const T fy1 = *yx_at(xs, warp + 1, WHICH, 0);
+                    T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
+                    if (lane == 31) fx1 = *xe_at(xs, WHICH, 0, warp);
+                    const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
+                    const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower[WHICH]));
+                    T term = T(0);
+#pragma unroll
+                    for (int m = 0; m < NCL; m++) {
+                        const T cx = FY.template own_closure_flux<WHICH, 0>(m);
+                        const T cyv = *yx_at(xs, warp, WHICH, 1 + m);
+                        const T cy1 = *yx_at(xs, warp + 1, WHICH, 1 + m);
+                        T cx1 = __shfl_down_sync(0xffffffffu, cx, 1);
+                        if (lane == 31) cx1 = *xe_at(xs, WHICH, 1 + m, warp);
+                        const T d = Vi * ((cx1 - cx) + (cy1 - cyv) + (cup[m] - lower_c[WHICH][m]));
+                        term = m == 0 ? d : term + d;
+                    }
+                    const T res = FY.template finish<WHICH, NCL>(adv, term);
+                    if (live) G.p[G.off + eo] = res;
+                }
+                lower[WHICH] = upper;
+#pragma unroll
+                for (int m = 0; m < NCL; m++) lower_c[WHICH][m] = cup[m];
+            };
+            if (mom) {
+                tendency(std::integral_constant<int, 0>{});
+                tendency(std::integral_constant<int, 1>{});
+                tendency(std::integral_constant<int, 2>{});
+            }
+            if (has_tr) tendency(std::integral_constant<int, 3>{});
+        }
+        // history shift: level k becomes k-1 (helper: u at its west-flux point, v at its south-flux point)
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+#pragma unroll
+            for (int m = 0; m + 1 < N - 1; m++) h[f][m] = h[f][m + 1];
+            h[f][N - 2] = lev[0][f * PL + (f == 0 ? ownX : ownY)];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[sk]);
+        if (++sk == D) sk = 0;
+        if (++sn == D) { sn = 0; pn ^= 1; }
     }
 }
 

@@ -301,12 +301,13 @@ static bool stage_map(CUtensorMap *out, const void *ptr, cuuint64_t Px, cuuint64
     return true;
 }
 
-template <typename T, class S, int W, int R>
-static cudaError_t launch_stage(const TendP<T> &P, int fast, cudaStream_t st, int sm_count, int *nlaunch) {
+template <typename T, class S, int W, int NCL, bool LES>
+static cudaError_t launch_stage(const TendP<T> &P, cudaStream_t st, int sm_count, int *nlaunch) {
     if constexpr (S::kind != ADV_WENO) return cudaErrorNotSupported;
     else {
         constexpr int N = S::n;
-        using C = StageCfg<T, N, W, R>;
+        using C = StageCfg<T, N, W, NCL>;
+        static_assert(C::FITS, "staged-ring tile does not fit in shared memory");
         const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
         StageLaunch L;
         L.ntx = (Nx + C::TXC - 1) / C::TXC;
@@ -344,22 +345,14 @@ static cudaError_t launch_stage(const TendP<T> &P, int fast, cudaStream_t st, in
         }
         if ((long)L.ntx * L.nty * L.nkc > 2147483647L) return cudaErrorInvalidConfiguration;
         dim3 grid((unsigned)(L.ntx * L.nty * L.nkc), (unsigned)L.npass), block(C::THREADS);
-        cudaError_t e;
-        if (fast) {
-            auto kern = P.g.dzc ? tendency_stage_kernel<T, N, true, W, R, true> : tendency_stage_kernel<T, N, true, W, R, false>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            kern<<<grid, block, C::SMEM_BYTES, st>>>(P, M, L);
-        } else {
-            auto kern = P.g.dzc ? tendency_stage_kernel<T, N, false, W, R, true> : tendency_stage_kernel<T, N, false, W, R, false>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            kern<<<grid, block, C::SMEM_BYTES, st>>>(P, M, L);
-        }
+        auto kern = P.g.dzc ? tendency_stage_kernel<T, N, W, NCL, LES, true> : tendency_stage_kernel<T, N, W, NCL, LES, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, block, C::SMEM_BYTES, st>>>(P, M, L);
         *nlaunch += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        if (walls) return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch, 0, -1, 0, 1);
+        if (walls) return launch_march<T, S, 8, 32, 4>(P, 1, st, nlaunch, 0, -1, 0, 1);
         return cudaSuccess;
     }
 }
@@ -373,14 +366,17 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     done = true;
     const bool whole = tx_lo == 0 && tx_hi < 0 && !invert;
     if constexpr (StageSel<T, S>::built) {
-        if ((mode == 0 || mode == 8 || mode == 9) && whole && stage_applicable<T, S>(P)) {
-#ifdef OB_STAGE_ALT
-            if (mode == 9) return launch_stage<T, S, StageSel<T, S>::ALT_W, StageSel<T, S>::ALT_R>(P, fast, st, sm_count, nlaunch);
-#endif
-            return launch_stage<T, S, StageSel<T, S>::W, StageSel<T, S>::R>(P, fast, st, sm_count, nlaunch);
+        // the staged-ring kernel is built for the device division mode (rcp + Newton step, the default on this architecture)
+        if ((mode == 0 || mode == 8) && whole && fast && stage_applicable<T, S>(P)) {
+            bool les = false;
+            for (int m = 0; m < P.ncl; m++) les |= P.cl[m].kind != CL_SCALAR;
+            constexpr int W01 = StageSel<T, S>::W01, W2 = StageSel<T, S>::W2;
+            if (P.ncl == 0) return launch_stage<T, S, W01, 0, false>(P, st, sm_count, nlaunch);
+            if (P.ncl == 1) return les ? launch_stage<T, S, W01, 1, true>(P, st, sm_count, nlaunch) : launch_stage<T, S, W01, 1, false>(P, st, sm_count, nlaunch);
+            return launch_stage<T, S, W2, 2, true>(P, st, sm_count, nlaunch);
         }
     }
-    if (mode == 8 || mode == 9) mode = 0;
+    if (mode == 8) mode = 0;
     // auto: Float32 takes the TMA-staged variant (measured 4.5 % faster at 256^3), Float64 the LDG one (2 % faster)
     if (mode == 0 && sizeof(T) == 4 && S::kind == ADV_WENO) mode = 3;
     if (mode == 3) {   // TMA-staged planes (falls back to the LDG marching kernel where TMA does not apply)
