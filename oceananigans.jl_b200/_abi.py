@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libocean_b200.so")
+LIB_PATH = os.environ.get("OCEAN_B200_LIB") or os.path.join(HERE, "libocean_b200.so")   # same override as the Julia shim
 
 OB_MAX_TRACERS = 8
 OB_MAX_CLOSURES = 4

@@ -29,6 +29,10 @@
 #include "tendency_fast.cuh"
 #include "tendency_tma.cuh"
 
+#ifndef OB_STAGE_LIT
+#define OB_STAGE_LIT true   // coefficients as compile-time literals (false: constant-bank tables, for A/B checks)
+#endif
+
 namespace ob {
 
 template <typename T, int N, int W, int NCL>
@@ -83,7 +87,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *b, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) break;
-        __nanosleep(200);
+        __nanosleep(500);
     }
 }
 __device__ __forceinline__ void cp_async_elem(void *dst, const void *src, int bytes, bool valid) {
@@ -128,7 +132,7 @@ __device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const 
     }
     if constexpr (WHICH == 3) {
         T a[1] = {V.at(AF, LV, 0, 0)};
-        return flux_from_values<T, N, true, WHICH, ADV, STR, true>(s, a, g, k + LV);
+        return flux_from_values<T, N, true, WHICH, ADV, STR, OB_STAGE_LIT>(s, a, g, k + LV);
     } else {
         T a[2 * NC];
 #pragma unroll
@@ -137,7 +141,7 @@ __device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const 
             else if constexpr (WHICH == 1) a[m] = V.at(AF, LV, 0, m - NC);
             else a[m] = zval<T, N, TW, PL>(V, ha, AF, LV - NC + m);
         }
-        return flux_from_values<T, N, true, WHICH, ADV, STR, true>(s, a, g, k + LV);
+        return flux_from_values<T, N, true, WHICH, ADV, STR, OB_STAGE_LIT>(s, a, g, k + LV);
     }
 }
 
@@ -257,7 +261,7 @@ struct StageTerms {
         } else if constexpr (WHICH == 2) {
             if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
         }
-        if constexpr (NCL > 0) r = r - closure_term;
+        if constexpr (NCL > 0) r = sub_rn(r, closure_term);
         return r;
     }
 };
@@ -274,7 +278,9 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::RING_BYTES + C::XCH_BYTES);
     uint64_t *full = bars, *empty = bars + D, *pub = bars + 2 * D;   // pub[2*w + slot], w = 1 .. W (W: helper)
 
-    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps role branches and the
+    // coefficient literals on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0), lane = (int)threadIdx.x & 31;
     const GridD<T> &gg = P.g;
     const int Nx = gg.N[0], Ny = gg.N[1];
     int b = blockIdx.x;
@@ -437,11 +443,8 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
         }
         if (!helper && k >= k0 - 1) {
             // ---- phase C: upper fluxes; on full levels the west fluxes, the divergence and the tendency ----------------
-            if (full_level) {
-                mbar_wait(&pub[2 * (warp + 1) + xs], (uint32_t)xp);
-                if (warp + 1 != W) mbar_wait(&pub[2 * W + xs], (uint32_t)xp);
-            }
             const int eo = eoY + k * g.sz;
+            bool waited = false;   // the published fluxes are awaited as late as possible: right before their first use
             auto tendency = [&](auto which_tag) {
                 constexpr int WHICH = decltype(which_tag)::value;
                 const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[tstage];
@@ -451,6 +454,11 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
                 for (int m = 0; m < NCL; m++) cup[m] = FY.template own_closure_flux<WHICH, 2>(m);
                 if (full_level) {
                     const T fx = stage_flux<T, N, WHICH, 0, STR, TW, PL>(VY, h[WHICH], h[0], g, k);
+                    if (!waited) {
+                        mbar_wait(&pub[2 * (warp + 1) + xs], (uint32_t)xp);
+                        if (warp + 1 != W) mbar_wait(&pub[2 * W + xs], (uint32_t)xp);
+                        waited = true;
+                    }
                     const T fy = *yx_at(xs, warp, WHICH, 0);
                     const T fy1 = *yx_at(xs, warp + 1, WHICH, 0);
                     T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
@@ -465,8 +473,9 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
                         const T cy1 = *yx_at(xs, warp + 1, WHICH, 1 + m);
                         T cx1 = __shfl_down_sync(0xffffffffu, cx, 1);
                         if (lane == 31) cx1 = *xe_at(xs, WHICH, 1 + m, warp);
-                        const T d = Vi * ((cx1 - cx) + (cy1 - cyv) + (cup[m] - lower_c[WHICH][m]));
-                        term = m == 0 ? d : term + d;
+                        // (the marching kernel forms these under run-time closure counts, where nothing contracts; pinned here)
+                        const T d = mul_rn(Vi, (cx1 - cx) + (cy1 - cyv) + (cup[m] - lower_c[WHICH][m]));
+                        term = m == 0 ? d : add_rn(term, d);
                     }
                     const T res = FY.template finish<WHICH, NCL>(adv, term);
                     if (live) G.p[G.off + eo] = res;
