@@ -83,6 +83,15 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
+// ℑxy of four area-weighted values, 0.5 (0.5 (A a + A b) + 0.5 (A c + A d)), evaluated as the reference does: products and sums
+// rounded one by one (interpolation_operators.jl has no @muladd).  `A a + A b` would otherwise contract into an FMA around
+// either product, at the compiler's whim, and two kernels of this library would differ in the last bit.
+template <typename T> __device__ __forceinline__ T interp4_rn(T A, T a, T b, T c, T d) {
+    const T h = T(0.5);
+    return mul_rn(h, add_rn(mul_rn(h, add_rn(mul_rn(A, a), mul_rn(A, b))), mul_rn(h, add_rn(mul_rn(A, c), mul_rn(A, d)))));
+}
+template <typename T> __device__ __forceinline__ T interp2_rn(T A, T a, T b) { return mul_rn(T(0.5), add_rn(mul_rn(A, a), mul_rn(A, b))); }
+
 // Makhoul (1980) permutation of a DCT line (index_permutations.jl:18-36), 0-based: even i -> i/2 ; odd i -> N-1-(i-1)/2
 __device__ __forceinline__ int makhoul_index(int i, int N) { const int h = i >> 1; return (i & 1) ? N - 1 - h : h; }  // i >= 0
 

@@ -98,9 +98,9 @@ template <typename T> struct Grad {
     __device__ __forceinline__ T S11(int i, int j, int k) const { return dx_u(i, j, k); }
     __device__ __forceinline__ T S22(int i, int j, int k) const { return dy_v(i, j, k); }
     __device__ __forceinline__ T S33(int i, int j, int k) const { return dz_w(i, j, k); }
-    __device__ __forceinline__ T S12(int i, int j, int k) const { return T(0.5) * (dy_u(i, j, k) + dx_v(i, j, k)); }
-    __device__ __forceinline__ T S13(int i, int j, int k) const { return T(0.5) * (dz_u(i, j, k) + dx_w(i, j, k)); }
-    __device__ __forceinline__ T S23(int i, int j, int k) const { return T(0.5) * (dz_v(i, j, k) + dy_w(i, j, k)); }
+    __device__ __forceinline__ T S12(int i, int j, int k) const { return T(0.5) * add_rn(dy_u(i, j, k), dx_v(i, j, k)); }
+    __device__ __forceinline__ T S13(int i, int j, int k) const { return T(0.5) * add_rn(dz_u(i, j, k), dx_w(i, j, k)); }
+    __device__ __forceinline__ T S23(int i, int j, int k) const { return T(0.5) * add_rn(dz_v(i, j, k), dy_w(i, j, k)); }
 };
 
 // two-point interpolation of a ccc array to faces (interpolation_operators.jl:8-71), Flat => identity
@@ -223,10 +223,11 @@ template <typename T> __device__ __forceinline__ T Gu_finish(const TendP<T> &P, 
     if (P.has_cor) {  // coriolis_schemes.jl:67 : -ℑy(f) * ℑxyᶠᶜᵃ(Ay_q v) * Ay⁻¹ᶠᶜᶜ
         const bool fy = P.g.topo[1] == FLAT, fx = P.g.topo[0] == FLAT;
         T fbar = fy ? P.f : T(0.5) * (P.f + P.f);
-        auto Ayv = [&](int a, int b) { return (DXC * DZC(k)) * P.v.ld(a, b, k); };
-        auto Ix = [&](int b) { return fx ? Ayv(i, b) : T(0.5) * (Ayv(i - 1, b) + Ayv(i, b)); };
-        T I = fy ? Ix(j) : T(0.5) * (Ix(j) + Ix(j + 1));
-        r = r - (-fbar * I * (1 / (DXF * DZC(k))));
+        // products and sums rounded one by one, as the reference evaluates them (interp4_rn, common.cuh)
+        auto Ayv = [&](int a, int b) { return mul_rn(DXC * DZC(k), P.v.ld(a, b, k)); };
+        auto Ix = [&](int b) { return fx ? Ayv(i, b) : mul_rn(T(0.5), add_rn(Ayv(i - 1, b), Ayv(i, b))); };
+        T I = fy ? Ix(j) : mul_rn(T(0.5), add_rn(Ix(j), Ix(j + 1)));
+        r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (DXF * DZC(k))));
     }
     if (P.has_pHY) r = r - (P.g.topo[0] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i - 1, j, k)) * P.g.rdx;
     if (P.ncl > 0) {
@@ -247,10 +248,10 @@ template <typename T> __device__ __forceinline__ T Gv_finish(const TendP<T> &P, 
     if (P.has_cor) {  // coriolis_schemes.jl:68 : +ℑx(f) * ℑxyᶜᶠᵃ(Ax_q u) * Ax⁻¹ᶜᶠᶜ
         const bool fy = P.g.topo[1] == FLAT, fx = P.g.topo[0] == FLAT;
         T fbar = fx ? P.f : T(0.5) * (P.f + P.f);
-        auto Axu = [&](int a, int b) { return (DYC * DZC(k)) * P.u.ld(a, b, k); };
-        auto Ix = [&](int b) { return fx ? Axu(i, b) : T(0.5) * (Axu(i, b) + Axu(i + 1, b)); };
-        T I = fy ? Ix(j) : T(0.5) * (Ix(j - 1) + Ix(j));
-        r = r - (fbar * I * (1 / (DYF * DZC(k))));
+        auto Axu = [&](int a, int b) { return mul_rn(DYC * DZC(k), P.u.ld(a, b, k)); };
+        auto Ix = [&](int b) { return fx ? Axu(i, b) : mul_rn(T(0.5), add_rn(Axu(i, b), Axu(i + 1, b))); };
+        T I = fy ? Ix(j) : mul_rn(T(0.5), add_rn(Ix(j - 1), Ix(j)));
+        r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (DYF * DZC(k))));
     }
     if (P.has_pHY) r = r - (P.g.topo[1] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i, j - 1, k)) * P.g.rdy;
     if (P.ncl > 0) {

@@ -144,9 +144,9 @@ struct FastTerms {
     __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (ld(u, a, b, c) - ld(u, a, b, c - 1)) * G.rdzF(k + c); }
     __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (ld(w, a, b, c) - ld(w, a, b - 1, c)) * G.rdy; }
     __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (ld(v, a, b, c) - ld(v, a, b, c - 1)) * G.rdzF(k + c); }
-    __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * (dy_u(a, b, c) + dx_v(a, b, c)); }
-    __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * (dz_u(a, b, c) + dx_w(a, b, c)); }
-    __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * (dz_v(a, b, c) + dy_w(a, b, c)); }
+    __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * add_rn(dy_u(a, b, c), dx_v(a, b, c)); }
+    __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * add_rn(dz_u(a, b, c), dx_w(a, b, c)); }
+    __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * add_rn(dz_v(a, b, c), dy_w(a, b, c)); }
     // ℑ of a ccc array to faces (interpolation_operators.jl:8-71): D = direction of the -1 shift
     __device__ __forceinline__ T If1(const T *f, int D, int a, int b, int c) const {
         return T(0.5) * (ld(f, a - (D == 0), b - (D == 1), c - (D == 2)) + ld(f, a, b, c));
@@ -234,16 +234,16 @@ struct FastTerms {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
                 const T A = G.dx * dzC(0);
-                const T I = T(0.5) * (T(0.5) * (A * ld(v, -1, 0, 0) + A * ld(v, 0, 0, 0)) + T(0.5) * (A * ld(v, -1, 1, 0) + A * ld(v, 0, 1, 0)));
-                r = r - (-fbar * I * (1 / (G.dx * dzC(0))));
+                const T I = interp4_rn(A, ld(v, -1, 0, 0), ld(v, 0, 0, 0), ld(v, -1, 1, 0), ld(v, 0, 1, 0));
+                r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (G.dx * dzC(0))));
             }
             if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, -1, 0, 0)) * G.rdx; }
         } else if constexpr (WHICH == 1) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
                 const T A = G.dy * dzC(0);
-                const T I = T(0.5) * (T(0.5) * (A * ld(u, 0, -1, 0) + A * ld(u, 1, -1, 0)) + T(0.5) * (A * ld(u, 0, 0, 0) + A * ld(u, 1, 0, 0)));
-                r = r - (fbar * I * (1 / (G.dy * dzC(0))));
+                const T I = interp4_rn(A, ld(u, 0, -1, 0), ld(u, 1, -1, 0), ld(u, 0, 0, 0), ld(u, 1, 0, 0));
+                r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (G.dy * dzC(0))));
             }
             if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, 0, -1, 0)) * G.rdy; }
         } else if constexpr (WHICH == 2) {

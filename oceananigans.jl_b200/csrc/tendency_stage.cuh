@@ -175,9 +175,9 @@ struct StageTerms {
     __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (fld(0, a, b, c) - fld(0, a, b, c - 1)) * G.rdzF(k + c); }
     __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (fld(2, a, b, c) - fld(2, a, b - 1, c)) * G.rdy; }
     __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (fld(1, a, b, c) - fld(1, a, b, c - 1)) * G.rdzF(k + c); }
-    __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * (dy_u(a, b, c) + dx_v(a, b, c)); }
-    __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * (dz_u(a, b, c) + dx_w(a, b, c)); }
-    __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * (dz_v(a, b, c) + dy_w(a, b, c)); }
+    __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * add_rn(dy_u(a, b, c), dx_v(a, b, c)); }
+    __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * add_rn(dz_u(a, b, c), dx_w(a, b, c)); }
+    __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * add_rn(dz_v(a, b, c), dy_w(a, b, c)); }
     __device__ __forceinline__ T If1(const T *f, int D, int a, int b, int c) const {
         return T(0.5) * (ldg(f, a - (D == 0), b - (D == 1), c - (D == 2)) + ldg(f, a, b, c));
     }
@@ -246,16 +246,16 @@ struct StageTerms {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
                 const T A = G.dx * dzC(0);
-                const T I = T(0.5) * (T(0.5) * (A * fld(1, -1, 0, 0) + A * fld(1, 0, 0, 0)) + T(0.5) * (A * fld(1, -1, 1, 0) + A * fld(1, 0, 1, 0)));
-                r = r - (-fbar * I * (1 / (G.dx * dzC(0))));
+                const T I = interp4_rn(A, fld(1, -1, 0, 0), fld(1, 0, 0, 0), fld(1, -1, 1, 0), fld(1, 0, 1, 0));
+                r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (G.dx * dzC(0))));
             }
             if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, -1, 0, 0)) * G.rdx; }
         } else if constexpr (WHICH == 1) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
                 const T A = G.dy * dzC(0);
-                const T I = T(0.5) * (T(0.5) * (A * fld(0, 0, -1, 0) + A * fld(0, 1, -1, 0)) + T(0.5) * (A * fld(0, 0, 0, 0) + A * fld(0, 1, 0, 0)));
-                r = r - (fbar * I * (1 / (G.dy * dzC(0))));
+                const T I = interp4_rn(A, fld(0, 0, -1, 0), fld(0, 1, -1, 0), fld(0, 0, 0, 0), fld(0, 1, 0, 0));
+                r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (G.dy * dzC(0))));
             }
             if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, 0, -1, 0)) * G.rdy; }
         } else if constexpr (WHICH == 2) {

@@ -8,6 +8,15 @@ from test_gpu_parity import CONFIGS
 arch = ob.B200(0)
 for name in sys.argv[1:] or ["ppp_weno5", "stage_ppp"]:
     cfg = CONFIGS[name]
+    d = dict(cfg.__dict__)
+    if os.environ.get("DEBUG_FT") == "f32":
+        d["ft"] = np.float32
+    if os.environ.get("DEBUG_NOCOR"):
+        d["coriolis_f"] = None
+    if os.environ.get("DEBUG_NOCL"):
+        d["closure"] = ()
+    from helpers import Config
+    cfg = Config(**d)
     bm = cfg.b200_model(arch)
     ob.set(bm, **cfg.initial_conditions(5))
     bm.update_state()
