@@ -22,8 +22,14 @@ INSTANCES += [(t, tn, 1, nb) for t, tn in (("double", "f64"), ("float", "f32")) 
 INSTANCES += [(t, tn, 2, nb) for t, tn in (("double", "f64"), ("float", "f32")) for nb in (2, 3, 4, 5)]
 
 
-def _headers():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+# tendency_stage.cuh is only instantiated for the schemes StageSel marks as built (every TU includes it, but the others
+# never instantiate its templates): a change there rebuilds those instances only
+STAGE_HEADERS = ("tendency_stage.cuh",)
+STAGE_INSTANCES = {(2, 3)}
+
+
+def _headers(stage=True):
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")) and (stage or f not in STAGE_HEADERS)]
     hs.append(os.path.join(HERE, "..", "include", "ocean_b200.h"))
     return hs
 
@@ -44,7 +50,8 @@ def _run(cmd):
 
 def build(force=False, verbose=False, jobs=None):
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = _headers()
+    hdrs = _headers(stage=False)
+    hdrs_stage = _headers(stage=True)
     jobs_list = []
     objs = []
     main_o = os.path.join(OBJ, "ocean_b200.o")
@@ -56,7 +63,7 @@ def build(force=False, verbose=False, jobs=None):
     for t, tn, kind, nb in INSTANCES:
         o = os.path.join(OBJ, "tend_%s_k%d_n%d.o" % (tn, kind, nb))
         objs.append(o)
-        if force or _stale(o, [inst] + hdrs):
+        if force or _stale(o, [inst] + (hdrs_stage if (kind, nb) in STAGE_INSTANCES else hdrs)):
             jobs_list.append([NVCC, *FLAGS, "-DOB_TI_T=%s" % t, "-DOB_TI_TN=%s" % tn, "-DOB_TI_KIND=%d" % kind,
                               "-DOB_TI_NB=%d" % nb, "-c", inst, "-o", o])
     if jobs_list:

@@ -3,17 +3,20 @@
 // One CTA computes ALL tendencies of a 32 x W tile of columns (Gu, Gv, Gw and one tracer per pass) while it marches
 // in k.  Every stencil operand is read from shared memory:
 //
-//   * a PRODUCER warp feeds a ring of D = N+2 levels; each level holds the halo'd (32+2N) x (W+2N) planes of u, v, w
-//     and the tracer, brought in by TMA (cp.async.bulk.tensor.3d, one box per field and level, completion on an mbarrier)
-//     -- or by cp.async when the row pitch of the parent arrays is not a multiple of 16 bytes (Float32 with odd padding).
+//   * a ring of D = N+2 levels holds the halo'd (32+2N) x (W+2N) planes of u, v, w and the tracer, brought in by TMA
+//     (cp.async.bulk.tensor.3d, one box per field and level, completion on an mbarrier); the warp that is LAST to release
+//     a level issues the loads of the level that takes its place -- no thread spins as a producer.  When the row pitch of
+//     the parent arrays is not a multiple of 16 bytes (Float32 with odd padding) cp.async copies take the place of TMA.
 //     Levels k .. k+N live in the ring; the N-1 levels below k of a thread's own column are kept in registers, so the
 //     z-lines of the stencils cost no memory traffic at all.
 //   * W COMPUTE warps: warp w owns row w of the tile, lane l the column i0+l.  A thread evaluates, per level and
 //     tendency, the flux through the west face and the south face of its cell and through the upper face; the east flux
 //     comes from lane+1 (shuffle), the north flux is the south flux the next warp published in shared memory, the lower
 //     flux is last level's upper flux (register).  Every face flux is evaluated ONCE.
-//   * a HELPER warp evaluates the tile's east-edge x fluxes (lanes = rows) and north-edge y fluxes (lanes = columns) and
-//     publishes them, so tiles advance by the full 32 x W cells: no overlap lanes, no overlap rows.
+//   * four HELPER warps (one per SM sub-partition, so the FP64 pipes stay balanced) evaluate the tile's east-edge x
+//     fluxes (lanes = rows) and north-edge y fluxes (lanes = columns) -- helper q those of tendency q -- and publish them,
+//     so tiles advance by the full 32 x W cells: no overlap lanes, no overlap rows.  When TMA is not applicable the
+//     helpers also feed the ring (helper f copies field f with cp.async).
 //   * warps never meet at a CTA barrier: ring slots are recycled through full/empty mbarriers (the empty barrier of a
 //     level needs one arrival per consumer warp), published fluxes through one mbarrier per publishing warp.  Because a
 //     level k+N can only be loaded after EVERY consumer has released level k-2, two consumer warps are never more than one
@@ -55,9 +58,10 @@ struct StageCfg {
     static constexpr int XE_SLOT = NQ * NV * 32;              // published east-edge fluxes: [q][v][row]
     static constexpr int XCH_SLOT = YX_SLOT + XE_SLOT;
     static constexpr int XCH_BYTES = 2 * XCH_SLOT * (int)sizeof(T);
+    static constexpr int NH = 4;                              // helper warps: helper q serves tendency q
     static constexpr int NBAR = 2 * D + 2 * (W + 1);
-    static constexpr int SMEM_BYTES = RING_BYTES + XCH_BYTES + NBAR * 8;
-    static constexpr int THREADS = (W + 2) * 32;
+    static constexpr int SMEM_BYTES = RING_BYTES + XCH_BYTES + NBAR * 8 + D * 4;   // + the release counters of the TMA path
+    static constexpr int THREADS = (W + NH) * 32;
     static constexpr bool FITS = SMEM_BYTES <= 227 * 1024;
 };
 
@@ -267,7 +271,7 @@ struct StageTerms {
 };
 
 template <typename T, int N, int W, int NCL, bool LES, bool STR>
-__global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M, const StageLaunch L) {
+__global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M, const StageLaunch L) {
     using C = StageCfg<T, N, W, NCL>;
     constexpr int TW = C::TW, PL = C::PL, D = C::D, NV = C::NV;
     using View = StageView<T, N, TW, PL>;
@@ -296,70 +300,46 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
     const bool has_tr = tstage < P.ntr;
     const int nfields = has_tr ? 4 : 3;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < D; s++) { mbar_init(&full[s], L.use_tma ? 1 : 32); mbar_init(&empty[s], W + 1); }
-        for (int s = 0; s < 2 * (W + 1); s++) mbar_init(&pub[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
+    int *done = reinterpret_cast<int *>(smem + C::RING_BYTES + C::XCH_BYTES + C::NBAR * 8);   // TMA path: releases per slot (monotonic)
     // tile origin in parent coordinates (0-based); the box starts on a 16-byte boundary of the row
     const int cxu = i0 - N + gg.H[0] - 1;
     const int cx0 = cxu & ~(C::EPV - 1), cy0 = j0 - N + gg.H[1] - 1;
     const int sh = cxu - cx0;
-
-    // ---------------------------------------------------------------- producer warp --------------------------------
-    if (warp == W + 1) {
-        if (L.use_tma) {
-            if (lane == 0) {
-                for (int Lv = kfirst; Lv <= klast; Lv++) {
-                    const int n = Lv - kfirst, s = n % D;
-                    if (n >= D) mbar_wait_sleep(&empty[s], (uint32_t)(((n / D) - 1) & 1));
-                    unsigned char *dst = smem + s * C::LEVEL_BYTES;
-                    mbar_expect_tx(&full[s], nfields * C::BOX_BYTES);
-                    const int cz = Lv + gg.H[2] - 1;
-                    tma_load_3d(dst, &M.m[0], &full[s], cx0, cy0, cz);
-                    tma_load_3d(dst + C::PLANE_BYTES, &M.m[1], &full[s], cx0, cy0, cz);
-                    tma_load_3d(dst + 2 * C::PLANE_BYTES, &M.m[2], &full[s], cx0, cy0, cz);
-                    if (has_tr) tma_load_3d(dst + 3 * C::PLANE_BYTES, &M.m[3 + tstage], &full[s], cx0, cy0, cz);
-                }
-            }
-        } else {
-            // cp.async path: the 32 lanes copy the boxes element by element (zero-fill outside the parent array)
-            const int Px = P.u.sy, Py = (int)(P.u.sz / P.u.sy);
-            for (int Lv = kfirst; Lv <= klast; Lv++) {
-                const int n = Lv - kfirst, s = n % D;
-                if (n >= D) mbar_wait_sleep(&empty[s], (uint32_t)(((n / D) - 1) & 1));
-                const int cz = Lv + gg.H[2] - 1;
-                for (int f = 0; f < nfields; f++) {
-                    const Fld<T> &F = f == 0 ? P.u : f == 1 ? P.v : f == 2 ? P.w : P.c[tstage];
-                    T *dst = reinterpret_cast<T *>(smem + s * C::LEVEL_BYTES + f * C::PLANE_BYTES);
-                    const T *src = F.p + (long)cz * F.sz;
-                    for (int e = lane; e < C::TW * C::TH; e += 32) {
-                        const int yy = e / C::TW, xx = e - yy * C::TW;
-                        const int gx = cx0 + xx, gy = cy0 + yy;
-                        const bool ok = gx < Px && gy < Py;
-                        cp_async_elem(dst + e, src + (ok ? (long)gy * Px + gx : 0), (int)sizeof(T), ok);
-                    }
-                }
-                cp_async_mbar_arrive(&full[s]);
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-        }
-        return;
+    const bool use_tma = L.use_tma != 0;
+    auto tma_issue = [&](int Lv) {   // one thread: the boxes of level Lv into its ring slot
+        const int s = (Lv - kfirst) % D;
+        unsigned char *dst = smem + s * C::LEVEL_BYTES;
+        mbar_expect_tx(&full[s], nfields * C::BOX_BYTES);
+        const int cz = Lv + gg.H[2] - 1;
+        tma_load_3d(dst, &M.m[0], &full[s], cx0, cy0, cz);
+        tma_load_3d(dst + C::PLANE_BYTES, &M.m[1], &full[s], cx0, cy0, cz);
+        tma_load_3d(dst + 2 * C::PLANE_BYTES, &M.m[2], &full[s], cx0, cy0, cz);
+        if (has_tr) tma_load_3d(dst + 3 * C::PLANE_BYTES, &M.m[3 + tstage], &full[s], cx0, cy0, cz);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < D; s++) { mbar_init(&full[s], use_tma ? 1 : nfields * 32); mbar_init(&empty[s], W + C::NH); done[s] = 0; }
+        for (int s = 0; s < 2 * (W + 1); s++) mbar_init(&pub[s], s >= 2 * W ? C::NH : 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (use_tma)
+            for (int Lv = kfirst; Lv < kfirst + D && Lv <= klast; Lv++) tma_issue(Lv);
     }
+    __syncthreads();
 
     // ---------------------------------------------------------------- consumers ------------------------------------
-    // Compute warps (warp < W): own point (i0+lane, j0+warp), the same for every phase.  Helper (warp == W): its south-flux
-    // point is (i0+lane, j0+TYC) -- the tile's north edge, lanes = columns -- and its west-flux point (i0+32, j0+lane) --
-    // the east edge, lanes = rows.  Phase A (south fluxes) runs the same code in every consumer warp.
-    const bool helper = warp == W;
+    // Compute warps (warp < W): own point (i0+lane, j0+warp), the same for every phase.  Helpers (warp >= W): the south-flux
+    // point is (i0+lane, j0+TYC) -- the tile's north edge, lanes = columns -- and the west-flux point (i0+32, j0+lane) --
+    // the east edge, lanes = rows; helper hq does tendency hq.  Phase A (south fluxes) is the same code in every warp.
+    const bool helper = warp >= W;
+    const int hq = warp - W;
+    const bool do0 = mom && (!helper || hq == 0), do1 = mom && (!helper || hq == 1), do2 = mom && (!helper || hq == 2);
+    const bool do3 = has_tr && (!helper || hq == 3);
+    const int pw = helper ? W : warp;   // publication row of this warp's south fluxes
     FastGeom<T, STR> g;
     g.init(gg, P.u.sy, P.u.sz);
     const int rowB = min(lane, C::TYC - 1);
     const int ownY = (helper ? C::TYC + N : warp + N) * TW + lane + N + sh;
     const int ownX = helper ? (rowB + N) * TW + 32 + N + sh : ownY;
-    const int gi = i0 + lane, gj = j0 + warp;
+    const int gi = i0 + lane, gj = j0 + (helper ? 0 : warp);
     const int eoY = min(gi, Nx + 1) + min(helper ? j0 + C::TYC : gj, Ny + 1) * g.sy;
     const int eoX = helper ? min(i0 + 32, Nx + 1) + min(j0 + rowB, Ny + 1) * g.sy : eoY;
     const bool live = !helper && gi <= Nx && gj <= Ny;
@@ -379,9 +359,42 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
     }
     // running ring positions: level k is in slot sk; level k+N (the newest one this level needs) in slot sn with phase pn
     int sk = 0, sn = N % D, pn = (N / D) & 1;
+    // cp.async path: the 32 lanes of helper f copy the box of field f element by element (zero-fill outside the parent
+    // array) for every level up to `upto`; a slot is reused once every consumer has released its previous level.
+    int fed = kfirst - 1;
+    auto feed = [&](bool blocking, int upto) {
+        const int Px = P.u.sy, Py = (int)(P.u.sz / P.u.sy);
+        const Fld<T> &F = hq == 0 ? P.u : hq == 1 ? P.v : hq == 2 ? P.w : P.c[tstage];
+        while (fed < upto && fed < klast) {
+            const int Lv = fed + 1, n = Lv - kfirst, s = n % D;
+            if (n >= D) {
+                const uint32_t par = (uint32_t)(((n / D) - 1) & 1);
+                if (blocking) mbar_wait(&empty[s], par);
+                else {
+                    uint32_t ok;
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(smem_u32(&empty[s])), "r"(par) : "memory");
+                    if (!ok) return;
+                }
+            }
+            T *dst = reinterpret_cast<T *>(smem + s * C::LEVEL_BYTES + hq * C::PLANE_BYTES);
+            const T *src = F.p + (long)(Lv + gg.H[2] - 1) * F.sz;
+            for (int e = lane; e < C::TW * C::TH; e += 32) {
+                const int yy = e / C::TW, xx = e - yy * C::TW;
+                const int gx = cx0 + xx, gy = cy0 + yy;
+                const bool ok = gx < Px && gy < Py;
+                cp_async_elem(dst + e, src + (ok ? (long)gy * Px + gx : 0), (int)sizeof(T), ok);
+            }
+            cp_async_mbar_arrive(&full[s]);
+            fed = Lv;
+        }
+    };
+    const bool feeder = !use_tma && helper && hq < nfields;
+    if (feeder) feed(true, kfirst + N - 1);
     for (int n = 0; n < N; n++) mbar_wait(&full[n], 0);
 
     for (int k = kfirst; k <= k1; k++) {
+        if (feeder) feed(true, k + N);
         mbar_wait(&full[sn], (uint32_t)pn);
         const T *lev[N + 1];
 #pragma unroll
@@ -393,22 +406,26 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
         for (int d = 0; d <= N; d++) VY.pl[d] = lev[d] + ownY;
         const Terms FY{P, g, VY, h[0], h[1], h[2], h[3], eoY + k * g.sz, k, tstage};
         if (full_level) {
-            // ---- phase A: south fluxes, published for the warp below (helper: the tile's north edge) ------------------
-            if (mom) {
-                *yx_at(xs, warp, 0, 0) = stage_flux<T, N, 0, 1, STR, TW, PL>(VY, h[0], h[1], g, k);
-                *yx_at(xs, warp, 1, 0) = stage_flux<T, N, 1, 1, STR, TW, PL>(VY, h[1], h[1], g, k);
-                *yx_at(xs, warp, 2, 0) = stage_flux<T, N, 2, 1, STR, TW, PL>(VY, h[2], h[1], g, k);
+            // ---- phase A: south fluxes, published for the warp below (helpers: the tile's north edge) ------------------
+            if (do0) {
+                *yx_at(xs, pw, 0, 0) = stage_flux<T, N, 0, 1, STR, TW, PL>(VY, h[0], h[1], g, k);
 #pragma unroll
-                for (int m = 0; m < NCL; m++) {
-                    *yx_at(xs, warp, 0, 1 + m) = FY.template own_closure_flux<0, 1>(m);
-                    *yx_at(xs, warp, 1, 1 + m) = FY.template own_closure_flux<1, 1>(m);
-                    *yx_at(xs, warp, 2, 1 + m) = FY.template own_closure_flux<2, 1>(m);
-                }
+                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 0, 1 + m) = FY.template own_closure_flux<0, 1>(m);
             }
-            if (has_tr) {
-                *yx_at(xs, warp, 3, 0) = stage_flux<T, N, 3, 1, STR, TW, PL>(VY, h[3], h[1], g, k);
+            if (do1) {
+                *yx_at(xs, pw, 1, 0) = stage_flux<T, N, 1, 1, STR, TW, PL>(VY, h[1], h[1], g, k);
 #pragma unroll
-                for (int m = 0; m < NCL; m++) *yx_at(xs, warp, 3, 1 + m) = FY.template own_closure_flux<3, 1>(m);
+                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 1, 1 + m) = FY.template own_closure_flux<1, 1>(m);
+            }
+            if (do2) {
+                *yx_at(xs, pw, 2, 0) = stage_flux<T, N, 2, 1, STR, TW, PL>(VY, h[2], h[1], g, k);
+#pragma unroll
+                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 2, 1 + m) = FY.template own_closure_flux<2, 1>(m);
+            }
+            if (do3) {
+                *yx_at(xs, pw, 3, 0) = stage_flux<T, N, 3, 1, STR, TW, PL>(VY, h[3], h[1], g, k);
+#pragma unroll
+                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 3, 1 + m) = FY.template own_closure_flux<3, 1>(m);
             }
             if (helper) {
                 // ---- helper phase B: west fluxes at the tile's east edge, lanes = rows -----------------------------------
@@ -417,18 +434,22 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
                 for (int d = 0; d <= N; d++) VX.pl[d] = lev[d] + ownX;
                 const Terms FX{P, g, VX, h[0], h[1], h[2], h[3], eoX + k * g.sz, k, tstage};
                 if (lane < C::TYC) {
-                    if (mom) {
+                    if (do0) {
                         *xe_at(xs, 0, 0, lane) = stage_flux<T, N, 0, 0, STR, TW, PL>(VX, h[0], h[0], g, k);
+#pragma unroll
+                        for (int m = 0; m < NCL; m++) *xe_at(xs, 0, 1 + m, lane) = FX.template own_closure_flux<0, 0>(m);
+                    }
+                    if (do1) {
                         *xe_at(xs, 1, 0, lane) = stage_flux<T, N, 1, 0, STR, TW, PL>(VX, h[1], h[0], g, k);
+#pragma unroll
+                        for (int m = 0; m < NCL; m++) *xe_at(xs, 1, 1 + m, lane) = FX.template own_closure_flux<1, 0>(m);
+                    }
+                    if (do2) {
                         *xe_at(xs, 2, 0, lane) = stage_flux<T, N, 2, 0, STR, TW, PL>(VX, h[2], h[0], g, k);
 #pragma unroll
-                        for (int m = 0; m < NCL; m++) {
-                            *xe_at(xs, 0, 1 + m, lane) = FX.template own_closure_flux<0, 0>(m);
-                            *xe_at(xs, 1, 1 + m, lane) = FX.template own_closure_flux<1, 0>(m);
-                            *xe_at(xs, 2, 1 + m, lane) = FX.template own_closure_flux<2, 0>(m);
-                        }
+                        for (int m = 0; m < NCL; m++) *xe_at(xs, 2, 1 + m, lane) = FX.template own_closure_flux<2, 0>(m);
                     }
-                    if (has_tr) {
+                    if (do3) {
                         *xe_at(xs, 3, 0, lane) = stage_flux<T, N, 3, 0, STR, TW, PL>(VX, h[3], h[0], g, k);
 #pragma unroll
                         for (int m = 0; m < NCL; m++) *xe_at(xs, 3, 1 + m, lane) = FX.template own_closure_flux<3, 0>(m);
@@ -499,7 +520,25 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) tendency_stage_kernel(const _
             h[f][N - 2] = lev[0][f * PL + (f == 0 ? ownX : ownY)];
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[sk]);
+        if (use_tma) {
+            // release level k; the last of the W+NH consumer warps to do so issues the loads of level k+D into the slot
+            if (lane == 0) {
+                __threadfence_block();
+                const int old = atomicAdd(&done[sk], 1);
+                if (old % (W + C::NH) == W + C::NH - 1 && k + D <= klast) {
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tma_issue(k + D);
+                }
+            }
+        } else {
+            if (lane == 0) mbar_arrive(&empty[sk]);
+            if (helper && hq < nfields) {
+                // cp.async path: helper f copies field f.  Opportunistic: if the level that takes this slot can be loaded
+                // already, do it now; otherwise the blocking catch-up at the top of a later level does it.
+                feed(false, k + N + 1);
+            }
+        }
         if (++sk == D) sk = 0;
         if (++sn == D) { sn = 0; pn ^= 1; }
     }
