@@ -83,16 +83,15 @@ struct StageLaunch {
 __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// wait with back-off: the producer spends its life here and must not compete for issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *b, uint32_t parity) {
+// wait of a warp that is expected to be early (the helpers run ahead of the compute warps): the try_wait carries a
+// suspend-time hint, so the warp sleeps in hardware instead of competing for issue slots with a polling loop
+__device__ __forceinline__ void mbar_wait_long(uint64_t *b, uint32_t parity) {
     const uint32_t a = smem_u32(b);
     uint32_t ok;
-    for (;;) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) break;
-        __nanosleep(500);
-    }
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void cp_async_elem(void *dst, const void *src, int bytes, bool valid) {
     const int sz = valid ? bytes : 0;
@@ -369,7 +368,7 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
             const int Lv = fed + 1, n = Lv - kfirst, s = n % D;
             if (n >= D) {
                 const uint32_t par = (uint32_t)(((n / D) - 1) & 1);
-                if (blocking) mbar_wait(&empty[s], par);
+                if (blocking) mbar_wait_long(&empty[s], par);
                 else {
                     uint32_t ok;
                     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -395,7 +394,16 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
 
     for (int k = kfirst; k <= k1; k++) {
         if (feeder) feed(true, k + N);
+        // The helpers have a sixth of a compute warp's work: left to themselves they would spend the level polling the ring
+        // barrier and take issue slots from the compute warps.  They block on a hardware named barrier instead, which
+        // compute warp 0 arrives at (without waiting) once it has seen level k+N in the ring.
+        // Two barrier ids alternate with the level: warp 0 can be up to two levels ahead of a helper while the ring is still
+        // being primed (afterwards a level k+N is only loaded once every consumer has released k-2), and arrivals of
+        // different levels must not meet in one barrier phase.
+        const int bar_id = 1 + ((k - kfirst) & 1);
+        if (helper) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * (1 + C::NH)) : "memory");
         mbar_wait(&full[sn], (uint32_t)pn);
+        if (warp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "n"(32 * (1 + C::NH)) : "memory");
         const T *lev[N + 1];
 #pragma unroll
         for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * C::LEVEL; }
