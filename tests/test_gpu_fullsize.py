@@ -70,7 +70,13 @@ def test_marching_and_generic_tendency_kernels_agree_at_256(big):
     m.compute_tendencies()
     for r, g in zip(march, m.Gn):
         assert np.array_equal(g.interior(), r)
-    m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, 0)
+    for mode in (8, 0):   # staged-ring kernel (explicitly and as the automatic choice): same arithmetic, bit-identical
+        for g in m.Gn:
+            g.set_parent(np.zeros(g.P[::-1], g.grid.FT))
+        m.set_option(_abi.OB_OPT_TENDENCY_KERNEL, mode)
+        m.compute_tendencies()
+        for r, g in zip(march, m.Gn):
+            assert np.array_equal(g.interior(), r)
 
 
 def test_poisson_solver_inverts_the_laplacian_at_256(arch):
