@@ -147,7 +147,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="device lanes (independent host-resident members) of the e2e leg; 1 = serial only")
     ap.add_argument("--overlap", action="store_true", help="distributed: compute interior tendency tiles while the x halos are in flight (OB_OPT_OVERLAP_HALO)")
     ap.add_argument("--f32", action="store_true")
-    ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is --size x size x size whatever N (default: weak, size^3 per GPU)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is --nx x ny x nz whatever N (default: weak, size^3 per GPU)")
+    ap.add_argument("--nx", type=int, default=0, help="strong scaling: global cells in x (default: --size); the recorded runs use --strong --nx 512 --size 256")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -171,8 +172,9 @@ def main():
     ft = np.float32 if args.f32 else np.float64
     n = args.size
     ny, nz = args.ny or n, args.nz or n
-    cfg = workload_config(n, ft=ft, nx=n if args.strong else n * world, ny=ny, nz=nz)
-    nx_local = n // world if args.strong else n
+    nx_global = (args.nx or n) if args.strong else n * world
+    cfg = workload_config(n, ft=ft, nx=nx_global, ny=ny, nz=nz)
+    nx_local = nx_global // world
     model = cfg.b200_model(arch)
     if args.overlap:
         model.set_option(_abi.OB_OPT_OVERLAP_HALO, 1)
@@ -243,21 +245,24 @@ def main():
     if tend["calls"]:
         avg_ms = tend["ms_total"] / tend["calls"]
         ach = alg_bytes / (avg_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic cannot be measured without a profiler: it is the figure of the committed ncu capture of this kernel
+        # on this workload (profiles/tendency_traffic.json names the capture), reported only for the configuration captured
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "tendency_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and (n, ny, nz) == (256, 256, 256) and not args.f32 and world == 1:
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
             except Exception:
                 pass
         roofline = {"kernel": "fused tendency (Gu,Gv,Gw,Gb in one launch)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "note": "Float64 WENO-5 is FP64-issue bound on B200, not HBM bound (DESIGN.md §roofline)"}
     # second roofline of the same kernel: FP64 issue.  FP64 thread-instructions per cell come from the committed ncu capture
     # (profiles/tendency_traffic.json: DFMA+DMUL+DADD executed / cells, tile-overlap lanes included); the peak is measured
     # live with a DFMA microbenchmark (ob_fp64_peak).
-    if roofline is not None and not args.f32:
+    if roofline is not None and not args.f32 and (n, ny, nz) == (256, 256, 256):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "tendency_traffic.json")))
             per_cell = tj.get("fp64_instructions_per_cell")

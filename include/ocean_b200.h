@@ -117,7 +117,7 @@ typedef struct {
 typedef struct {
     ob_grid_desc grid;
     int32_t advection_kind;   /* ob_advection_kind */
-    int32_t advection_order;  /* WENO: 3,5,7,9,11 ; Centered: 2,4,..,12 */
+    int32_t advection_order;  /* WENO: 3,5,7,9 ; Centered: 2,4,6 (anything else: OB_ERR_UNSUPPORTED) */
     int32_t weno_division;    /* ob_weno_division */
     int32_t n_closures;
     ob_closure_desc closures[OB_MAX_CLOSURES];
@@ -180,6 +180,13 @@ int32_t ob_model_bind_field(ob_model *m, int32_t field_id, void *device_ptr);
 int32_t ob_model_set_bc_array(ob_model *m, int32_t field_id, int32_t side, const void *values);
 /* fill_halo_regions!(field) -- src/BoundaryConditions/fill_halo_regions.jl:20-38 */
 int32_t ob_fill_halo(ob_model *m, int32_t field_id, int32_t fill_normal_flow_bcs);
+/* fill_halo_regions!(c::OffsetArray, bcs, indices, loc, grid) for ANY field array, model-bound or not (diagnostics, user
+ * fields, closure fields built by the host): the same kernels and the same ordering (non-periodic sides first, then
+ * periodic over the full parent extent) as ob_fill_halo.  `loc[d]` = 1 for a Face location along d; `bc_arrays` is NULL or six
+ * device pointers (NULL entries = constant conditions) laid out as for ob_model_set_bc_array.  Communication halos of a
+ * distributed field belong to a model (ob_fill_halo).  src/BoundaryConditions/fill_halo_regions.jl:20-38 */
+int32_t ob_fill_halo_array(ob_ctx *ctx, const ob_grid_desc *grid, void *device_ptr, const int32_t *loc, const ob_bc_desc *bcs,
+                           const void *const *bc_arrays, int32_t fill_normal_flow_bcs);
 /* update_state!(model) -- update_nonhydrostatic_model_state.jl:22-62 (halos, closure fields, pHY′, tendencies) */
 int32_t ob_update_state(ob_model *m);
 /* compute_tendencies!(model) -- compute_nonhydrostatic_tendencies.jl:12-40 */
@@ -200,8 +207,9 @@ int32_t ob_make_pressure_correction(ob_model *m, double dtau);
  * `first` != 0 replays maybe_prepare_first_time_step! (an extra update_state!). */
 int32_t ob_time_step_rk3(ob_model *m, double dt, int32_t first);
 int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first);
-/* implementation options (testing / profiling): OB_OPT_TENDENCY_KERNEL = 0 auto, 1 generic one-thread-per-cell kernel,
- * 2 flux-sharing marching kernel, 3 marching kernel with TMA-staged stencil planes (falls back to 2 where TMA does not apply) */
+/* implementation options (testing / profiling): OB_OPT_TENDENCY_KERNEL = 0 auto (the staged-ring kernel where it applies,
+ * else the marching kernel), 1 generic one-thread-per-cell kernel, 2 flux-sharing marching kernel, 3 marching kernel with
+ * TMA-staged stencil planes, 8 staged-ring kernel (tendency_stage.cuh; falls back to 0 where it does not apply) */
 #define OB_OPT_TENDENCY_KERNEL 1
 /* OB_OPT_FUSE_PROJECTION = 1 (default): single-device substeps fuse real-copy + correction + p rescale; 0: reference kernel sequence */
 #define OB_OPT_FUSE_PROJECTION 2

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "ob_cell_advection_timescale": [_P, C.POINTER(_dbl)],
     "ob_model_create": [_P, C.POINTER(ModelDesc), _PP], "ob_model_destroy": [_P],
     "ob_model_bind_field": [_P, _i32, _P], "ob_model_set_bc_array": [_P, _i32, _i32, _P], "ob_fill_halo": [_P, _i32, _i32],
+    "ob_fill_halo_array": [_P, C.POINTER(GridDesc), _P, C.POINTER(_i32 * 3), C.POINTER(BcDesc), _P, _i32],
     "ob_update_state": [_P], "ob_compute_tendencies": [_P], "ob_compute_closure_fields": [_P],
     "ob_update_hydrostatic_pressure": [_P],
     "ob_rk3_substep": [_P, _dbl, _dbl, _dbl, _i32], "ob_ab2_step": [_P, _dbl, _dbl], "ob_cache_tendencies": [_P],

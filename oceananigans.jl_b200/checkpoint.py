@@ -20,7 +20,9 @@ def checkpoint(model, path):
     out["pNHS"] = model.pressures["pNHS"].parent()
     c = model.clock
     out["clock"] = np.array([c.time, c.iteration, c.stage, c.last_dt, c.last_stage_dt], dtype=np.float64)
+    arch = model.grid.architecture
     out["meta"] = np.array([model.timestepper, str(np.dtype(model.grid.FT)), ",".join(model.tracer_names)])
+    out["layout"] = np.array([getattr(arch, "rank", 0), getattr(arch, "world", 1)] + [int(n) for n in model.grid.N], dtype=np.int64)
     np.savez(path, **out)
     return path
 
@@ -31,6 +33,11 @@ def restore(model, path):
     ts, ft, names = [str(x) for x in z["meta"]]
     if ts != model.timestepper or names != ",".join(model.tracer_names) or ft != str(np.dtype(model.grid.FT)):
         raise ValueError("checkpoint %r was written by a different model (%s, %s, tracers %s)" % (path, ts, ft, names))
+    if "layout" in z:
+        arch = model.grid.architecture
+        want = [getattr(arch, "rank", 0), getattr(arch, "world", 1)] + [int(n) for n in model.grid.N]
+        if [int(x) for x in z["layout"]] != want:
+            raise ValueError("checkpoint %r holds rank/world/local size %r, this model is %r" % (path, [int(x) for x in z["layout"]], want))
     for name, f in model.prognostic_fields.items():
         f.set_parent(z["field__" + name])
     for n, f in enumerate(model.Gm):

@@ -178,16 +178,22 @@ extern "C" int32_t ob_free_host(ob_ctx *ctx, void *ptr) {
     return OB_OK;
 }
 extern "C" int32_t ob_memcpy_h2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return fail(OB_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));   // the caller may have made another device current (multi-context hosts)
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return OB_OK;
 }
 extern "C" int32_t ob_memcpy_d2h(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return fail(OB_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return OB_OK;
 }
 // stream-ordered device -> pinned-host copy: the host may read dst after ob_sync (or after a later blocking call on ctx)
 extern "C" int32_t ob_memcpy_d2h_async(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return fail(OB_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));   // the caller may have made another device current (multi-context hosts)
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return OB_OK;
 }
@@ -205,6 +211,8 @@ extern "C" int32_t ob_stream_wait(ob_ctx *ctx, ob_ctx *other) {
     return OB_OK;
 }
 extern "C" int32_t ob_memcpy_d2d(ob_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return fail(OB_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));   // the caller may have made another device current (multi-context hosts)
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return OB_OK;
 }
@@ -1055,6 +1063,16 @@ struct ModelT : ob_model {
     // parent extent in y and z (OneDBuffer, communication_buffers.jl:96-114), so corners stay consistent exactly as
     // with the local periodic copy.
     int32_t exchange_x_halos(const std::vector<int> &ids, bool defer = false) {
+        // more fields than one batch descriptor holds (several AMD closures x several tracers): one push/unpack epoch per
+        // chunk, as fill_halos() does for the local directions
+        if (ids.size() > OB_MAX_HALO_TASKS) {
+            if (defer) return fail(OB_ERR_INVALID, "a deferred halo exchange is limited to %d fields", OB_MAX_HALO_TASKS);
+            for (size_t pos = 0; pos < ids.size(); pos += OB_MAX_HALO_TASKS) {
+                std::vector<int> part(ids.begin() + pos, ids.begin() + std::min(ids.size(), pos + (size_t)OB_MAX_HALO_TASKS));
+                OB_TRY(exchange_x_halos(part, false));
+            }
+            return OB_OK;
+        }
         XHaloBatch<T> B;
         B.count = 0; B.H = g.H[0]; B.N = g.N[0];
         size_t total = 0;
@@ -1476,6 +1494,70 @@ struct ModelT : ob_model {
 #include "diagnostics.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
+// fill_halo_regions! of ANY field array (not bound to a model): what the reference's
+// fill_halo_regions!(c::OffsetArray, bcs, indices, loc, grid) does for diagnostic / user fields
+// (src/BoundaryConditions/fill_halo_regions.jl:20-38).  Same kernel, same ordering as ModelT::fill_halos.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int32_t fill_halo_array_t(ob_ctx *ctx, const ob_grid_desc *gd, void *ptr, const int32_t *loc, const ob_bc_desc *bc, const void *const *bc_arrays,
+                                 int fill_normal) {
+    int N[3], H[3], topo[3], n[3], P[3];
+    for (int d = 0; d < 3; d++) {
+        N[d] = gd->N[d]; topo[d] = gd->topology[d];
+        H[d] = topo[d] == OB_FLAT ? 0 : gd->H[d];
+        n[d] = N[d] + ((loc[d] && topo[d] == OB_BOUNDED) ? 1 : 0);
+        P[d] = n[d] + 2 * H[d];
+    }
+    const T *dzf = (const T *)gd->dzf_host, *dzc = (const T *)gd->dzc_host;
+    if ((dzf == nullptr) != (dzc == nullptr)) return fail(OB_ERR_INVALID, "dzf given without dzc (or the reverse)");
+    for (int pass = 0; pass < 2; pass++)
+        for (int d = 2; d >= 0; d--) {
+            if (topo[d] == OB_FLAT) continue;
+            const bool per = topo[d] == OB_PERIODIC;
+            if ((pass == 0) == per) continue;
+            const int lo = bc->kind[2 * d], hi = bc->kind[2 * d + 1];
+            if (lo == OB_BC_NONE && hi == OB_BC_NONE) continue;
+            if (lo == OB_BC_COMMUNICATION || hi == OB_BC_COMMUNICATION)
+                return fail(OB_ERR_UNSUPPORTED, "communication halos are exchanged through a model (ob_fill_halo), not through ob_fill_halo_array");
+            if ((lo == OB_BC_PERIODIC) != per || (hi == OB_BC_PERIODIC) != per)
+                return fail(OB_ERR_INVALID, "boundary condition along %d does not match the topology", d);
+            HaloBatch<T> B;
+            B.count = 1; B.dir = d; B.N = N[d]; B.H = H[d]; B.fill_normal = fill_normal ? 1 : 0;
+            for (int k = 0; k < 3; k++) B.Hother[k] = H[k];
+            HaloTask<T> &t = B.t[0];
+            t.p = (T *)ptr;
+            for (int k = 0; k < 3; k++) { t.P[k] = P[k]; t.n[k] = n[k]; }
+            t.face = loc[d];
+            t.bc_lo = lo; t.bc_hi = hi;
+            t.v_lo = (T)bc->value[2 * d]; t.v_hi = (T)bc->value[2 * d + 1];
+            t.a_lo = bc_arrays ? (const T *)bc_arrays[2 * d] : nullptr;
+            t.a_hi = bc_arrays ? (const T *)bc_arrays[2 * d + 1] : nullptr;
+            auto sp = [&](int idx) -> T {   // Δ at flip(loc) at the boundary index (fill_halo_regions_value_gradient.jl:35-119)
+                if (d == 0) return (T)gd->d[0];
+                if (d == 1) return (T)gd->d[1];
+                if (!dzf) return (T)gd->d[2];
+                return loc[2] ? dzc[idx + H[2] - 1] : dzf[idx + H[2]];
+            };
+            t.d_lo = sp(1);
+            t.d_hi = sp(N[d] + 1);
+            const int da = d == 0 ? 1 : 0, db = d == 2 ? 1 : 2;
+            const long th = per ? (long)P[da] * P[db] : (long)n[da] * n[db];
+            dim3 grid(nblk(th, 256), 1);
+            halo_kernel<T><<<grid, 256, 0, ctx->stream>>>(B);
+        }
+    CUDA_TRY(cudaGetLastError());
+    return OB_OK;
+}
+extern "C" int32_t ob_fill_halo_array(ob_ctx *ctx, const ob_grid_desc *grid, void *device_ptr, const int32_t *loc, const ob_bc_desc *bcs,
+                                      const void *const *bc_arrays, int32_t fill_normal_flow_bcs) {
+    if (!ctx || !grid || !device_ptr || !loc || !bcs) return fail(OB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (grid->float_type == OB_F64) return fill_halo_array_t<double>(ctx, grid, device_ptr, loc, bcs, bc_arrays, fill_normal_flow_bcs);
+    if (grid->float_type == OB_F32) return fill_halo_array_t<float>(ctx, grid, device_ptr, loc, bcs, bc_arrays, fill_normal_flow_bcs);
+    return fail(OB_ERR_INVALID, "unknown float type %d", grid->float_type);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // C ABI: model
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int32_t ob_model_create(ob_ctx *ctx, const ob_model_desc *desc, ob_model **out) {
@@ -1525,8 +1607,17 @@ extern "C" int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t valu
     }
     return fail(OB_ERR_INVALID, "unknown option %d", option);
 }
-extern "C" int32_t ob_launch_count(ob_model *m, int64_t *n) { *n = m->launches; return OB_OK; }
-extern "C" int32_t ob_enable_timing(ob_model *m, int32_t e) { m->collect(); m->timing = e != 0; return OB_OK; }
+extern "C" int32_t ob_launch_count(ob_model *m, int64_t *n) {
+    if (!m || !n) return fail(OB_ERR_INVALID, "null model or output pointer");
+    *n = m->launches;
+    return OB_OK;
+}
+extern "C" int32_t ob_enable_timing(ob_model *m, int32_t e) {
+    if (!m) return fail(OB_ERR_INVALID, "null model");
+    m->collect();
+    m->timing = e != 0;
+    return OB_OK;
+}
 extern "C" int32_t ob_phase_count(int32_t *n) { *n = PH_COUNT; return OB_OK; }
 extern "C" const char *ob_phase_name(int32_t p) { return (p >= 0 && p < PH_COUNT) ? PHASE_NAMES[p] : ""; }
 extern "C" int32_t ob_phase_time_ms(ob_model *m, int32_t p, double *ms, int64_t *calls) {

@@ -168,6 +168,17 @@ class Field:
                 inter[...] = a.reshape(inter.shape)
         self.set_parent(full)
 
+    def fill_halo_regions(self, fill_normal_flow_bcs=True):
+        """fill_halo_regions!(field) for a field that is not (necessarily) bound to a model: ob_fill_halo_array.  Constant
+        Flux / Value / Gradient conditions only (array-valued conditions go through the model: ob_model_set_bc_array)."""
+        g = self.grid
+        if getattr(self.arch, "world", 1) > 1:
+            raise NotImplementedError("distributed halos are exchanged through the model (model.fill_halo_regions)")
+        desc = g.desc()   # (keeps the host spacing arrays alive for the duration of the call)
+        loc = (C.c_int32 * 3)(*[1 if c == "f" else 0 for c in self.loc])
+        bcs = bc_desc(self.boundary_conditions)
+        _abi.call("ob_fill_halo_array", self.arch.ctx, C.byref(desc), self.data, C.byref(loc), C.byref(bcs), None, int(bool(fill_normal_flow_bcs)))
+
     def any_nan(self):
         flag = C.c_int32(0)
         ft = _abi.OB_F64 if self.grid.FT == np.float64 else _abi.OB_F32

@@ -21,12 +21,31 @@ class IterationInterval:
 
 
 class TimeInterval:
+    """Utils/schedules.jl: fires at first_actuation_time + n * interval; the first actuation time is the clock time when the
+    simulation is initialised (so a writer fires at iteration 0, and after a restore at t > 0 it does not fire on every
+    iteration until it has caught up); next = first + (actuations + 1) * interval, without accumulated rounding."""
+
     def __init__(self, interval):
-        self.interval, self.next = float(interval), float(interval)
+        self.interval = float(interval)
+        self.first, self.actuations = None, 0
+
+    def initialize(self, model):
+        self.first = float(model.clock.time)
+        self.actuations = 0
+        return True   # initialize!(schedule, model) actuates at initialisation
+
+    def next_actuation_time(self):
+        first = 0.0 if self.first is None else self.first
+        return first + (self.actuations + 1) * self.interval
 
     def __call__(self, model):
-        if model.clock.time >= self.next - 1e-12 * max(1.0, abs(self.next)):
-            self.next += self.interval
+        if self.first is None:
+            return self.initialize(model)
+        t = self.next_actuation_time()
+        if model.clock.time >= t - 1e-12 * max(1.0, abs(t)):
+            # catch up if several intervals were skipped by one long step
+            while model.clock.time >= self.next_actuation_time() - 1e-12 * max(1.0, abs(t)):
+                self.actuations += 1
             return True
         return False
 
@@ -37,17 +56,24 @@ class Callback:
 
 
 class NaNChecker:
-    """Diagnostics/nan_checker.jl: `any(isnan, parent(field))` on the first prognostic field (u); stops the run."""
+    """Diagnostics/nan_checker.jl: `any(isnan, parent(field))` on the first prognostic field (u).  Default erroring=False,
+    as in the reference: the run is stopped (sim.running = False) and run! returns normally, so the final synchronize and the
+    remaining writers still happen; erroring=True raises."""
 
-    def __init__(self, fields):
-        self.fields = fields
+    def __init__(self, fields, erroring=False):
+        self.fields, self.erroring = fields, erroring
+        self.message = None
 
     def __call__(self, sim):
         for name, f in self.fields.items():
             if f.any_nan():
                 sim.running = False
-                raise FloatingPointError("time = %s, iteration = %d: NaN found in field %s. Aborting simulation."
-                                         % (sim.model.clock.time, sim.model.clock.iteration, name))
+                self.message = ("time = %s, iteration = %d: NaN found in field %s. Stopping simulation."
+                                % (sim.model.clock.time, sim.model.clock.iteration, name))
+                if self.erroring:
+                    raise FloatingPointError(self.message)
+                print("[NaNChecker] " + self.message)
+                return
 
 
 class TimeStepWizard:
@@ -100,10 +126,17 @@ class NPZOutputWriter:
         import numpy as np
         out = {n: (f.parent() if self.with_halos else np.ascontiguousarray(f.interior())) for n, f in self.fields.items()}
         out["time"], out["iteration"] = np.float64(model.clock.time), np.int64(model.clock.iteration)
-        path = "%s_iteration%d.npz" % (self.prefix, model.clock.iteration)
+        path = "%s%s_iteration%d.npz" % (self.prefix, _rank_suffix(model), model.clock.iteration)
         np.savez(path, **out)
         self.written.append(path)
         return path
+
+
+def _rank_suffix(model):
+    """"_rank{r}" under a distributed architecture: every rank writes its own x-slab (output_writer_utils.jl:266-267,
+    checkpointer.jl:42); empty on one device"""
+    arch = model.grid.architecture
+    return "_rank%d" % arch.rank if getattr(arch, "world", 1) > 1 else ""
 
 
 class Checkpointer:
@@ -114,7 +147,7 @@ class Checkpointer:
 
     def write(self, model):
         from .checkpoint import checkpoint
-        path = checkpoint(model, "%s_iteration%d.npz" % (self.prefix, model.clock.iteration))
+        path = checkpoint(model, "%s%s_iteration%d.npz" % (self.prefix, _rank_suffix(model), model.clock.iteration))
         self.written.append(path)
         return path
 
@@ -125,12 +158,19 @@ def conjure_time_step_wizard(sim, schedule=None, **kw):
 
 
 def _aligned_time_step(sim, dt):
-    """run.jl:40-58: do not step past stop_time"""
+    """run.jl:40-58: do not step past stop_time, nor past the next actuation of a TimeInterval callback / writer
+    (schedule_aligned_time_step)"""
     clk = sim.model.clock
     if math.isfinite(sim.stop_time):
         remaining = sim.stop_time - clk.time
         if remaining > 0:
             dt = min(dt, remaining)
+    for item in list(sim.callbacks.values()) + list(sim.output_writers.values()):
+        sch = getattr(item, "schedule", None)
+        if isinstance(sch, TimeInterval) and sch.first is not None:
+            remaining = sch.next_actuation_time() - clk.time
+            if remaining > 1e-12 * max(1.0, abs(clk.time)):
+                dt = min(dt, remaining)
     return dt
 
 

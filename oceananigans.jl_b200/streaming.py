@@ -24,6 +24,8 @@ class HostMember:
     def __init__(self, arch, fields):
         self.arch = arch
         self.nbytes = [f.nbytes for f in fields]
+        self.lane = None          # the device lane this member is bound to (set by its first step)
+        self.clock = None         # (time, iteration, last_dt, last_stage_dt) of this member, carried between steps
         self.ptrs = []
         for f in fields:
             p = C.c_void_p()
@@ -57,7 +59,7 @@ class HostStreamedStepper:
             self.archs.append(arch)
             self.models.append(model)
         self._next = 0
-        self._busy_out = [None] * lanes
+        self._holder = [None] * lanes   # the member whose state (and tendencies) each lane holds
 
     @property
     def lanes(self):
@@ -73,15 +75,36 @@ class HostStreamedStepper:
             _abi.call("ob_memcpy_d2h", arch.ctx, p, f.data, f.nbytes)
 
     def step(self, member_in, member_out, dt):
-        lane = self._next
-        self._next = (lane + 1) % self.lanes
+        """One step of `member_in`; the result lands in `member_out` (usually the same object).  A member is bound to the
+        lane of its first step, so its uploads and downloads are ordered on one stream.  When a lane receives a member
+        other than the one it held last (more members than lanes), the tendencies left on the lane belong to another
+        state: `update_state!` is re-run after the upload and the member's own clock is installed.  Adams-Bashforth
+        models are refused in that case: G⁻ is part of their state and is not carried in a HostMember."""
+        if member_in.lane is None:
+            member_in.lane = self._next
+            self._next = (self._next + 1) % self.lanes
+        lane = member_in.lane
+        if member_out.lane is None:
+            member_out.lane = lane
+        if member_out.lane != lane:
+            raise ValueError("member_out is bound to lane %d, member_in to lane %d: a member's copies must stay on one stream" % (member_out.lane, lane))
         arch, model = self.archs[lane], self.models[lane]
         fields = list(model.prognostic_fields.values())
         for f, p in zip(fields, member_in.ptrs):
             _abi.call("ob_memcpy_h2d", arch.ctx, f.data, p, f.nbytes)        # async, pinned source
+        clk = model.clock
+        if self._holder[lane] is not member_in:
+            if member_in.clock is not None:
+                clk.time, clk.iteration, clk.last_dt, clk.last_stage_dt = member_in.clock
+            if clk.iteration != 0:   # (at iteration 0 the step itself starts with update_state!)
+                if model.timestepper != "RungeKutta3":
+                    raise NotImplementedError("sharing a lane between members needs G⁻ in the host state (QuasiAdamsBashforth2)")
+                model.update_state()   # Gⁿ of THIS member, not of the member the lane held before
         time_step(model, dt)                                                  # ONE C-ABI call, async on the lane's stream
+        member_out.clock = (clk.time, clk.iteration, clk.last_dt, clk.last_stage_dt)
         for f, p in zip(fields, member_out.ptrs):
             _abi.call("ob_memcpy_d2h_async", arch.ctx, p, f.data, f.nbytes)  # stream-ordered, pinned destination
+        self._holder[lane] = member_out
         return lane
 
     def join_into(self, lane=0):

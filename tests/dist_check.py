@@ -19,6 +19,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 arch = ob.Distributed(ob.B200(local))
 TWO_PI = 2 * np.pi
+# every size divides by 8 in y and z (the distributed solvers transpose x <-> z or y <-> x over up to 8 ranks)
 CASES = {
     "ppp_weno5": (Config((32, 24, 16), ((0, TWO_PI),) * 3, "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
                          buoyancy=("tracer",), tracers=("b",)), 1e-3),
@@ -26,17 +27,17 @@ CASES = {
     # tiles, waits + unpacks, then computes the edge tiles (OB_OPT_OVERLAP_HALO)
     "wide_overlap_ppp": (Config((256, 12, 10), ((0, 8.0), (0, 1.0), (0, 1.0)), "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
                                 buoyancy=("tracer",), tracers=("b",)), 1e-3),
-    "wide_overlap_ppb": (Config((192, 10, 12), ((0, 6.0), (0, 1.0), (-1.2, 0.0)), "PPB", advection=("weno", 5), closure=[("scalar", 1e-3, 2e-3)],
+    "wide_overlap_ppb": (Config((192, 16, 16), ((0, 6.0), (0, 1.6), (-1.6, 0.0)), "PPB", advection=("weno", 5), closure=[("scalar", 1e-3, 2e-3)],
                                 buoyancy=("tracer",), coriolis_f=0.5, tracers=("b", "c"),
                                 bcs={"u": {"top": ("Flux", -2e-3)}, "b": {"top": ("Flux", 5e-4)}}), 1e-3),
     # vertically-implicit diffusion: the column solves are rank-local
-    "vi_scalar_ppb": (Config((32, 12, 10), ((0, 3.2), (0, 1.2), (-1.0, 0.0)), "PPB", advection=("weno", 5), closure=[("vi_scalar", 2e-2, 1e-2)],
+    "vi_scalar_ppb": (Config((32, 16, 16), ((0, 3.2), (0, 1.6), (-1.6, 0.0)), "PPB", advection=("weno", 5), closure=[("vi_scalar", 2e-2, 1e-2)],
                              buoyancy=("tracer",), tracers=("b",), bcs={"b": {"top": ("Flux", 2e-4)}}), 0.05),
-    "les_amd_dct": (Config((32, 16, 12), ((0, 32.0), (0, 16.0), (-12.0, 0.0)), "PPB", advection=("weno", 5),
+    "les_amd_dct": (Config((64, 16, 16), ((0, 64.0), (0, 16.0), (-16.0, 0.0)), "PPB", advection=("weno", 5),
                            closure=[("amd",), ("scalar", 1.05e-6, 1.46e-7)], buoyancy=("seawater", 9.80665, 2e-4, 8e-4),
                            coriolis_f=1e-4, tracers=("T", "S"),
                            bcs={"u": {"top": ("Flux", -2e-5)}, "T": {"top": ("Flux", 5e-5), "bottom": ("Gradient", 0.005)}}), 0.5),
-    "stretched_tridiag": (Config((32, 16, 12), ((0, 32.0), (0, 16.0), stretched_faces(12, 12.0)), "PPB", advection=("weno", 5),
+    "stretched_tridiag": (Config((32, 16, 16), ((0, 32.0), (0, 16.0), stretched_faces(16, 16.0)), "PPB", advection=("weno", 5),
                                  closure=[("amd",)], buoyancy=("seawater", 9.80665, 2e-4, 8e-4), tracers=("T", "S")), 0.5),
 }
 ok = True
@@ -104,7 +105,7 @@ for name, (cfg, dt) in CASES.items():
 for name, cfg in {"fft_ppp": Config((32, 16, 24), ((0, 1.0), (0, 2.0), (0, 3.0)), "PPP"),
                   "fft_ppb": Config((32, 16, 24), ((0, 1.0), (0, 2.0), (0, 3.0)), "PPB"),
                   "fft_ppp_odd_levels": Config((32, 16, 18), ((0, 1.0), (0, 2.0), (0, 3.0)), "PPP"),
-                  "tridiagonal": Config((32, 16, 12), ((0, 1.0), (0, 2.0), stretched_faces(12, 3.0)), "PPB")}.items():
+                  "tridiagonal": Config((32, 16, 16), ((0, 1.0), (0, 2.0), stretched_faces(16, 3.0)), "PPB")}.items():
     dg, sg = cfg.b200_grid(arch), cfg.b200_grid(ob.B200(local))
     cls = ob.FourierTridiagonalPoissonSolver if name == "tridiagonal" else ob.FFTBasedPoissonSolver
     ds, ss = cls(dg), cls(sg)

@@ -132,6 +132,10 @@ def test_halo_fill_bit_exact(arch, case, ft):
             bm.fill_halo_regions(name, fill_normal_flow_bcs=fill_normal)
             got = bf.parent()
             assert np.array_equal(got.view(np.uint8), of.data.view(np.uint8)), (name, fill_normal)
+            # the model-free entry point (ob_fill_halo_array: any Field, as the reference's fill_halo_regions!) is the same fill
+            bf.set_parent(parent)
+            bf.fill_halo_regions(fill_normal_flow_bcs=fill_normal)
+            assert np.array_equal(bf.parent().view(np.uint8), of.data.view(np.uint8)), (name, fill_normal, "ob_fill_halo_array")
 
 
 def test_advection_timescale_and_nan_checker(arch):
@@ -230,6 +234,42 @@ def test_host_streamed_stepper_matches_resident_stepping(arch):
         for p, nb, r, f in zip(mem.ptrs, mem.nbytes, ref, model.prognostic_fields.values()):
             got = np.frombuffer((C.c_char * nb).from_address(p.value), dtype=r.dtype).reshape(r.shape)
             assert np.array_equal(got, r), f.name
+        mem.free()
+
+
+def test_host_streamed_stepper_with_more_members_than_lanes(arch):
+    """four members through TWO lanes: a lane then receives a member other than the one it held last, whose tendencies and
+    clock must not leak into it (update_state! is re-run after the upload; the member's own clock is installed)"""
+    import ctypes as C
+    import ocean_b200 as ob
+    cfg = Config((24, 20, 16), ((0, 2 * np.pi),) * 3, "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)],
+                 buoyancy=("tracer",), tracers=("b",))
+    ics = [cfg.initial_conditions(seed) for seed in (1, 2, 3, 4)]
+    want = []
+    for ic in ics:
+        m = cfg.b200_model(arch)
+        ob.set(m, **ic)
+        for _ in range(3):
+            ob.time_step(m, 1e-3)
+        want.append([f.parent() for f in m.prognostic_fields.values()])
+        del m
+    stepper = ob.HostStreamedStepper(lambda a: cfg.b200_model(a), lanes=2, device=arch.device)
+    members = []
+    for n, ic in enumerate(ics):
+        ob.set(stepper.models[n % 2], **ic)
+        mem = stepper.new_member()
+        stepper.download(mem, n % 2)
+        mem.clock = (0.0, 0, 0.0, 0.0)
+        members.append(mem)
+    for s in range(12):
+        mem = members[s % 4]
+        assert stepper.step(mem, mem, 1e-3) == (s % 4) % 2   # a member stays on the lane of its first step
+    stepper.synchronize()
+    for mem, ref in zip(members, want):
+        assert mem.clock[1] == 3
+        for p, nb, r in zip(mem.ptrs, mem.nbytes, ref):
+            got = np.frombuffer((C.c_char * nb).from_address(p.value), dtype=r.dtype).reshape(r.shape)
+            assert np.array_equal(got, r)
         mem.free()
 
 

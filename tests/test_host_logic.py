@@ -111,3 +111,41 @@ def test_schedules_and_wizard_arithmetic():
     assert w.new_time_step(1.0, _Model()) == pytest.approx(1.1)           # limited by max_change (wizard.jl)
     assert w.new_time_step(10.0, _Model()) == pytest.approx(5.0)          # limited by min_change
     assert ob.TimeStepWizard(cfl=0.5, max_dt=1.5).new_time_step(1.4, _Model()) == pytest.approx(1.5)
+
+
+def test_time_interval_schedule_follows_the_reference():
+    """Utils/schedules.jl: the first actuation time is the clock time at initialisation (fires there), later actuations are at
+    first + n * interval without accumulated rounding; aligned_time_step clips dt to the next actuation (run.jl:43-55)"""
+    import ocean_b200 as ob
+    from ocean_b200 import simulations as S
+
+    class _Clock:
+        iteration, time = 0, 0.0
+
+    class _M:
+        clock = _Clock()
+    m = _M()
+    s = ob.TimeInterval(0.3)
+    fired = []
+    for it in range(12):
+        m.clock.time = 0.1 * it
+        if s(m):
+            fired.append(it)
+    assert fired == [0, 3, 6, 9]
+    # restored at t > 0: fires at initialisation, then only every interval (not on every iteration until caught up)
+    m.clock.time = 5.0
+    s2 = ob.TimeInterval(1.0)
+    assert s2(m)
+    m.clock.time = 5.1
+    assert not s2(m)
+    m.clock.time = 6.0
+    assert s2(m)
+    assert s2.next_actuation_time() == pytest.approx(7.0)
+
+    class _Sim:
+        stop_time = float("inf")
+        model = m
+        callbacks = {}
+        output_writers = {"w": type("W", (), {"schedule": s2})()}
+    m.clock.time = 6.75
+    assert S._aligned_time_step(_Sim(), 1.0) == pytest.approx(0.25)
