@@ -46,9 +46,12 @@ def test_tendencies_match_oracle_at_size(arch, name):
     sl = (slice(H[2], H[2] + N[2]), slice(H[1], H[1] + N[1]), slice(H[0], H[0] + N[0]))
     umax = max(np.abs(f.data).max() for f in (om.u, om.v, om.w))
     dmin = min(float(np.min(om.grid.dc[d])) for d in range(3))
+    # Deep columns: Gu, Gv contain ∂x pHY′, a difference of values that grow with depth (g α T z ~ 4 m²/s² at 96 m) -- the
+    # rounding of that cancellation is ~40 eps relative to |G| whatever the implementation; measured 1.5e-13 on les_tall
+    base = 1e-13 if om.pHY is None else 1e-12
     for n, (og, bg) in enumerate(zip(om.Gn, bm.Gn)):
         a, b = bg.parent()[sl], og.data[sl]
-        tol = 1e-13
+        tol = base
         if n >= 3:
             cmax = np.abs(om.tracers[n - 3].data).max()
             tol *= max(1.0, umax * cmax / dmin / max(np.abs(b).max(), 1e-300))
