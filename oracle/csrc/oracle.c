@@ -30,7 +30,16 @@
 #ifndef FT
 #define FT double
 #endif
-#ifdef ORACLE_F32
+#ifdef ORACLE_F80
+/* extended precision (x87 long double): same formulas, used only to measure the rounding error of the Float64 evaluation */
+#define SUF(n) n##_f80
+#define FMA(a, b, c) fmal((a), (b), (c))
+#define FABS(a) fabsl(a)
+#define SQRT(a) sqrtl(a)
+#define CBRT(a) cbrtl(a)
+#define FMAX(a, b) fmaxl((a), (b))
+#define FMIN(a, b) fminl((a), (b))
+#elif defined(ORACLE_F32)
 #define SUF(n) n##_f32
 #define FMA(a, b, c) fmaf((a), (b), (c))
 #define FABS(a) fabsf(a)
@@ -894,7 +903,7 @@ void SUF(orc_amd_diffusivity)(const oparams *g, int m, int t) {
 
 /* thread control for bench.py's CPU arm: torchrun exports OMP_NUM_THREADS=1, so the count is set explicitly and the number
  * actually in effect is what gets reported */
-#ifndef ORACLE_F32
+#if !defined(ORACLE_F32) && !defined(ORACLE_F80)
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);

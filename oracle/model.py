@@ -47,7 +47,7 @@ def set_num_threads(n):
 
 
 def _mkstructs(ft):
-    cft = C.c_double if ft == np.float64 else C.c_float
+    cft = C.c_double if ft == np.float64 else C.c_longdouble if ft == np.longdouble else C.c_float
     P = C.POINTER(cft)
 
     class OField(C.Structure):
@@ -96,6 +96,12 @@ class Grid:
 
     def __init__(self, size, extent, topology=("P", "P", "B"), halo=(3, 3, 3), ft=np.float64):
         self.ft = np.dtype(ft).type
+        # Extended precision (np.longdouble, x87 80-bit): the SAME discrete problem as Float64 -- every parameter (spacings,
+        # coefficients, constants) is the Float64 value, only the arithmetic is carried with 64 significand bits.  Used by
+        # tests/test_oracle_extended.py to measure how far the Float64 oracle and the GPU are from the exactly-rounded answer.
+        self.extended = self.ft == np.longdouble
+        if self.extended:
+            self.ft = np.float64
         self.topo = tuple(TOPO[t] for t in topology)
         self.N = tuple(int(n) for n in size)
         self.H = tuple(0 if self.topo[d] == FLAT else int(halo[d]) for d in range(3))
@@ -106,6 +112,11 @@ class Grid:
         self.regular = []
         for d in range(3):
             self._generate(d, extent[d])
+        if self.extended:
+            self.ft = np.longdouble
+            for name in ("df", "dc", "faces", "centers"):
+                setattr(self, name, [a.astype(np.longdouble) for a in getattr(self, name)])
+            self.L = [np.longdouble(x) for x in self.L]
 
     def _generate(self, d, ext):
         ft, N, H, topo = self.ft, self.N[d], self.H[d], self.topo[d]
@@ -308,6 +319,10 @@ def _fill_side_pair(f, d, bc_lo, bc_hi, fill_normal_flow_bcs):
 # ---------------------------------------------------------------------------------------------
 # Poisson solvers
 # ---------------------------------------------------------------------------------------------
+def _complex_of(ft):
+    return np.complex128 if ft == np.float64 else np.clongdouble if ft == np.longdouble else np.complex64
+
+
 def poisson_eigenvalues(grid, d):
     """poisson_eigenvalues.jl:8-32"""
     N, L, t = grid.N[d], np.float64(grid.L[d]), grid.topo[d]
@@ -329,7 +344,7 @@ class FFTPoissonSolver:
     def __init__(self, grid):
         self.grid = grid
         self.lam = [poisson_eigenvalues(grid, d) for d in range(3)]
-        self.cft = np.complex128 if grid.ft == np.float64 else np.complex64
+        self.cft = _complex_of(grid.ft)
 
     def solve(self, rhs):
         g = self.grid
@@ -363,7 +378,7 @@ class FourierTridiagonalPoissonSolver:
         g = self.grid = grid
         assert g.topo[2] == BOUNDED
         ft = g.ft
-        self.cft = np.complex128 if ft == np.float64 else np.complex64
+        self.cft = _complex_of(ft)
         Nx, Ny, Nz = g.N
         lx, ly = poisson_eigenvalues(g, 0), poisson_eigenvalues(g, 1)
         lam = (lx[None, :] + ly[:, None]).astype(ft)  # (Ny, Nx)
@@ -488,7 +503,9 @@ class Model:
         self.time = 0.0
         self.iteration = 0
         self.last_dt = np.inf
-        self._tables = (coef.weno_coeff_table(ft), coef.smoothness_table(ft), coef.cstar_table(ft), coef.centered_coeff_table(ft))
+        tft = np.float64 if ft == np.longdouble else ft   # extended precision keeps the Float64 coefficient VALUES
+        self._tables = tuple(t.astype(ft) for t in (coef.weno_coeff_table(tft), coef.smoothness_table(tft), coef.cstar_table(tft),
+                                                    coef.centered_coeff_table(tft)))
         self.update_state()
 
     # -- helpers ------------------------------------------------------------------------------
@@ -516,7 +533,7 @@ class Model:
         wc, wb, cs, cc = self._tables
         p.weno_coeff = wc.ctypes.data_as(P); p.weno_beta = wb.ctypes.data_as(P)
         p.weno_cstar = cs.ctypes.data_as(P); p.cen_coeff = cc.ctypes.data_as(P)
-        p.weno_eps = coef.weno_eps(ft)
+        p.weno_eps = ft(coef.weno_eps(np.float64 if ft == np.longdouble else ft))
         p.nclosures = len(self.closures)
         nt = len(self.tracers)
         for m, c in enumerate(self.closures):
@@ -563,7 +580,7 @@ class Model:
         return p
 
     def _fn(self, name):
-        return getattr(lib(), name + ("_f64" if self.grid.ft == np.float64 else "_f32"))
+        return getattr(lib(), name + ("_f64" if self.grid.ft == np.float64 else "_f80" if self.grid.ft == np.longdouble else "_f32"))
 
     # -- update_state! (update_nonhydrostatic_model_state.jl:22-83) -----------------------------
     def update_state(self):

@@ -286,8 +286,33 @@ def test_one_step_f32(arch, name):
     dt = 1e-3 if name in ("ppp_weno5", "readme_2d") else 0.05 if name.startswith("vi_") else 0.5
     om.time_step(dt)
     ob.time_step(bm, dt)
-    # pNHS in Float32 is a near-cancelling quantity (∇·u* of a projected field); hold it to a looser bound
+    # contract: 1e-5 on u, v, w and the tracers.  pNHS in Float32 is a near-cancelling quantity (the solve of ∇·u* / Δτ of an
+    # almost divergence-free field): stated bound 5e-2 of its own norm -- measured 1e-4 .. 2e-2 across the configurations
     _compare(om, bm, 1e-5, what=("u", "v", "w"))
+    _compare(om, bm, 5e-2, what=("pNHS",))
+
+
+@pytest.mark.parametrize("name", sorted(P_ILL_CONDITIONED))
+def test_pressure_error_is_the_float64_rounding_error(arch, name):
+    """pNHS of these configurations is held to 10-100x the contract tolerance.  Why that is the attainable accuracy: the same
+    step evaluated in x87 extended precision (tests/test_oracle_extended.py) is the exactly-rounded answer; the Float64 ORACLE
+    is ~1e-10 away from it, and the GPU result must be no further from it than three times that (both are Float64
+    evaluations of the same formulas with different association / FMA contraction / FFT libraries)"""
+    import ocean_b200 as ob
+    from test_oracle_extended import run_oracle
+    cfg = CONFIGS[name]
+    dt = 0.5 if name in ("les_amd", "stretched", "amd_cb", "stage_les") else 1e-3
+    p64 = run_oracle(name, np.float64, dt)["pNHS"]
+    p80 = run_oracle(name, np.longdouble, dt)["pNHS"].astype(np.float64)
+    bm = cfg.b200_model(arch)
+    ob.set(bm, **cfg.initial_conditions(3))
+    ob.time_step(bm, dt)
+    pg = bm.pressures["pNHS"].parent()
+    H, N = bm.grid.H, bm.grid.N
+    sl = (slice(H[2], H[2] + N[2]), slice(H[1], H[1] + N[1]), slice(H[0], H[0] + N[0]))
+    e_orc, e_gpu = rel_l2(p64[sl], p80[sl]), rel_l2(pg[sl], p80[sl])
+    print(name, "oracle vs extended %.2e, GPU vs extended %.2e, GPU vs oracle %.2e" % (e_orc, e_gpu, rel_l2(pg[sl], p64[sl])))
+    assert e_gpu <= 3 * e_orc + 1e-11, (name, e_gpu, e_orc)
 
 
 def test_closure_fields_match_oracle(arch):

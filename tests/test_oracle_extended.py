@@ -1,0 +1,40 @@
+"""CPU-only: how accurate is the Float64 oracle itself?  The same discrete problem (identical Float64 parameters, coefficients
+and initial data) evaluated with x87 extended precision (oracle compiled with FT = long double, numpy/scipy long-double FFTs)
+is the exactly-rounded answer to ~1e-19.  The Float64 evaluation differs from it by the rounding error that ANY Float64
+implementation of the reference's formulas carries -- the reference included.
+
+Result: u, v, w, tracers carry ~1e-13 after one step; pNHS of the ocean-LES configurations carries ~1e-10, i.e. MORE than the
+1e-11 contract tolerance.  This is what justifies the relaxed pNHS bound of tests/test_gpu_parity.py (P_ILL_CONDITIONED), and
+tests/test_gpu_parity.py::test_pressure_error_is_the_float64_rounding_error shows the GPU is as close to the extended result as
+the oracle is."""
+import numpy as np
+import pytest
+
+from helpers import Config, oracle_fields, rel_l2
+from test_gpu_parity import CONFIGS
+
+
+def run_oracle(name, ft, dt, seed=3):
+    d = dict(CONFIGS[name].__dict__)
+    ic = Config(**d).initial_conditions(seed)          # Float64 initial data for both precisions
+    d["ft"] = ft
+    om = Config(**d).oracle_model()
+    om.set(**{k: v.astype(ft) for k, v in ic.items()})
+    om.time_step(dt)
+    return {k: np.asarray(v) for k, v in oracle_fields(om).items()}
+
+
+@pytest.mark.parametrize("name,dt", [("les_amd", 0.5), ("stretched", 0.5)])
+def test_float64_pressure_of_the_les_configs_carries_more_than_the_contract_tolerance(name, dt):
+    a, b = run_oracle(name, np.float64, dt), run_oracle(name, np.longdouble, dt)
+    errs = {k: float(rel_l2(a[k], b[k].astype(np.float64))) for k in a}
+    assert 1e-11 < errs["pNHS"] < 1e-9, errs
+    for k in errs:
+        if k != "pNHS":
+            assert errs[k] < 1e-12, errs
+
+
+def test_float64_rounding_of_the_headline_config_is_far_inside_the_tolerance():
+    a, b = run_oracle("ppp_weno5", np.float64, 1e-3), run_oracle("ppp_weno5", np.longdouble, 1e-3)
+    errs = {k: float(rel_l2(a[k], b[k].astype(np.float64))) for k in a}
+    assert all(e < 1e-13 for e in errs.values()), errs
