@@ -22,10 +22,10 @@ INSTANCES += [(t, tn, 1, nb) for t, tn in (("double", "f64"), ("float", "f32")) 
 INSTANCES += [(t, tn, 2, nb) for t, tn in (("double", "f64"), ("float", "f32")) for nb in (2, 3, 4, 5)]
 
 
-# tendency_stage.cuh is only instantiated for the schemes StageSel marks as built (every TU includes it, but the others
-# never instantiate its templates): a change there rebuilds those instances only
+# the staged-ring tendency kernels have their own translation units (csrc/stage_inst.cu): (buffer, mode, closures, LES kind)
+# -- the list of csrc/stage_launch.h; a change to tendency_stage.cuh rebuilds only those
 STAGE_HEADERS = ("tendency_stage.cuh",)
-STAGE_INSTANCES = {(2, 3)}
+STAGE_VARIANTS = [(3, 0, 0, 0), (3, 0, 1, 0), (3, 1, 1, 2), (3, 1, 1, 3), (3, 1, 2, 2), (3, 1, 2, 3), (3, 2, 1, 2), (3, 2, 1, 3), (3, 2, 2, 2), (3, 2, 2, 3)]
 
 
 def _headers(stage=True):
@@ -63,9 +63,17 @@ def build(force=False, verbose=False, jobs=None):
     for t, tn, kind, nb in INSTANCES:
         o = os.path.join(OBJ, "tend_%s_k%d_n%d.o" % (tn, kind, nb))
         objs.append(o)
-        if force or _stale(o, [inst] + (hdrs_stage if (kind, nb) in STAGE_INSTANCES else hdrs)):
+        if force or _stale(o, [inst] + hdrs):
             jobs_list.append([NVCC, *FLAGS, "-DOB_TI_T=%s" % t, "-DOB_TI_TN=%s" % tn, "-DOB_TI_KIND=%d" % kind,
                               "-DOB_TI_NB=%d" % nb, "-c", inst, "-o", o])
+    sinst = os.path.join(CSRC, "stage_inst.cu")
+    for t, tn in (("double", "f64"), ("float", "f32")):
+        for n, mode, ncl, kl in STAGE_VARIANTS:
+            o = os.path.join(OBJ, "stage_%s_n%d_m%d_c%d_k%d.o" % (tn, n, mode, ncl, kl))
+            objs.append(o)
+            if force or _stale(o, [sinst] + hdrs_stage):
+                jobs_list.append([NVCC, *FLAGS, "-DOB_SI_T=%s" % t, "-DOB_SI_TN=%s" % tn, "-DOB_SI_N=%d" % n, "-DOB_SI_MODE=%d" % mode,
+                                  "-DOB_SI_NCL=%d" % ncl, "-DOB_SI_KL=%d" % kl, "-c", sinst, "-o", o])
     if jobs_list:
         with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
             for out in ex.map(_run, jobs_list):

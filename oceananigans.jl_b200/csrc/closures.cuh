@@ -70,8 +70,11 @@ template <typename T>
 __device__ __forceinline__ T interp4(const T (&f)[2][2]) {  // ℑ_outer(ℑ_inner f), f[inner][outer]
     return T(0.5) * (T(0.5) * (f[0][0] + f[1][0]) + T(0.5) * (f[0][1] + f[1][1]));
 }
+#ifndef OB_AMD_MINB
+#define OB_AMD_MINB 4   // resident CTAs per SM the register budget is set for (tuning knob; see profiles/r2_les_kernels.txt)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(128) amd_kernel(const __grid_constant__ TendP<T> P, int m) {
+__global__ void __launch_bounds__(128, OB_AMD_MINB) amd_kernel(const __grid_constant__ TendP<T> P, int m) {
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const GridD<T> &g = P.g;

@@ -65,19 +65,28 @@ struct StageCfg {
     static constexpr bool FITS = SMEM_BYTES <= 227 * 1024;
 };
 
-// which (float type, scheme) combinations have a staged-ring kernel, and its tile height (= compute warps) per closure count
-template <typename T, class S>
-struct StageSel {
-    static constexpr bool built = S::kind == ADV_WENO && S::n == 3;
-    static constexpr int W01 = 16;   // no closure / one closure
-    static constexpr int W2 = 12;    // two closures: the published fluxes need a third component
-};
+// tile height (= compute warps): 16 rows; 12 when two closures add a third published flux component
+constexpr int stage_rows(int ncl) { return ncl >= 2 ? 12 : 16; }
+
+// What the four staged fields and the (up to) four tendencies of a CTA are:
+//   MT  momentum + one tracer per pass: slots (u, v, w, c_t); tendencies Gu, Gv, Gw (pass 0 only), Gc_t.  Every closure is a
+//       ScalarDiffusivity (constants, no closure fields).
+//   MN  momentum of an LES model: slots (u, v, w, nu_e); tendencies Gu, Gv, Gw.  Closure 0 is the eddy-viscosity closure
+//       (Smagorinsky or AMD) whose nu_e is staged like a velocity component; closure 1, if any, is a ScalarDiffusivity.
+//   TT  two tracers of an LES model per pass: slots (c_A, kappa_A, c_B, kappa_B); tendencies Gc_A, Gc_B.  kappa is the AMD
+//       kappa_e of the tracer, or nu_e for Smagorinsky (divided by Pr at the face); the advecting velocities are single
+//       own-point values and come straight from global memory (three coalesced loads per cell and level).
+enum { STAGE_MT = 0, STAGE_MN = 1, STAGE_TT = 2 };
 
 struct StageLaunch {
     int ntx, nty, nkc;      // tiles in x, y and k-chunks
     int kbeg, kend, klen;   // levels kbeg .. kend in chunks of klen
-    int use_tma;            // 0: the producer warp copies with cp.async (row pitch not 16-byte aligned)
-    int npass;              // 1 + extra tracers
+    int use_tma;            // 0: the helper warps copy with cp.async (row pitch not 16-byte aligned)
+    int npass;              // gridDim.y
+};
+#define OB_STAGE_MAXPASS 8
+struct StageMaps {
+    CUtensorMap m[OB_STAGE_MAXPASS][4];   // tensor map of slot s in pass p
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
@@ -102,39 +111,43 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *b) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 
-// The levels k .. k+N of the ring as seen from one point of the tile: pl[d] points at field 0 of level k+d, already
-// offset to that point; field f is PL elements further, a row TW elements.
+// The levels k .. k+N of the ring as seen from one point of the tile: pl[d] points at slot 0 of level k+d, already
+// offset to that point; slot f is PL elements further, a row TW elements.
 template <typename T, int N, int TW, int PL>
 struct StageView {
     const T *pl[N + 1];
     __device__ __forceinline__ T at(int f, int d, int dx, int dy) const { return pl[d][f * PL + dy * TW + dx]; }
 };
 
-// own-column value of field f at level k+dl, dl in [-(N-1), N]: below k from the register history (h[m] = level k-(N-1)+m)
+// own-column value of slot f at level k+dl, dl in [-(N-1), N]: below k from the register history (h[m] = level k-(N-1)+m)
 template <typename T, int N, int TW, int PL>
 __device__ __forceinline__ T zval(const StageView<T, N, TW, PL> &V, const T (&h)[N - 1], int f, int dl) {
     if (dl < 0) return h[N - 1 + dl];
     return V.at(f, dl, 0, 0);
 }
 
-// Advective flux of tendency WHICH through the face owned in direction ADV (0: west, 1: south, 2: upper face k+1), from
-// the staged planes; the operands and their order are those of fast_flux (tendency_fast.cuh).
-// hq: history of the advected field; ha: history of the advecting component whose z-line is needed (u for ADV 0, v for 1, w for 2)
-template <typename T, int N, int WHICH, int ADV, bool STR, int TW, int PL>
-__device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const T (&hq)[N - 1], const T (&ha)[N - 1], const FastGeom<T, STR> &g, int k) {
+// Advective flux of a tendency of kind WHICH (0 u, 1 v, 2 w, 3 tracer) through the face owned in direction ADV (0: west,
+// 1: south, 2: upper face k+1), from the staged planes; the operands and their order are those of fast_flux
+// (tendency_fast.cuh).  QS: slot of the advected field.  hq: its history; ha: history of the advecting component whose
+// z-line is needed (u for ADV 0, v for 1, w for 2).  GV: the advecting velocity of a tracer flux is passed in `vel`
+// (tracer-only passes read it from global memory) instead of being taken from slot ADV.
+template <typename T, int N, int WHICH, int ADV, bool STR, int TW, int PL, int QS = WHICH, bool GV = false>
+__device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const T (&hq)[N - 1], const T (&ha)[N - 1], const FastGeom<T, STR> &g, int k,
+                                        T vel = T(0)) {
     constexpr int NC = N - 1;
-    constexpr int QF = WHICH;    // field index of the advected quantity (3 = the tracer of the pass)
-    constexpr int AF = ADV;      // field index of the advecting component
+    constexpr int AF = ADV;      // slot of the advecting component
     constexpr int LV = ADV == 2 ? 1 : 0;   // the upper face belongs to level k+1
     T s[2 * N];
 #pragma unroll
     for (int m = 0; m < 2 * N; m++) {
-        if constexpr (ADV == 0) s[m] = V.at(QF, 0, m - N, 0);
-        else if constexpr (ADV == 1) s[m] = V.at(QF, 0, 0, m - N);
-        else s[m] = zval<T, N, TW, PL>(V, hq, QF, 1 - N + m);
+        if constexpr (ADV == 0) s[m] = V.at(QS, 0, m - N, 0);
+        else if constexpr (ADV == 1) s[m] = V.at(QS, 0, 0, m - N);
+        else s[m] = zval<T, N, TW, PL>(V, hq, QS, 1 - N + m);
     }
     if constexpr (WHICH == 3) {
-        T a[1] = {V.at(AF, LV, 0, 0)};
+        T a[1];
+        if constexpr (GV) a[0] = vel;
+        else a[0] = V.at(AF, LV, 0, 0);
         return flux_from_values<T, N, true, WHICH, ADV, STR, OB_STAGE_LIT>(s, a, g, k + LV);
     } else {
         T a[2 * NC];
@@ -148,108 +161,104 @@ __device__ __forceinline__ T stage_flux(const StageView<T, N, TW, PL> &V, const 
     }
 }
 
-// Non-advective terms from the staged planes: FastTerms (tendency_fast.cuh) with the velocity / tracer loads redirected to
-// shared memory (level offset -1: register history of the own column; 0, +1: ring).  Closure fields (nu_e, kappa_e) and
-// pHY' stay on the global path: each is read at most a few times per cell.  LES = false: every closure is a
-// ScalarDiffusivity (no closure fields), which removes the global path from the code altogether.
-template <typename T, int N, bool LES, bool STR, int TW, int PL>
+// Non-advective terms from the staged planes: FastTerms (tendency_fast.cuh) with every load redirected to shared memory
+// (level offset -1: register history of the own column; 0, +1: ring).  MODE / NCL / KL fix at compile time which closures
+// exist and where their fields are, so no closure-kind branch and no global closure-field load is left in the code:
+//   closure 0 of an LES mode (KL = CL_SMAG or CL_AMD): nu_e in slot 3 (MN), kappa in slot CS+1 (TT); every other closure:
+//   ScalarDiffusivity constants.  pHY' and a non-staged buoyancy tracer stay on the global path.
+template <typename T, int N, int MODE, int NCL, int KL, bool STR, int TW, int PL>
 struct StageTerms {
     const TendP<T> &P;
     const FastGeom<T, STR> &G;
     const StageView<T, N, TW, PL> &V;
-    const T (&hu)[N - 1], (&hv)[N - 1], (&hw)[N - 1], (&hc)[N - 1];
-    int eo;   // global element offset of the (clamped) point at level k
+    const T (&h0)[N - 1], (&h1)[N - 1], (&h2)[N - 1], (&h3)[N - 1];   // own-column histories of the four slots
+    int eo;       // global element offset of the (clamped) point at level k
     int k;
-    int tstage;   // tracer index staged as field 3
-    __device__ __forceinline__ T fld(int f, int a, int b, int c) const {
-        if (c < 0) return f == 0 ? hu[N - 2] : f == 1 ? hv[N - 2] : f == 2 ? hw[N - 2] : hc[N - 2];
+    int tr;       // tracer index of the tracer tendency (MT: the pass's tracer; TT: set per tracer)
+    int cs;       // TT: slot of that tracer (its kappa is in slot cs + 1)
+    T ixp, iyp;   // MN: If1x / If1y of nu_e at this point one level below (carried in registers)
+    static constexpr bool LES0 = MODE != STAGE_MT;
+    __device__ __forceinline__ T slot(int f, int a, int b, int c) const {
+        if (c < 0) return f == 0 ? h0[N - 2] : f == 1 ? h1[N - 2] : f == 2 ? h2[N - 2] : h3[N - 2];
         return V.at(f, c, a, b);
     }
     __device__ __forceinline__ T ldg(const T *p, int a, int b, int c) const { return __ldg(p + (a + b * G.sy + c * G.sz)); }
     __device__ __forceinline__ const T *at(const Fld<T> &f) const { return f.p + f.off + eo; }
     __device__ __forceinline__ T dzC(int c) const { return G.dzC(k + c); }
     __device__ __forceinline__ T dzF(int c) const { return G.dzF(k + c); }
-    __device__ __forceinline__ T dx_u(int a, int b, int c) const { return (fld(0, a + 1, b, c) - fld(0, a, b, c)) * G.rdx; }
-    __device__ __forceinline__ T dy_v(int a, int b, int c) const { return (fld(1, a, b + 1, c) - fld(1, a, b, c)) * G.rdy; }
-    __device__ __forceinline__ T dz_w(int a, int b, int c) const { return (fld(2, a, b, c + 1) - fld(2, a, b, c)) * G.rdzC(k + c); }
-    __device__ __forceinline__ T dx_v(int a, int b, int c) const { return (fld(1, a, b, c) - fld(1, a - 1, b, c)) * G.rdx; }
-    __device__ __forceinline__ T dy_u(int a, int b, int c) const { return (fld(0, a, b, c) - fld(0, a, b - 1, c)) * G.rdy; }
-    __device__ __forceinline__ T dx_w(int a, int b, int c) const { return (fld(2, a, b, c) - fld(2, a - 1, b, c)) * G.rdx; }
-    __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (fld(0, a, b, c) - fld(0, a, b, c - 1)) * G.rdzF(k + c); }
-    __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (fld(2, a, b, c) - fld(2, a, b - 1, c)) * G.rdy; }
-    __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (fld(1, a, b, c) - fld(1, a, b, c - 1)) * G.rdzF(k + c); }
+    __device__ __forceinline__ T dx_u(int a, int b, int c) const { return (slot(0, a + 1, b, c) - slot(0, a, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dy_v(int a, int b, int c) const { return (slot(1, a, b + 1, c) - slot(1, a, b, c)) * G.rdy; }
+    __device__ __forceinline__ T dz_w(int a, int b, int c) const { return (slot(2, a, b, c + 1) - slot(2, a, b, c)) * G.rdzC(k + c); }
+    __device__ __forceinline__ T dx_v(int a, int b, int c) const { return (slot(1, a, b, c) - slot(1, a - 1, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dy_u(int a, int b, int c) const { return (slot(0, a, b, c) - slot(0, a, b - 1, c)) * G.rdy; }
+    __device__ __forceinline__ T dx_w(int a, int b, int c) const { return (slot(2, a, b, c) - slot(2, a - 1, b, c)) * G.rdx; }
+    __device__ __forceinline__ T dz_u(int a, int b, int c) const { return (slot(0, a, b, c) - slot(0, a, b, c - 1)) * G.rdzF(k + c); }
+    __device__ __forceinline__ T dy_w(int a, int b, int c) const { return (slot(2, a, b, c) - slot(2, a, b - 1, c)) * G.rdy; }
+    __device__ __forceinline__ T dz_v(int a, int b, int c) const { return (slot(1, a, b, c) - slot(1, a, b, c - 1)) * G.rdzF(k + c); }
     __device__ __forceinline__ T S12(int a, int b, int c) const { return T(0.5) * add_rn(dy_u(a, b, c), dx_v(a, b, c)); }
     __device__ __forceinline__ T S13(int a, int b, int c) const { return T(0.5) * add_rn(dz_u(a, b, c), dx_w(a, b, c)); }
     __device__ __forceinline__ T S23(int a, int b, int c) const { return T(0.5) * add_rn(dz_v(a, b, c), dy_w(a, b, c)); }
-    __device__ __forceinline__ T If1(const T *f, int D, int a, int b, int c) const {
-        return T(0.5) * (ldg(f, a - (D == 0), b - (D == 1), c - (D == 2)) + ldg(f, a, b, c));
+    // two-point interpolation of the ccc array in slot f to the face in direction D (interpolation_operators.jl:8-28); level -1
+    // of the x / y interpolants at the own point comes from the carried registers
+    __device__ __forceinline__ T If1(int f, int D, int a, int b, int c) const {
+        if (c < 0) return D == 0 ? ixp : iyp;
+        return T(0.5) * (V.at(f, c - (D == 2), a - (D == 0), b - (D == 1)) + V.at(f, c, a, b));
     }
-    __device__ __forceinline__ T If2(const T *f, int D2, int D1, int a, int b, int c) const {
+    __device__ __forceinline__ T If2(int f, int D2, int D1, int a, int b, int c) const {
         return T(0.5) * (If1(f, D1, a - (D2 == 0), b - (D2 == 1), c - (D2 == 2)) + If1(f, D1, a, b, c));
     }
-    __device__ __forceinline__ T nu_ccc(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? ldg(ne, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
-    __device__ __forceinline__ T nu_ffc(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? If2(ne, 1, 0, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
-    __device__ __forceinline__ T nu_fcf(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? If2(ne, 2, 0, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
-    __device__ __forceinline__ T nu_cff(int m, const T *ne, int a, int b, int c) const { if constexpr (LES) return ne ? If2(ne, 2, 1, a, b, c) : P.cl[m].nu; else return P.cl[m].nu; }
-    __device__ __forceinline__ T ux(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dx_u(a, b, c))); }
-    __device__ __forceinline__ T uy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
-    __device__ __forceinline__ T uz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
-    __device__ __forceinline__ T vx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ffc(m, ne, a, b, c) * S12(a, b, c))); }
-    __device__ __forceinline__ T vy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ccc(m, ne, a, b, c) * dy_v(a, b, c))); }
-    __device__ __forceinline__ T vz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
-    __device__ __forceinline__ T wx(int m, const T *ne, int a, int b, int c) const { return (G.dy * dzF(c)) * (-2 * (nu_fcf(m, ne, a, b, c) * S13(a, b, c))); }
-    __device__ __forceinline__ T wy(int m, const T *ne, int a, int b, int c) const { return (G.dx * dzF(c)) * (-2 * (nu_cff(m, ne, a, b, c) * S23(a, b, c))); }
-    __device__ __forceinline__ T wz(int m, const T *ne, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_ccc(m, ne, a, b, c) * dz_w(a, b, c))); }
-    __device__ __forceinline__ const T *nue_ptr(int m) const {
-        if constexpr (LES) return P.cl[m].kind == CL_SCALAR ? nullptr : at(P.nue[m]);
-        else return nullptr;
-    }
-    // diffusive flux of the staged tracer along D at the face (a, b, c)
-    __device__ __forceinline__ T qflux(int m, const T *kf, int D, int a, int b, int c) const {
+    // viscosity of closure m at ccc / ffc / fcf / cff (abstract_scalar_diffusivity_closure.jl:330-351)
+    __device__ __forceinline__ T nu_ccc(int m, int a, int b, int c) const { if (LES0 && m == 0) return V.at(3, c, a, b); return P.cl[m].nu; }
+    __device__ __forceinline__ T nu_ffc(int m, int a, int b, int c) const { if (LES0 && m == 0) return If2(3, 1, 0, a, b, c); return P.cl[m].nu; }
+    __device__ __forceinline__ T nu_fcf(int m, int a, int b, int c) const { if (LES0 && m == 0) return If2(3, 2, 0, a, b, c); return P.cl[m].nu; }
+    __device__ __forceinline__ T nu_cff(int m, int a, int b, int c) const { if (LES0 && m == 0) return If2(3, 2, 1, a, b, c); return P.cl[m].nu; }
+    __device__ __forceinline__ T ux(int m, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ccc(m, a, b, c) * dx_u(a, b, c))); }
+    __device__ __forceinline__ T uy(int m, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ffc(m, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T uz(int m, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_fcf(m, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T vx(int m, int a, int b, int c) const { return (G.dy * dzC(c)) * (-2 * (nu_ffc(m, a, b, c) * S12(a, b, c))); }
+    __device__ __forceinline__ T vy(int m, int a, int b, int c) const { return (G.dx * dzC(c)) * (-2 * (nu_ccc(m, a, b, c) * dy_v(a, b, c))); }
+    __device__ __forceinline__ T vz(int m, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_cff(m, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wx(int m, int a, int b, int c) const { return (G.dy * dzF(c)) * (-2 * (nu_fcf(m, a, b, c) * S13(a, b, c))); }
+    __device__ __forceinline__ T wy(int m, int a, int b, int c) const { return (G.dx * dzF(c)) * (-2 * (nu_cff(m, a, b, c) * S23(a, b, c))); }
+    __device__ __forceinline__ T wz(int m, int a, int b, int c) const { return (G.dx * G.dy) * (-2 * (nu_ccc(m, a, b, c) * dz_w(a, b, c))); }
+    // diffusive flux of the tracer along D at the face (a, b, c) (abstract_scalar_diffusivity_closure.jl:260-262)
+    __device__ __forceinline__ T qflux(int m, int D, int a, int b, int c) const {
+        const int fc = MODE == STAGE_TT ? cs : 3;   // slot of the tracer
         T kap;
-        if constexpr (LES) {
-            const int kind = P.cl[m].kind;
-            kap = kind == CL_SCALAR ? P.cl[m].kappa[tstage] : kind == CL_SMAG ? If1(kf, D, a, b, c) / P.cl[m].Pr[tstage] : If1(kf, D, a, b, c);
+        if (LES0 && m == 0) {
+            if constexpr (KL == CL_SMAG) kap = If1(fc + 1, D, a, b, c) / P.cl[0].Pr[tr];
+            else kap = If1(fc + 1, D, a, b, c);
         } else {
-            kap = P.cl[m].kappa[tstage];
+            kap = P.cl[m].kappa[tr];
         }
         const T rd = D == 0 ? G.rdx : D == 1 ? G.rdy : G.rdzF(k + c);
         const T A = D == 0 ? G.dy * dzC(c) : D == 1 ? G.dx * dzC(c) : G.dx * G.dy;
-        const T dc = (fld(3, a, b, c) - fld(3, a - (D == 0), b - (D == 1), c - (D == 2))) * rd;
+        const T dc = (slot(fc, a, b, c) - slot(fc, a - (D == 0), b - (D == 1), c - (D == 2))) * rd;
         return A * (-kap * dc);
     }
-    // closure flux of tendency WHICH through the owned face in direction D (D == 2: the UPPER face)
+    // closure flux of a tendency of kind WHICH through the owned face in direction D (D == 2: the UPPER face)
     template <int WHICH, int D> __device__ __forceinline__ T own_closure_flux(int m) const {
-        if constexpr (WHICH == 3) {
-            const T *kf = nullptr;
-            if constexpr (LES) {
-                const int kind = P.cl[m].kind;
-                kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][tstage]);
-            }
-            return qflux(m, kf, D, 0, 0, D == 2 ? 1 : 0);
-        } else {
-            const T *ne = nue_ptr(m);
-            if constexpr (WHICH == 0) return D == 0 ? ux(m, ne, -1, 0, 0) : D == 1 ? uy(m, ne, 0, 0, 0) : uz(m, ne, 0, 0, 1);
-            else if constexpr (WHICH == 1) return D == 0 ? vx(m, ne, 0, 0, 0) : D == 1 ? vy(m, ne, 0, -1, 0) : vz(m, ne, 0, 0, 1);
-            else return D == 0 ? wx(m, ne, 0, 0, 0) : D == 1 ? wy(m, ne, 0, 0, 0) : wz(m, ne, 0, 0, 0);
-        }
+        if constexpr (WHICH == 3) return qflux(m, D, 0, 0, D == 2 ? 1 : 0);
+        else if constexpr (WHICH == 0) return D == 0 ? ux(m, -1, 0, 0) : D == 1 ? uy(m, 0, 0, 0) : uz(m, 0, 0, 1);
+        else if constexpr (WHICH == 1) return D == 0 ? vx(m, 0, 0, 0) : D == 1 ? vy(m, 0, -1, 0) : vz(m, 0, 0, 1);
+        else return D == 0 ? wx(m, 0, 0, 0) : D == 1 ? wy(m, 0, 0, 0) : wz(m, 0, 0, 0);
     }
     __device__ __forceinline__ T bpert(int c) const {
         if (P.buoy == BUOY_TRACER) {
-            if (P.ib == tstage) return fld(3, 0, 0, c);
+            if (MODE == STAGE_MT && P.ib == tr) return slot(3, 0, 0, c);
             return ldg(at(P.c[P.ib]), 0, 0, c);
         }
         if (P.buoy == BUOY_SEAWATER) return P.grav * (P.alpha * ldg(at(P.c[P.iT]), 0, 0, c) - P.beta * ldg(at(P.c[P.iS]), 0, 0, c));
         return 0;
     }
     // the tendency assemblers, same term order as FastTerms::finish<WHICH, true>
-    template <int WHICH, int NCL> __device__ __forceinline__ T finish(T adv, T closure_term) const {
+    template <int WHICH> __device__ __forceinline__ T finish(T adv, T closure_term) const {
         T r = -adv;
         if constexpr (WHICH == 0) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
                 const T A = G.dx * dzC(0);
-                const T I = interp4_rn(A, fld(1, -1, 0, 0), fld(1, 0, 0, 0), fld(1, -1, 1, 0), fld(1, 0, 1, 0));
+                const T I = interp4_rn(A, slot(1, -1, 0, 0), slot(1, 0, 0, 0), slot(1, -1, 1, 0), slot(1, 0, 1, 0));
                 r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (G.dx * dzC(0))));
             }
             if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, -1, 0, 0)) * G.rdx; }
@@ -257,7 +266,7 @@ struct StageTerms {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
                 const T A = G.dy * dzC(0);
-                const T I = interp4_rn(A, fld(0, 0, -1, 0), fld(0, 1, -1, 0), fld(0, 0, 0, 0), fld(0, 1, 0, 0));
+                const T I = interp4_rn(A, slot(0, 0, -1, 0), slot(0, 1, -1, 0), slot(0, 0, 0, 0), slot(0, 1, 0, 0));
                 r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (G.dy * dzC(0))));
             }
             if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, 0, -1, 0)) * G.rdy; }
@@ -269,17 +278,19 @@ struct StageTerms {
     }
 };
 
-template <typename T, int N, int W, int NCL, bool LES, bool STR>
-__global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ TmaMaps M, const StageLaunch L) {
+template <typename T, int N, int W, int MODE, int NCL, int KL, bool STR>
+__global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const __grid_constant__ TendP<T> P, const __grid_constant__ StageMaps M, const StageLaunch L) {
     using C = StageCfg<T, N, W, NCL>;
     constexpr int TW = C::TW, PL = C::PL, D = C::D, NV = C::NV;
+    constexpr int NCLR = NCL > 0 ? NCL : 1;
     using View = StageView<T, N, TW, PL>;
-    using Terms = StageTerms<T, N, LES, STR, TW, PL>;
+    using Terms = StageTerms<T, N, MODE, NCL, KL, STR, TW, PL>;
     extern __shared__ __align__(128) unsigned char smem[];
     T *ring = reinterpret_cast<T *>(smem);
     T *xch = reinterpret_cast<T *>(smem + C::RING_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::RING_BYTES + C::XCH_BYTES);
-    uint64_t *full = bars, *empty = bars + D, *pub = bars + 2 * D;   // pub[2*w + slot], w = 1 .. W (W: helper)
+    uint64_t *full = bars, *empty = bars + D, *pub = bars + 2 * D;   // pub[2*w + slot], w = 1 .. W (W: the helpers)
+    int *done = reinterpret_cast<int *>(smem + C::RING_BYTES + C::XCH_BYTES + C::NBAR * 8);   // TMA path: releases per slot (monotonic)
 
     // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps role branches and the
     // coefficient literals on the uniform datapath
@@ -294,12 +305,27 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
     const int i0 = 1 + tile_x * C::TXC, j0 = 1 + tile_y * C::TYC;
     const int k0 = L.kbeg + kc * L.klen, k1 = min(k0 + L.klen - 1, L.kend);
     const int kfirst = k0 - N, klast = k1 + N;
-    const bool mom = pass == 0;                 // CTA-uniform: pass 0 = momentum + tracer 0, pass p = tracer p alone
-    const int tstage = pass;
-    const bool has_tr = tstage < P.ntr;
-    const int nfields = has_tr ? 4 : 3;
 
-    int *done = reinterpret_cast<int *>(smem + C::RING_BYTES + C::XCH_BYTES + C::NBAR * 8);   // TMA path: releases per slot (monotonic)
+    // ---- what this pass stages and computes (CTA-uniform) ----------------------------------------------------------------
+    // tendency slot q: active?  MT: q = 0..2 momentum (pass 0), q = 3 tracer `pass`;  MN: q = 0..2;  TT: q = 0, 1 tracers 2*pass, 2*pass+1
+    const int trA = MODE == STAGE_MT ? pass : 2 * pass, trB = 2 * pass + 1;
+    bool act[4];
+    const T *slotp[4];   // parent array of each slot (cp.async path, and which slots exist)
+    if constexpr (MODE == STAGE_MT) {
+        act[0] = act[1] = act[2] = pass == 0; act[3] = trA < P.ntr;
+        slotp[0] = P.u.p; slotp[1] = P.v.p; slotp[2] = P.w.p; slotp[3] = act[3] ? P.c[trA].p : nullptr;
+    } else if constexpr (MODE == STAGE_MN) {
+        act[0] = act[1] = act[2] = true; act[3] = false;
+        slotp[0] = P.u.p; slotp[1] = P.v.p; slotp[2] = P.w.p; slotp[3] = P.nue[0].p;
+    } else {
+        act[0] = true; act[1] = trB < P.ntr; act[2] = act[3] = false;
+        slotp[0] = P.c[trA].p; slotp[1] = KL == CL_AMD ? P.kappae[0][trA].p : P.nue[0].p;
+        slotp[2] = act[1] ? P.c[trB].p : nullptr; slotp[3] = act[1] ? (KL == CL_AMD ? P.kappae[0][trB].p : P.nue[0].p) : nullptr;
+    }
+    int nfields = 0;
+#pragma unroll
+    for (int f = 0; f < 4; f++) nfields += slotp[f] != nullptr;
+
     // tile origin in parent coordinates (0-based); the box starts on a 16-byte boundary of the row
     const int cxu = i0 - N + gg.H[0] - 1;
     const int cx0 = cxu & ~(C::EPV - 1), cy0 = j0 - N + gg.H[1] - 1;
@@ -310,10 +336,9 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
         unsigned char *dst = smem + s * C::LEVEL_BYTES;
         mbar_expect_tx(&full[s], nfields * C::BOX_BYTES);
         const int cz = Lv + gg.H[2] - 1;
-        tma_load_3d(dst, &M.m[0], &full[s], cx0, cy0, cz);
-        tma_load_3d(dst + C::PLANE_BYTES, &M.m[1], &full[s], cx0, cy0, cz);
-        tma_load_3d(dst + 2 * C::PLANE_BYTES, &M.m[2], &full[s], cx0, cy0, cz);
-        if (has_tr) tma_load_3d(dst + 3 * C::PLANE_BYTES, &M.m[3 + tstage], &full[s], cx0, cy0, cz);
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+            if (slotp[f]) tma_load_3d(dst + f * C::PLANE_BYTES, &M.m[pass][f], &full[s], cx0, cy0, cz);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < D; s++) { mbar_init(&full[s], use_tma ? 1 : nfields * 32); mbar_init(&empty[s], W + C::NH); done[s] = 0; }
@@ -327,11 +352,11 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
     // ---------------------------------------------------------------- consumers ------------------------------------
     // Compute warps (warp < W): own point (i0+lane, j0+warp), the same for every phase.  Helpers (warp >= W): the south-flux
     // point is (i0+lane, j0+TYC) -- the tile's north edge, lanes = columns -- and the west-flux point (i0+32, j0+lane) --
-    // the east edge, lanes = rows; helper hq does tendency hq.  Phase A (south fluxes) is the same code in every warp.
+    // the east edge, lanes = rows; helper hq does tendency slot hq.  Phase A (south fluxes) is the same code in every warp.
     const bool helper = warp >= W;
     const int hq = warp - W;
-    const bool do0 = mom && (!helper || hq == 0), do1 = mom && (!helper || hq == 1), do2 = mom && (!helper || hq == 2);
-    const bool do3 = has_tr && (!helper || hq == 3);
+    const bool do0 = act[0] && (!helper || hq == 0), do1 = act[1] && (!helper || hq == 1), do2 = act[2] && (!helper || hq == 2);
+    const bool do3 = act[3] && (!helper || hq == 3);
     const int pw = helper ? W : warp;   // publication row of this warp's south fluxes
     FastGeom<T, STR> g;
     g.init(gg, P.u.sy, P.u.sz);
@@ -345,25 +370,26 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
     auto yx_at = [&](int slot, int w, int q, int v) -> T * { return xch + slot * C::XCH_SLOT + ((w * C::NQ + q) * NV + v) * 32 + lane; };
     auto xe_at = [&](int slot, int q, int v, int row) -> T * { return xch + slot * C::XCH_SLOT + C::YX_SLOT + (q * NV + v) * 32 + row; };
 
-    // register state carried from level to level: own-column history (helper: h[0] = u at its west-flux point, h[1] = v at its
-    // south-flux point), lower-face fluxes
-    T h[4][N - 1], lower[4], lower_c[4][NCL > 0 ? NCL : 1];
+    // register state carried from level to level: own-column history of every slot (helpers, MT / MN: h[0] = u at the west-flux
+    // point, h[1] = v at the south-flux point), lower-face fluxes, and (MN) the x / y face interpolants of nu_e one level below
+    T h[4][N - 1], lower[4], lower_c[4][NCLR];
+    T ixp = T(0), iyp = T(0);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         lower[q] = T(0);
 #pragma unroll
-        for (int m = 0; m < (NCL > 0 ? NCL : 1); m++) lower_c[q][m] = T(0);
+        for (int m = 0; m < NCLR; m++) lower_c[q][m] = T(0);
 #pragma unroll
         for (int m = 0; m < N - 1; m++) h[q][m] = T(0);
     }
     // running ring positions: level k is in slot sk; level k+N (the newest one this level needs) in slot sn with phase pn
     int sk = 0, sn = N % D, pn = (N / D) & 1;
-    // cp.async path: the 32 lanes of helper f copy the box of field f element by element (zero-fill outside the parent
-    // array) for every level up to `upto`; a slot is reused once every consumer has released its previous level.
+    // cp.async path: the 32 lanes of helper f copy the box of slot f element by element (zero-fill outside the parent
+    // array) for every level up to `upto`; a ring slot is reused once every consumer has released its previous level.
     int fed = kfirst - 1;
     auto feed = [&](bool blocking, int upto) {
         const int Px = P.u.sy, Py = (int)(P.u.sz / P.u.sy);
-        const Fld<T> &F = hq == 0 ? P.u : hq == 1 ? P.v : hq == 2 ? P.w : P.c[tstage];
+        const T *base = hq == 0 ? slotp[0] : hq == 1 ? slotp[1] : hq == 2 ? slotp[2] : slotp[3];
         while (fed < upto && fed < klast) {
             const int Lv = fed + 1, n = Lv - kfirst, s = n % D;
             if (n >= D) {
@@ -377,7 +403,7 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
                 }
             }
             T *dst = reinterpret_cast<T *>(smem + s * C::LEVEL_BYTES + hq * C::PLANE_BYTES);
-            const T *src = F.p + (long)(Lv + gg.H[2] - 1) * F.sz;
+            const T *src = base + (long)(Lv + gg.H[2] - 1) * P.u.sz;
             for (int e = lane; e < C::TW * C::TH; e += 32) {
                 const int yy = e / C::TW, xx = e - yy * C::TW;
                 const int gx = cx0 + xx, gy = cy0 + yy;
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
             fed = Lv;
         }
     };
-    const bool feeder = !use_tma && helper && hq < nfields;
+    const bool feeder = !use_tma && helper && (hq == 0 ? slotp[0] : hq == 1 ? slotp[1] : hq == 2 ? slotp[2] : slotp[3]) != nullptr;
     if (feeder) feed(true, kfirst + N - 1);
     for (int n = 0; n < N; n++) mbar_wait(&full[n], 0);
 
@@ -409,58 +435,56 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
         for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * C::LEVEL; }
         const int e = k - k0, xs = e & 1, xp = (e >> 1) & 1;
         const bool full_level = k >= k0;
-        View VY;
+        View VY, VX;
 #pragma unroll
-        for (int d = 0; d <= N; d++) VY.pl[d] = lev[d] + ownY;
-        const Terms FY{P, g, VY, h[0], h[1], h[2], h[3], eoY + k * g.sz, k, tstage};
+        for (int d = 0; d <= N; d++) { VY.pl[d] = lev[d] + ownY; VX.pl[d] = lev[d] + ownX; }
+        Terms FY{P, g, VY, h[0], h[1], h[2], h[3], eoY + k * g.sz, k, trA, 0, ixp, iyp};
+        // TT: the advecting velocities at the own points, from global memory (u at the west-flux point, v at the south-flux
+        // point, w one level up)
+        T gu = T(0), gv = T(0), gw = T(0);
+        if constexpr (MODE == STAGE_TT) {
+            if (k >= k0 - 1) {
+                gu = __ldg(P.u.p + P.u.off + eoX + k * g.sz);
+                gv = __ldg(P.v.p + P.v.off + eoY + k * g.sz);
+                gw = __ldg(P.w.p + P.w.off + eoY + (k + 1) * g.sz);
+            }
+        }
+        // one tendency slot q: kind of tendency, slot of its field, tracer index
+        auto south = [&](auto qtag) {   // phase A of slot q
+            constexpr int Q = decltype(qtag)::value;
+            constexpr int WHICH = MODE == STAGE_TT ? 3 : Q;
+            constexpr int QS = MODE == STAGE_TT ? 2 * Q : Q;
+            if constexpr (MODE == STAGE_TT) { FY.tr = Q == 0 ? trA : trB; FY.cs = QS; }
+            *yx_at(xs, pw, Q, 0) = stage_flux<T, N, WHICH, 1, STR, TW, PL, QS, MODE == STAGE_TT>(VY, h[QS], h[1], g, k, gv);
+#pragma unroll
+            for (int m = 0; m < NCL; m++) *yx_at(xs, pw, Q, 1 + m) = FY.template own_closure_flux<WHICH, 1>(m);
+        };
         if (full_level) {
             // ---- phase A: south fluxes, published for the warp below (helpers: the tile's north edge) ------------------
-            if (do0) {
-                *yx_at(xs, pw, 0, 0) = stage_flux<T, N, 0, 1, STR, TW, PL>(VY, h[0], h[1], g, k);
-#pragma unroll
-                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 0, 1 + m) = FY.template own_closure_flux<0, 1>(m);
-            }
-            if (do1) {
-                *yx_at(xs, pw, 1, 0) = stage_flux<T, N, 1, 1, STR, TW, PL>(VY, h[1], h[1], g, k);
-#pragma unroll
-                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 1, 1 + m) = FY.template own_closure_flux<1, 1>(m);
-            }
-            if (do2) {
-                *yx_at(xs, pw, 2, 0) = stage_flux<T, N, 2, 1, STR, TW, PL>(VY, h[2], h[1], g, k);
-#pragma unroll
-                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 2, 1 + m) = FY.template own_closure_flux<2, 1>(m);
-            }
-            if (do3) {
-                *yx_at(xs, pw, 3, 0) = stage_flux<T, N, 3, 1, STR, TW, PL>(VY, h[3], h[1], g, k);
-#pragma unroll
-                for (int m = 0; m < NCL; m++) *yx_at(xs, pw, 3, 1 + m) = FY.template own_closure_flux<3, 1>(m);
+            if (do0) south(std::integral_constant<int, 0>{});
+            if (do1) south(std::integral_constant<int, 1>{});
+            if constexpr (MODE != STAGE_TT) {
+                if (do2) south(std::integral_constant<int, 2>{});
+                if constexpr (MODE == STAGE_MT) { if (do3) south(std::integral_constant<int, 3>{}); }
             }
             if (helper) {
                 // ---- helper phase B: west fluxes at the tile's east edge, lanes = rows -----------------------------------
-                View VX;
+                Terms FX{P, g, VX, h[0], h[1], h[2], h[3], eoX + k * g.sz, k, trA, 0, ixp, iyp};
+                auto west_edge = [&](auto qtag) {
+                    constexpr int Q = decltype(qtag)::value;
+                    constexpr int WHICH = MODE == STAGE_TT ? 3 : Q;
+                    constexpr int QS = MODE == STAGE_TT ? 2 * Q : Q;
+                    if constexpr (MODE == STAGE_TT) { FX.tr = Q == 0 ? trA : trB; FX.cs = QS; }
+                    *xe_at(xs, Q, 0, lane) = stage_flux<T, N, WHICH, 0, STR, TW, PL, QS, MODE == STAGE_TT>(VX, h[QS], h[0], g, k, gu);
 #pragma unroll
-                for (int d = 0; d <= N; d++) VX.pl[d] = lev[d] + ownX;
-                const Terms FX{P, g, VX, h[0], h[1], h[2], h[3], eoX + k * g.sz, k, tstage};
+                    for (int m = 0; m < NCL; m++) *xe_at(xs, Q, 1 + m, lane) = FX.template own_closure_flux<WHICH, 0>(m);
+                };
                 if (lane < C::TYC) {
-                    if (do0) {
-                        *xe_at(xs, 0, 0, lane) = stage_flux<T, N, 0, 0, STR, TW, PL>(VX, h[0], h[0], g, k);
-#pragma unroll
-                        for (int m = 0; m < NCL; m++) *xe_at(xs, 0, 1 + m, lane) = FX.template own_closure_flux<0, 0>(m);
-                    }
-                    if (do1) {
-                        *xe_at(xs, 1, 0, lane) = stage_flux<T, N, 1, 0, STR, TW, PL>(VX, h[1], h[0], g, k);
-#pragma unroll
-                        for (int m = 0; m < NCL; m++) *xe_at(xs, 1, 1 + m, lane) = FX.template own_closure_flux<1, 0>(m);
-                    }
-                    if (do2) {
-                        *xe_at(xs, 2, 0, lane) = stage_flux<T, N, 2, 0, STR, TW, PL>(VX, h[2], h[0], g, k);
-#pragma unroll
-                        for (int m = 0; m < NCL; m++) *xe_at(xs, 2, 1 + m, lane) = FX.template own_closure_flux<2, 0>(m);
-                    }
-                    if (do3) {
-                        *xe_at(xs, 3, 0, lane) = stage_flux<T, N, 3, 0, STR, TW, PL>(VX, h[3], h[0], g, k);
-#pragma unroll
-                        for (int m = 0; m < NCL; m++) *xe_at(xs, 3, 1 + m, lane) = FX.template own_closure_flux<3, 0>(m);
+                    if (do0) west_edge(std::integral_constant<int, 0>{});
+                    if (do1) west_edge(std::integral_constant<int, 1>{});
+                    if constexpr (MODE != STAGE_TT) {
+                        if (do2) west_edge(std::integral_constant<int, 2>{});
+                        if constexpr (MODE == STAGE_MT) { if (do3) west_edge(std::integral_constant<int, 3>{}); }
                     }
                 }
                 __syncwarp();
@@ -474,58 +498,66 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
             // ---- phase C: upper fluxes; on full levels the west fluxes, the divergence and the tendency ----------------
             const int eo = eoY + k * g.sz;
             bool waited = false;   // the published fluxes are awaited as late as possible: right before their first use
-            auto tendency = [&](auto which_tag) {
-                constexpr int WHICH = decltype(which_tag)::value;
-                const Fld<T> &G = WHICH == 0 ? P.Gu : WHICH == 1 ? P.Gv : WHICH == 2 ? P.Gw : P.Gc[tstage];
-                const T upper = stage_flux<T, N, WHICH, 2, STR, TW, PL>(VY, h[WHICH], h[2], g, k);
-                T cup[NCL > 0 ? NCL : 1];
+            auto tendency = [&](auto qtag) {
+                constexpr int Q = decltype(qtag)::value;
+                constexpr int WHICH = MODE == STAGE_TT ? 3 : Q;
+                constexpr int QS = MODE == STAGE_TT ? 2 * Q : Q;
+                if constexpr (MODE == STAGE_TT) { FY.tr = Q == 0 ? trA : trB; FY.cs = QS; }
+                const Fld<T> &G = MODE == STAGE_TT ? P.Gc[Q == 0 ? trA : trB] : Q == 0 ? P.Gu : Q == 1 ? P.Gv : Q == 2 ? P.Gw : P.Gc[trA];
+                const T upper = stage_flux<T, N, WHICH, 2, STR, TW, PL, QS, MODE == STAGE_TT>(VY, h[QS], h[2], g, k, gw);
+                T cup[NCLR];
 #pragma unroll
                 for (int m = 0; m < NCL; m++) cup[m] = FY.template own_closure_flux<WHICH, 2>(m);
                 if (full_level) {
-                    const T fx = stage_flux<T, N, WHICH, 0, STR, TW, PL>(VY, h[WHICH], h[0], g, k);
+                    const T fx = stage_flux<T, N, WHICH, 0, STR, TW, PL, QS, MODE == STAGE_TT>(VY, h[QS], h[0], g, k, gu);
                     if (!waited) {
                         mbar_wait(&pub[2 * (warp + 1) + xs], (uint32_t)xp);
                         if (warp + 1 != W) mbar_wait(&pub[2 * W + xs], (uint32_t)xp);
                         waited = true;
                     }
-                    const T fy = *yx_at(xs, warp, WHICH, 0);
-                    const T fy1 = *yx_at(xs, warp + 1, WHICH, 0);
+                    const T fy = *yx_at(xs, warp, Q, 0);
+                    const T fy1 = *yx_at(xs, warp + 1, Q, 0);
                     T fx1 = __shfl_down_sync(0xffffffffu, fx, 1);
-                    if (lane == 31) fx1 = *xe_at(xs, WHICH, 0, warp);
+                    if (lane == 31) fx1 = *xe_at(xs, Q, 0, warp);
                     const T Vi = WHICH == 2 ? g.rVf(k) : g.rVc(k);
-                    const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower[WHICH]));
+                    const T adv = Vi * ((fx1 - fx) + (fy1 - fy) + (upper - lower[Q]));
                     T term = T(0);
 #pragma unroll
                     for (int m = 0; m < NCL; m++) {
                         const T cx = FY.template own_closure_flux<WHICH, 0>(m);
-                        const T cyv = *yx_at(xs, warp, WHICH, 1 + m);
-                        const T cy1 = *yx_at(xs, warp + 1, WHICH, 1 + m);
+                        const T cyv = *yx_at(xs, warp, Q, 1 + m);
+                        const T cy1 = *yx_at(xs, warp + 1, Q, 1 + m);
                         T cx1 = __shfl_down_sync(0xffffffffu, cx, 1);
-                        if (lane == 31) cx1 = *xe_at(xs, WHICH, 1 + m, warp);
+                        if (lane == 31) cx1 = *xe_at(xs, Q, 1 + m, warp);
                         // (the marching kernel forms these under run-time closure counts, where nothing contracts; pinned here)
-                        const T d = mul_rn(Vi, (cx1 - cx) + (cy1 - cyv) + (cup[m] - lower_c[WHICH][m]));
+                        const T d = mul_rn(Vi, (cx1 - cx) + (cy1 - cyv) + (cup[m] - lower_c[Q][m]));
                         term = m == 0 ? d : add_rn(term, d);
                     }
-                    const T res = FY.template finish<WHICH, NCL>(adv, term);
+                    const T res = FY.template finish<WHICH>(adv, term);
                     if (live) G.p[G.off + eo] = res;
                 }
-                lower[WHICH] = upper;
+                lower[Q] = upper;
 #pragma unroll
-                for (int m = 0; m < NCL; m++) lower_c[WHICH][m] = cup[m];
+                for (int m = 0; m < NCL; m++) lower_c[Q][m] = cup[m];
             };
-            if (mom) {
-                tendency(std::integral_constant<int, 0>{});
-                tendency(std::integral_constant<int, 1>{});
-                tendency(std::integral_constant<int, 2>{});
+            if (act[0]) tendency(std::integral_constant<int, 0>{});
+            if (act[1]) tendency(std::integral_constant<int, 1>{});
+            if constexpr (MODE != STAGE_TT) {
+                if (act[2]) tendency(std::integral_constant<int, 2>{});
+                if constexpr (MODE == STAGE_MT) { if (act[3]) tendency(std::integral_constant<int, 3>{}); }
             }
-            if (has_tr) tendency(std::integral_constant<int, 3>{});
         }
-        // history shift: level k becomes k-1 (helper: u at its west-flux point, v at its south-flux point)
+        // level k becomes k-1: history shift (helpers, MT / MN: u at the west-flux point, v at the south-flux point) and (MN) the
+        // face interpolants of nu_e that next level's wx / wy need
+        if constexpr (MODE == STAGE_MN) {
+            ixp = T(0.5) * (VX.at(3, 0, -1, 0) + VX.at(3, 0, 0, 0));
+            iyp = T(0.5) * (VY.at(3, 0, 0, -1) + VY.at(3, 0, 0, 0));
+        }
 #pragma unroll
         for (int f = 0; f < 4; f++) {
 #pragma unroll
             for (int m = 0; m + 1 < N - 1; m++) h[f][m] = h[f][m + 1];
-            h[f][N - 2] = lev[0][f * PL + (f == 0 ? ownX : ownY)];
+            h[f][N - 2] = lev[0][f * PL + ((f == 0 && MODE != STAGE_TT) ? ownX : ownY)];
         }
         __syncwarp();
         if (use_tma) {
@@ -541,11 +573,9 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
             }
         } else {
             if (lane == 0) mbar_arrive(&empty[sk]);
-            if (helper && hq < nfields) {
-                // cp.async path: helper f copies field f.  Opportunistic: if the level that takes this slot can be loaded
-                // already, do it now; otherwise the blocking catch-up at the top of a later level does it.
-                feed(false, k + N + 1);
-            }
+            // cp.async path: helper f copies slot f.  Opportunistic: if the level that takes this ring slot can be loaded already,
+            // do it now; otherwise the blocking catch-up at the top of a later level does it.
+            if (feeder) feed(false, k + N + 1);
         }
         if (++sk == D) sk = 0;
         if (++sn == D) { sn = 0; pn ^= 1; }

@@ -22,7 +22,8 @@
 #include <stdlib.h>
 #include "tendency.cuh"
 #include "tendency_tma.cuh"
-#include "tendency_stage.cuh"
+#include "tma_maps.h"
+#include "stage_launch.h"
 
 namespace ob {
 
@@ -191,19 +192,6 @@ __global__ void __launch_bounds__(32 * TY, MINB) tendency_march_tma_kernel(const
     else march_body<T, S, FAST, 3, TY, KC>(P, which - 3, i, j, k0, k1, sy);
 }
 
-typedef CUresult (*ob_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static ob_encode_tiled_fn encode_tiled_fn() {
-    static ob_encode_tiled_fn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        return (ob_encode_tiled_fn)p;
-    }();
-    return fn;
-}
-
 // true when the TMA variant applies: WENO, (Periodic, Periodic, non-Flat), 16-byte row pitch, one parent shape per field
 template <typename T, class S>
 static bool tma_applicable(const TendP<T> &P) {
@@ -263,98 +251,31 @@ static cudaError_t launch_march_tma(const TendP<T> &P, int fast, cudaStream_t st
     }
 }
 
-// ---- staged-ring kernel (tendency_stage.cuh) --------------------------------------------------------------------------
-// Applicable: WENO, (Periodic, Periodic, Periodic | Bounded) topology, at most OB_SHARED_CL closures, none vertically
-// implicit, 32-bit element offsets, the whole x range in one launch.
+// which (float type, scheme) combinations have a staged-ring kernel (stage_launch.h lists the variants)
 template <typename T, class S>
-static bool stage_applicable(const TendP<T> &P) {
+struct StageSel {
+    static constexpr bool built = S::kind == ADV_WENO && S::n == 3;
+};
+
+// ---- staged-ring kernel (tendency_stage.cuh, instantiated in stage_inst.cu) ------------------------------------------------
+// Applicable: WENO, (Periodic, Periodic, Periodic | Bounded) topology, the rcp + Newton division, at most two closures, none
+// vertically implicit, 32-bit element offsets, the whole x range in one launch; closures either all ScalarDiffusivity (mode MT)
+// or ONE eddy-viscosity closure in first position followed by at most one ScalarDiffusivity (modes MN + TT).
+template <typename T, class S>
+static bool stage_applicable(const TendP<T> &P, int &les_kind) {
+    les_kind = 0;
     if (S::kind != ADV_WENO) return false;
     const GridD<T> &g = P.g;
     if (g.topo[0] != PERIODIC || g.topo[1] != PERIODIC || g.topo[2] == FLAT) return false;
     if (P.ncl > OB_SHARED_CL) return false;
     for (int m = 0; m < P.ncl; m++) if (P.cl[m].vi) return false;
+    for (int m = 1; m < P.ncl; m++) if (P.cl[m].kind != CL_SCALAR) return false;
+    if (P.ncl >= 1 && P.cl[0].kind != CL_SCALAR) les_kind = P.cl[0].kind;
+    if (P.ncl == 2 && les_kind == 0) return false;   // two ScalarDiffusivities: not instantiated (marching kernel)
     if (P.u.sz * (long)(g.N[2] + 2 * g.H[2] + 1) >= 2147483647L) return false;
     if (g.topo[2] == BOUNDED && g.N[2] <= 2 * S::n) return false;
     for (int d = 0; d < 3; d++) if (g.H[d] < S::n) return false;
     return true;
-}
-
-// tensor maps are cached per (pointer, shape): a model re-launches with the same parents every stage
-struct StageMapKey { const void *p; unsigned long long px, py, pz; int tw, th, esz; };
-static bool stage_map(CUtensorMap *out, const void *ptr, cuuint64_t Px, cuuint64_t Py, cuuint64_t Pz, int tw, int th, int esz) {
-    struct Entry { StageMapKey k; CUtensorMap m; };
-    static thread_local std::vector<Entry> cache;
-    for (const Entry &e : cache)
-        if (e.k.p == ptr && e.k.px == Px && e.k.py == Py && e.k.pz == Pz && e.k.tw == tw && e.k.th == th && e.k.esz == esz) { *out = e.m; return true; }
-    if (!encode_tiled_fn()) return false;
-    const cuuint64_t dims[3] = {Px, Py, Pz};
-    const cuuint64_t strides[2] = {Px * (cuuint64_t)esz, Px * Py * (cuuint64_t)esz};
-    const cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)th, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUtensorMap m;
-    if (encode_tiled_fn()(&m, esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr), dims, strides, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
-    if (cache.size() > 256) cache.clear();
-    cache.push_back(Entry{StageMapKey{ptr, Px, Py, Pz, tw, th, esz}, m});
-    *out = m;
-    return true;
-}
-
-template <typename T, class S, int W, int NCL, bool LES>
-static cudaError_t launch_stage(const TendP<T> &P, cudaStream_t st, int sm_count, int *nlaunch) {
-    if constexpr (S::kind != ADV_WENO) return cudaErrorNotSupported;
-    else {
-        constexpr int N = S::n;
-        using C = StageCfg<T, N, W, NCL>;
-        static_assert(C::FITS, "staged-ring tile does not fit in shared memory");
-        const int Nx = P.g.N[0], Ny = P.g.N[1], Nz = P.g.N[2];
-        StageLaunch L;
-        L.ntx = (Nx + C::TXC - 1) / C::TXC;
-        L.nty = (Ny + C::TYC - 1) / C::TYC;
-        const bool walls = P.g.topo[2] == BOUNDED;
-        L.kbeg = walls ? N + 1 : 1;
-        L.kend = walls ? Nz - N : Nz;
-        L.npass = P.ntr > 1 ? P.ntr : 1;
-        // chunk length: balance whole waves of CTAs (one CTA per SM) against the N+1 warm-up levels of every chunk
-        const long tiles = (long)L.ntx * L.nty;
-        const int nlev = L.kend - L.kbeg + 1;
-        const int sms = sm_count > 0 ? sm_count : 148;
-        double best = 1e300;
-        int best_nk = 1;
-        for (int nk = 1; nk <= nlev; nk++) {
-            const int len = (nlev + nk - 1) / nk;
-            if (len < 4 && nk > 1) break;
-            const long ctas = tiles * nk;   // pass 0 dominates: the tracer-only passes fill in behind it
-            const long waves = (ctas + sms - 1) / sms;
-            const double cost = (double)waves * (len + 2.0);
-            if (cost < best) { best = cost; best_nk = nk; }
-        }
-        L.klen = (nlev + best_nk - 1) / best_nk;
-        L.nkc = (nlev + L.klen - 1) / L.klen;
-        TmaMaps M;
-        memset(&M, 0, sizeof(M));
-        const cuuint64_t Px = (cuuint64_t)P.u.sy, Py = (cuuint64_t)(P.u.sz / P.u.sy);
-        L.use_tma = ((Px * sizeof(T)) % 16 == 0 && !getenv("OB_STAGE_NO_TMA")) ? 1 : 0;
-        if (L.use_tma) {
-            const cuuint64_t Pzc = (cuuint64_t)(Nz + 2 * P.g.H[2]), Pzw = Pzc + (walls ? 1 : 0);
-            bool ok = stage_map(&M.m[0], P.u.p, Px, Py, Pzc, C::TW, C::TH, (int)sizeof(T)) && stage_map(&M.m[1], P.v.p, Px, Py, Pzc, C::TW, C::TH, (int)sizeof(T)) &&
-                      stage_map(&M.m[2], P.w.p, Px, Py, Pzw, C::TW, C::TH, (int)sizeof(T));
-            for (int t = 0; ok && t < P.ntr; t++) ok = stage_map(&M.m[3 + t], P.c[t].p, Px, Py, Pzc, C::TW, C::TH, (int)sizeof(T));
-            if (!ok) L.use_tma = 0;
-        }
-        if ((long)L.ntx * L.nty * L.nkc > 2147483647L) return cudaErrorInvalidConfiguration;
-        dim3 grid((unsigned)(L.ntx * L.nty * L.nkc), (unsigned)L.npass), block(C::THREADS);
-        auto kern = P.g.dzc ? tendency_stage_kernel<T, N, W, NCL, LES, true> : tendency_stage_kernel<T, N, W, NCL, LES, false>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, block, C::SMEM_BYTES, st>>>(P, M, L);
-        *nlaunch += 1;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (walls) return launch_march<T, S, 8, 32, 4>(P, 1, st, nlaunch, 0, -1, 0, 1);
-        return cudaSuccess;
-    }
 }
 
 // mode: 0 auto, 1 generic, 2 marching (LDG), 3 marching with TMA-staged planes (4.. = tuning variants when built with -DOB_TI_EXPERIMENT)
@@ -366,14 +287,19 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     done = true;
     const bool whole = tx_lo == 0 && tx_hi < 0 && !invert;
     if constexpr (StageSel<T, S>::built) {
-        // the staged-ring kernel is built for the device division mode (rcp + Newton step, the default on this architecture)
-        if ((mode == 0 || mode == 8) && whole && fast && stage_applicable<T, S>(P)) {
-            bool les = false;
-            for (int m = 0; m < P.ncl; m++) les |= P.cl[m].kind != CL_SCALAR;
-            constexpr int W01 = StageSel<T, S>::W01, W2 = StageSel<T, S>::W2;
-            if (P.ncl == 0) return launch_stage<T, S, W01, 0, false>(P, st, sm_count, nlaunch);
-            if (P.ncl == 1) return les ? launch_stage<T, S, W01, 1, true>(P, st, sm_count, nlaunch) : launch_stage<T, S, W01, 1, false>(P, st, sm_count, nlaunch);
-            return launch_stage<T, S, W2, 2, true>(P, st, sm_count, nlaunch);
+        int les_kind = 0;
+        if ((mode == 0 || mode == 8) && whole && fast && stage_applicable<T, S>(P, les_kind)) {
+            cudaError_t e;
+            if (les_kind == 0) {
+                e = launch_stage_variant(P, S::n, STAGE_MODE_MT, P.ncl, 0, st, sm_count, nlaunch);
+            } else {
+                e = launch_stage_variant(P, S::n, STAGE_MODE_MN, P.ncl, les_kind, st, sm_count, nlaunch);
+                if (e == cudaSuccess && P.ntr > 0) e = launch_stage_variant(P, S::n, STAGE_MODE_TT, P.ncl, les_kind, st, sm_count, nlaunch);
+            }
+            if (e != cudaSuccess) return e;
+            // Bounded z: the wall-adjacent chunks take the marching kernel with the fallback chain
+            if (P.g.topo[2] == BOUNDED) return launch_march<T, S, 8, 32, 4>(P, 1, st, nlaunch, 0, -1, 0, 1);
+            return cudaSuccess;
         }
     }
     if (mode == 8) mode = 0;

@@ -16,7 +16,13 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 arch = ob.B200(0)
 fts = {"f64": (np.float64,), "f32": (np.float32,)}.get(os.environ.get("OB_FT", ""), (np.float64, np.float32))
 for ft in fts:
-    cfg = workload_config(n, ft=ft)
+    if os.environ.get("OB_CASE") == "les":   # config 3 physics (AMD + ScalarDiffusivity, T, S, FPlane, PPB) on an n^3 grid
+        from helpers import Config
+        cfg = Config((n, n, n), ((0, float(n)), (0, float(n)), (-n / 2.0, 0.0)), "PPB", advection=("weno", 5), ft=ft,
+                     closure=[("amd",), ("scalar", 1.05e-6, 1.46e-7)], buoyancy=("seawater", 9.80665, 2e-4, 8e-4), coriolis_f=1e-4, tracers=("T", "S"),
+                     bcs={"u": {"top": ("Flux", -2e-5)}, "T": {"top": ("Flux", 5e-5), "bottom": ("Gradient", 0.005)}, "S": {"top": ("Flux", 5e-8)}})
+    else:
+        cfg = workload_config(n, ft=ft)
     m = cfg.b200_model(arch)
     ob.set(m, **cfg.initial_conditions(2))
     names = {0: "auto", 1: "generic", 2: "marching", 3: "tma", 8: "stage", 9: "stage-alt"}
