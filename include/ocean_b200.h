@@ -217,6 +217,9 @@ int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first);
  * slabs are in flight (interleave_communication_and_computation.jl:36-74); 0 (default): exchange first, then one launch
  * -- measured faster at 256^3 per GPU on NVLink, where an exchange costs ~50 us and the split launch ~70 us */
 #define OB_OPT_OVERLAP_HALO 3
+/* OB_OPT_VECTOR_STREAMS = 1 (default): the update, Poisson-source and fused-projection kernels use 128-bit accesses
+ * (csrc/streaming.cuh); 0: the one-cell-per-thread forms (bit-identical results; kept for A/B checks) */
+#define OB_OPT_VECTOR_STREAMS 4
 int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t value);
 /* number of kernels/library launches issued by this model so far (bench.py's gpu_launches) */
 int32_t ob_launch_count(ob_model *m, int64_t *n);

@@ -23,6 +23,7 @@ OB_DIV_EXACT, OB_DIV_RCP_NEWTON = 0, 1
 OB_OPT_TENDENCY_KERNEL = 1
 OB_OPT_FUSE_PROJECTION = 2
 OB_OPT_OVERLAP_HALO = 3
+OB_OPT_VECTOR_STREAMS = 4
 OB_FIELD_U, OB_FIELD_V, OB_FIELD_W, OB_FIELD_PNHS, OB_FIELD_PHY = 0, 1, 2, 3, 4
 OB_FIELD_TRACER0, OB_FIELD_GN0, OB_FIELD_GM0, OB_FIELD_NUE0, OB_FIELD_KAPPAE0 = 16, 32, 48, 64, 80
 

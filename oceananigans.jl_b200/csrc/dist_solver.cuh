@@ -107,6 +107,23 @@ __global__ void __launch_bounds__(256) pull_x_to_z_kernel(const __grid_constant_
     S[t] = peers.p[r][(rank * nx + xl) + (long)NxG * (y + (long)Ny * zl)];     // peer r's z-local layout (Nx, Ny, nz)
 }
 
+// the same with one extra column in front of every row: column 0 of the output is global column rank*nx - 1 (periodic), the
+// last column of the west neighbour's slab -- every peer holds complete x lines in the z-local layout, so the projection's
+// west neighbour of p comes along with the transposition instead of through a halo exchange
+template <typename C>
+__global__ void __launch_bounds__(256) pull_x_to_z_west_kernel(const __grid_constant__ PeerPtrs<C> peers, C *__restrict__ S, int nx, int NxG, int Ny,
+                                                               int nz, int Nz, int rank) {
+    const int nx1 = nx + 1;
+    const long n = (long)nx1 * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int xl = (int)(t % nx1), y = (int)((t / nx1) % Ny), z = (int)(t / ((long)nx1 * Ny));
+    const int r = z / nz, zl = z - r * nz;
+    int xg = rank * nx + xl - 1;
+    if (xg < 0) xg += NxG;
+    S[t] = peers.p[r][xg + (long)NxG * (y + (long)Ny * zl)];
+}
+
 // Stream-ordered barrier across the ranks without a collective: lane r publishes this rank's epoch into peer r's flag
 // array (release store over NVLink) and then waits until peer r's epoch has arrived in the local array.
 struct PeerFlags { int *p[OB_MAX_PEERS]; };
@@ -173,6 +190,12 @@ struct DistSolverT : ob_solver {
     ob::PeerFlags peerF;
     int bar_epoch = 0;
     C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
+    // west-column mode (enable_west_column): the closing transposition writes rows of nx + 1 columns into S2 and the inverse z
+    // transform runs on those (Rr2: its real output when zr)
+    bool west = false;
+    C *S2 = nullptr, *buf_a2 = nullptr;
+    T *Rr2 = nullptr;
+    cufftHandle plan_zc2r2 = 0, plan_z2 = 0;
     T *lam[3] = {nullptr, nullptr, nullptr};
     C *tw_f = nullptr, *tw_b = nullptr;          // z DCT twiddles (Bounded regular z)
     T *diag = nullptr, *lower = nullptr, *tscr = nullptr;
@@ -354,6 +377,36 @@ struct DistSolverT : ob_solver {
         use_ipc = ok != 0;
         return OB_OK;
     }
+    bool enable_west_column() override {
+        if (west) return true;
+        if (!zx || !use_ipc || getenv("OB_DIST_NO_WEST_COLUMN")) return false;
+        const int nx1 = nx + 1;
+        const long n1 = (long)nx1 * N[1] * NzT;
+        if (cudaMalloc(&S2, sizeof(C) * n1) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaMemsetAsync(S2, 0, sizeof(C) * n1, ctx->stream);
+        int nzz[1] = {N[2]};
+        bool ok = true;
+        if (zr) {
+            constexpr cufftType BWD = std::is_same<T, double>::value ? CUFFT_Z2D : CUFFT_C2R;
+            int nre[1] = {N[2]}, nco[1] = {Nzh};
+            ok = cudaMalloc(&Rr2, sizeof(T) * (long)nx1 * N[1] * N[2]) == cudaSuccess &&
+                 cufftPlanMany(&plan_zc2r2, 1, nzz, nco, nx1 * N[1], 1, nre, nx1 * N[1], 1, BWD, nx1 * N[1]) == CUFFT_SUCCESS &&
+                 cufftSetStream(plan_zc2r2, ctx->stream) == CUFFT_SUCCESS;
+        } else {
+            ok = cufftPlanMany(&plan_z2, 1, nzz, nzz, nx1 * N[1], 1, nzz, nx1 * N[1], 1, CT, nx1 * N[1]) == CUFFT_SUCCESS &&
+                 cufftSetStream(plan_z2, ctx->stream) == CUFFT_SUCCESS;
+            if (ok && topo[2] == OB_BOUNDED) ok = cudaMalloc(&buf_a2, sizeof(C) * n1) == cudaSuccess;
+        }
+        if (!ok) { cudaGetLastError(); return false; }
+        west = true;
+        return true;
+    }
+    const void *solution() override {
+        if (!west) return storage();
+        return zr ? (const void *)(Rr2 + 1) : (const void *)(S2 + 1);
+    }
+    long solution_ldx() const override { return west ? nx + 1 : nx; }
+    bool has_west_column() const override { return west; }
     // stream-ordered barrier across the ranks
     int32_t barrier() {
         ipc_barrier_kernel<<<1, 32, 0, ctx->stream>>>(peerF, d_bflags, R, rank, ++bar_epoch);
@@ -375,6 +428,9 @@ struct DistSolverT : ob_solver {
         if (has_x) cufftDestroy(plan_x);
         if (has_xy) cufftDestroy(plan_xy);
         if (zr) { cufftDestroy(plan_zr2c); cufftDestroy(plan_zc2r); cudaFree(Rr); }
+        if (plan_zc2r2) cufftDestroy(plan_zc2r2);
+        if (plan_z2) cufftDestroy(plan_z2);
+        cudaFree(S2); cudaFree(buf_a2); cudaFree(Rr2);
     }
     void *storage() override { return zr ? (void *)Rr : (void *)S; }
     double scale() override { return scale_; }
@@ -430,6 +486,30 @@ struct DistSolverT : ob_solver {
             OB_TRY(exec(plan_xy, Tt, CUFFT_FORWARD));
             eigen_divide_zslab_kernel<T, C><<<nb, 256, 0, st>>>(Tt, lam[0], lam[1], lam[2], NxG, N[1], nz, rank * nz, zr ? Nzh : N[2], rank == 0 ? 1 : 0);
             OB_TRY(exec(plan_xy, Tt, CUFFT_INVERSE));
+            if (west) {
+                // closing transposition with the west neighbour's last column in front of every row, inverse z transform on
+                // rows of nx + 1 columns
+                const int nx1 = nx + 1;
+                const long n1 = (long)nx1 * N[1] * NzT;
+                const unsigned nb1 = nblk(n1, 256);
+                OB_TRY(barrier());
+                pull_x_to_z_west_kernel<C><<<nb1, 256, 0, st>>>(peerT, S2, nx, NxG, N[1], nz, NzT, rank);
+                launches += 3;
+                if (z_dct) {
+                    twiddle_bwd_kernel<T, C><<<nb1, 256, 0, st>>>(S2, buf_a2, tw_b, nx1, N[1], N[2], 2);
+                    OB_TRY(exec(plan_z2, buf_a2, CUFFT_INVERSE));
+                    unpermute_kernel<C><<<nb1, 256, 0, st>>>(buf_a2, S2, nx1, N[1], N[2], 2);
+                    launches += 2;
+                } else if (zr) {
+                    launches++;
+                    if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2D(plan_zc2r2, S2, Rr2));
+                    else CUFFT_TRY(cufftExecC2R(plan_zc2r2, S2, Rr2));
+                } else {
+                    OB_TRY(exec(plan_z2, S2, CUFFT_INVERSE));
+                }
+                CUDA_TRY(cudaGetLastError());
+                return OB_OK;
+            }
             if (use_ipc) {
                 OB_TRY(barrier());        // every peer's inverse (x, y) transform is complete (and its forward pull long done)
                 pull_x_to_z_kernel<C><<<nb, 256, 0, st>>>(peerT, S, nx, NxG, N[1], nz, NzT, rank);

@@ -364,6 +364,18 @@ struct UpdateP {
     int do_cache;   // also write G⁻ = Gⁿ
     T dt, gamma, zeta, chi;
 };
+// The update of one value, rounded operation by operation as the reference's kernels are (no @muladd there, and Julia does not
+// contract): shared by update_kernel and its 128-bit form so that the two agree bit for bit whatever the compiler would fuse.
+//   mode 0: U += Δt γ¹ G¹ ((Δt γ¹) first);  mode 1: U += Δt (γ Gⁿ + ζ G⁻);  mode 2: U += Δt ((3/2 + χ) Gⁿ - (1/2 + χ) G⁻ not_euler)
+template <typename T>
+__device__ __forceinline__ T updated_value(const UpdateP<T> &P, T u, T gn, T gm) {
+    if (P.mode == 0) return add_rn(u, mul_rn(mul_rn(P.dt, P.gamma), gn));
+    if (P.mode == 1) return add_rn(u, mul_rn(P.dt, add_rn(mul_rn(P.gamma, gn), mul_rn(P.zeta, gm))));
+    const T a = T(1.5) + P.chi, b = T(0.5) + P.chi;
+    const bool not_euler = P.chi != T(-0.5);
+    const T G = sub_rn(mul_rn(a, gn), not_euler ? mul_rn(b, gm) : T(0));
+    return add_rn(u, mul_rn(P.dt, G));
+}
 template <typename T>
 __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ UpdateP<T> P) {
     const int f = blockIdx.y;
@@ -375,16 +387,8 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Upd
     const bool active = (i >= P.lo[f][0]) & (j >= P.lo[f][1]) & (k >= P.lo[f][2]);
     if (active) {
         T &u = P.U[f](i, j, k);
-        if (P.mode == 0) {
-            u += P.dt * P.gamma * gn;
-        } else if (P.mode == 1) {
-            u += P.dt * (P.gamma * gn + P.zeta * P.Gm[f].p[im]);
-        } else {
-            const T a = T(1.5) + P.chi, b = T(0.5) + P.chi;
-            const bool not_euler = P.chi != T(-0.5);
-            T G = not_euler ? a * gn - b * P.Gm[f].p[im] : a * gn - T(0);
-            u += P.dt * G;
-        }
+        const bool need_gm = P.mode == 1 || (P.mode == 2 && P.chi != T(-0.5));
+        u = updated_value(P, u, gn, need_gm ? P.Gm[f].p[im] : T(0));
     }
     if (P.do_cache) P.Gm[f].p[im] = gn;
 }
@@ -417,18 +421,26 @@ struct SourceP {
     int cplx;  // write complex (re, 0) pairs instead of reals
     int zperm; // write level k at the Makhoul-permuted position (real DCT path): even k-1 -> (k-1)/2, odd -> Nz-1-(k-2)/2
 };
+// divᶜᶜᶜ of one cell from its six face values, every product and sum rounded separately (divergence_operators.jl has no @muladd)
+template <typename T>
+__device__ __forceinline__ T source_value(const SourceP<T> &P, T Ax, T Ay, T Az, T Vi, T dzc, T u0, T u1, T v0, T v1, T w0, T w1) {
+    const T ddx = P.g.topo[0] == FLAT ? T(0) : sub_rn(mul_rn(Ax, u1), mul_rn(Ax, u0));
+    const T ddy = P.g.topo[1] == FLAT ? T(0) : sub_rn(mul_rn(Ay, v1), mul_rn(Ay, v0));
+    const T ddz = P.g.topo[2] == FLAT ? T(0) : sub_rn(mul_rn(Az, w1), mul_rn(Az, w0));
+    T div = mul_rn(Vi, add_rn(add_rn(ddx, ddy), ddz));
+    if (P.times_dz) div = mul_rn(dzc, div);
+    return div;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) source_term_kernel(const __grid_constant__ SourceP<T> P) {
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const T dzc = P.g.dzC(k);
     const T Ax = P.g.dy * dzc, Ay = P.g.dx * dzc, Az = P.g.dx * P.g.dy;
-    const T ddx = P.g.topo[0] == FLAT ? T(0) : Ax * P.u.ld(i + 1, j, k) - Ax * P.u.ld(i, j, k);
-    const T ddy = P.g.topo[1] == FLAT ? T(0) : Ay * P.v.ld(i, j + 1, k) - Ay * P.v.ld(i, j, k);
-    const T ddz = P.g.topo[2] == FLAT ? T(0) : Az * P.w.ld(i, j, k + 1) - Az * P.w.ld(i, j, k);
-    const T Vi = P.g.rVc(k);
-    T div = Vi * (ddx + ddy + ddz);
-    if (P.times_dz) div = dzc * div;
+    // (Flat directions: the index stays put -- there is no halo to read -- and source_value() drops the term)
+    const int fx = P.g.topo[0] == FLAT ? 0 : 1, fy = P.g.topo[1] == FLAT ? 0 : 1, fz = P.g.topo[2] == FLAT ? 0 : 1;
+    const T div = source_value(P, Ax, Ay, Az, P.g.rVc(k), dzc, P.u.ld(i, j, k), P.u.ld(i + fx, j, k), P.v.ld(i, j, k), P.v.ld(i, j + fy, k),
+                               P.w.ld(i, j, k), P.w.ld(i, j, k + fz));
     const int kk = P.zperm ? makhoul_index(k - 1, P.g.N[2]) : k - 1;
     const long o = (i - 1) + (j - 1) * P.ldx + (long)kk * P.ldxy;
     if (P.cplx) { P.out[2 * o] = div; P.out[2 * o + 1] = T(0); }
@@ -467,9 +479,9 @@ __global__ void __launch_bounds__(256) pressure_correct_kernel(const __grid_cons
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const T pc = P.p.ld(i, j, k);
-    if (P.g.topo[0] != FLAT) P.u(i, j, k) -= (pc - P.p.ld(i - 1, j, k)) * P.g.rdx;
-    if (P.g.topo[1] != FLAT) P.v(i, j, k) -= (pc - P.p.ld(i, j - 1, k)) * P.g.rdy;
-    if (P.g.topo[2] != FLAT) P.w(i, j, k) -= (pc - P.p.ld(i, j, k - 1)) * P.g.rdzF(k);
+    if (P.g.topo[0] != FLAT) P.u(i, j, k) = sub_rn(P.u(i, j, k), mul_rn(sub_rn(pc, P.p.ld(i - 1, j, k)), P.g.rdx));
+    if (P.g.topo[1] != FLAT) P.v(i, j, k) = sub_rn(P.v(i, j, k), mul_rn(sub_rn(pc, P.p.ld(i, j - 1, k)), P.g.rdy));
+    if (P.g.topo[2] != FLAT) P.w(i, j, k) = sub_rn(P.w(i, j, k), mul_rn(sub_rn(pc, P.p.ld(i, j, k - 1)), P.g.rdzF(k)));
 }
 
 // K15 + K16 + rescale fused (single-device path of rk3_substep! / ab2_step!): reads the solver output directly,
@@ -483,6 +495,7 @@ struct CorrectFusedP {
     const T *sol;
     long ldx, ldxy;
     int cplx, zperm;
+    int west;   // the solver output has the west neighbour's column at i = 0 (distributed slab-x): no periodic wrap in x
     T scale, denom;
 };
 template <typename T>
@@ -495,11 +508,11 @@ __global__ void __launch_bounds__(256) correct_fused_kernel(const __grid_constan
         return mul_rn(P.cplx ? __ldg(P.sol + 2 * o) : __ldg(P.sol + o), P.scale);   // rounded like the stored p of the reference
     };
     // index of the lower neighbour along d: periodic wrap, or the cell itself where the no-flux halo mirrors it
-    auto lower = [&](int idx, int d) { return idx > 1 ? idx - 1 : (P.g.topo[d] == PERIODIC ? P.g.N[d] : 1); };
+    auto lower = [&](int idx, int d) { return (idx > 1 || (d == 0 && P.west)) ? idx - 1 : (P.g.topo[d] == PERIODIC ? P.g.N[d] : 1); };
     const T pc = S(i, j, k);
-    if (P.g.topo[0] != FLAT) P.u(i, j, k) -= sub_rn(pc, S(lower(i, 0), j, k)) * P.g.rdx;
-    if (P.g.topo[1] != FLAT) P.v(i, j, k) -= sub_rn(pc, S(i, lower(j, 1), k)) * P.g.rdy;
-    if (P.g.topo[2] != FLAT) P.w(i, j, k) -= sub_rn(pc, S(i, j, lower(k, 2))) * P.g.rdzF(k);
+    if (P.g.topo[0] != FLAT) P.u(i, j, k) = sub_rn(P.u(i, j, k), mul_rn(sub_rn(pc, S(lower(i, 0), j, k)), P.g.rdx));
+    if (P.g.topo[1] != FLAT) P.v(i, j, k) = sub_rn(P.v(i, j, k), mul_rn(sub_rn(pc, S(i, lower(j, 1), k)), P.g.rdy));
+    if (P.g.topo[2] != FLAT) P.w(i, j, k) = sub_rn(P.w(i, j, k), mul_rn(sub_rn(pc, S(i, j, lower(k, 2))), P.g.rdzF(k)));
     P.p(i, j, k) = pc / P.denom;
 }
 

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cmath>
 #include <string>
 #include <type_traits>
@@ -22,6 +23,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "streaming.cuh"
 #include "poisson.cuh"
 #include "stencils.cuh"
 #include "tendency.cuh"
@@ -257,6 +259,14 @@ struct ob_solver {
     virtual bool real_storage() const { return false; }
     // true: level k of storage() lives at the Makhoul-permuted position (real DCT path)
     virtual bool z_permuted() const { return false; }
+    // Distributed solvers can leave the solution with ONE EXTRA WEST COLUMN (the last column of the west neighbour's slab,
+    // taken along by the closing transposition), so that the projection can form dp/dx at i = 1 without a halo exchange of
+    // the pressure.  Off unless enabled; solution() then points at column i = 1 of rows of solution_ldx() elements (column
+    // i = 0 is one element -- one complex number for complex storage -- in front of every row).
+    virtual bool enable_west_column() { return false; }
+    virtual const void *solution() { return storage(); }
+    virtual long solution_ldx() const { return N[0]; }
+    virtual bool has_west_column() const { return false; }
 };
 
 template <typename T>
@@ -707,6 +717,7 @@ struct ob_model {
     int opt_overlap = 0;          // OB_OPT_OVERLAP_HALO: distributed update_state computes interior tendency tiles while x halos are in flight
                                   // (off by default: at 256^3 per GPU the split launch costs 0.2 ms/step more than the exchange it hides)
     int opt_fuse = 1;             // OB_OPT_FUSE_PROJECTION: 1 fused single-device projection, 0 the reference kernel sequence
+    int opt_vector = 1;           // OB_OPT_VECTOR_STREAMS: 1 128-bit forms of update / source / projection kernels (streaming.cuh), 0 one cell per thread
     double phase_ms[PH_COUNT] = {0};
     int64_t phase_calls[PH_COUNT] = {0};
     struct Ev { int phase; cudaEvent_t a, b; };
@@ -931,14 +942,26 @@ struct ModelT : ob_model {
     // ---- halos --------------------------------------------------------------------------------------------------
     // fill_halo_regions! for a list of fields: per direction ONE launch for all fields; Bounded directions first,
     // then Periodic (boundary_condition_ordering.jl:17-46,116-142; within a class the reference order is z, y, x).
-    int32_t fill_halos(const std::vector<int> &ids, bool fill_normal, bool defer_x = false) {
+    // Distributed runs: `x_ids` (when given) replaces `ids` for the west/east exchange -- the local y / z fills of a field and
+    // its exchange can then be issued at different times (x comes last in the reference order, so splitting it off is safe);
+    // fields queued in `pending_x_ids` join the next exchange.
+    std::vector<int> pending_x_ids;
+    int32_t fill_halos(const std::vector<int> &ids, bool fill_normal, bool defer_x = false, const std::vector<int> *x_ids = nullptr) {
         PhaseScope ps(this, PH_HALO);
         for (int pass = 0; pass < 2; pass++)
             for (int d = 2; d >= 0; d--) {
                 if (g.topo[d] == FLAT) continue;
                 const bool per = g.topo[d] == PERIODIC;
                 if ((pass == 0) == per) continue;
-                if (dist && d == 0) { OB_TRY(exchange_x_halos(ids, defer_x)); continue; }
+                if (dist && d == 0) {
+                    std::vector<int> xl = x_ids ? *x_ids : ids;
+                    if (!x_ids && !pending_x_ids.empty()) {
+                        for (int id : pending_x_ids) if (std::find(xl.begin(), xl.end(), id) == xl.end()) xl.push_back(id);
+                        pending_x_ids.clear();
+                    }
+                    if (!xl.empty()) OB_TRY(exchange_x_halos(xl, defer_x));
+                    continue;
+                }
                 size_t pos = 0;
                 while (pos < ids.size()) {
                     HaloBatch<T> B;
@@ -1281,7 +1304,23 @@ struct ModelT : ob_model {
             }
         return OB_OK;
     }
-    bool fused_substep() const { return !dist && opt_fuse != 0; }
+    // single device, or distributed with a solver that hands over the west neighbour's pressure column (dist_solver.cuh)
+    bool fused_substep() { return opt_fuse != 0 && (!dist || (p2p_halo && solver->enable_west_column())); }
+    // what the 128-bit kernels of streaming.cuh assume of the fields one thread touches: no Flat direction, 16-byte aligned
+    // base pointers, one alignment phase (same off / sy / sz modulo `v` elements; v == 2 also needs even pitches so that rows
+    // j+1 and levels k+1 keep the phase), a halo row in front of the first interior row
+    bool vector_ok(std::initializer_list<int> ids, int v) const {
+        if (!opt_vector || g.topo[0] == FLAT || g.topo[1] == FLAT || g.topo[2] == FLAT) return false;
+        if (g.H[0] < 1 || g.H[1] < 1 || g.N[0] < 8) return false;
+        const Fld<T> a = fld(*ids.begin());
+        for (int id : ids) {
+            const Fld<T> f = fld(id);
+            if (!F[id].ptr || ((uintptr_t)F[id].ptr & 15)) return false;
+            if (((f.off - a.off) % v) || ((f.sy - a.sy) % v) || ((f.sz - a.sz) % v)) return false;
+            if (v == 2 && ((f.sy & 1) || (f.sz & 1))) return false;
+        }
+        return true;
+    }
     int32_t launch_update(int mode, double dt, double gamma, double zeta, double chi, bool cache) {
         PhaseScope ps(this, PH_UPDATE);
         OB_TRY(flux_bc_tendencies());
@@ -1297,9 +1336,22 @@ struct ModelT : ob_model {
         for (int k = 0; k < 3; k++) P.N[k] = g.N[k];
         P.mode = mode; P.do_cache = cache ? 1 : 0;
         P.dt = (T)dt; P.gamma = (T)gamma; P.zeta = (T)zeta; P.chi = (T)chi;
-        const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
-        dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], P.nfields);
-        update_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+        constexpr int V = Vec16<T>::V;
+        bool vec = true;
+        for (int n = 0; vec && n < P.nfields; n++) {
+            const int fid = n < 3 ? n : OB_FIELD_TRACER0 + (n - 3);
+            vec = vector_ok({fid, OB_FIELD_GN0 + n, OB_FIELD_GM0 + n}, V);
+        }
+        if (vec) {
+            constexpr int ROWS = 2;
+            const int ngx = (g.N[0] + V - 1) / V + 1;
+            dim3 grid(nblk(ngx, 128) * (unsigned)((g.N[1] + ROWS - 1) / ROWS) * (unsigned)g.N[2], P.nfields);
+            update_vec_kernel<T, ROWS><<<grid, 128, 0, ctx->stream>>>(P, ngx);
+        } else {
+            const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
+            dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], P.nfields);
+            update_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+        }
         launches++;
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
@@ -1312,7 +1364,9 @@ struct ModelT : ob_model {
             OB_TRY(compute_pressure_correction(dtau));
             return make_pressure_correction(dtau);
         }
-        OB_TRY(fill_halos({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W}, true));
+        // distributed: the divergence reads u(Nx+1) only -- v and w travel with the next exchange of the prognostic fields
+        const std::vector<int> x_u = {OB_FIELD_U}, x_none;
+        OB_TRY(fill_halos({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W}, true, false, dist ? &x_u : nullptr));
         const int bs = g.N[0] >= 256 ? 256 : g.N[0] >= 128 ? 128 : g.N[0] >= 64 ? 64 : 32;
         dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], 1);
         {
@@ -1325,7 +1379,13 @@ struct ModelT : ob_model {
             P.times_dz = solver->tridiag ? 1 : 0;
             P.cplx = solver->real_storage() ? 0 : 1;
             P.zperm = solver->z_permuted() ? 1 : 0;
-            source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            if (vector_ok({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W}, 2)) {
+                constexpr int ROWS = 2;
+                const int ngx = g.N[0] / 2 + 1;
+                source_pair_kernel<T, ROWS><<<nblk(ngx, 128) * (unsigned)((g.N[1] + ROWS - 1) / ROWS) * (unsigned)g.N[2], 128, 0, ctx->stream>>>(P, ngx);
+            } else {
+                source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            }
             launches++;
         }
         {
@@ -1339,16 +1399,26 @@ struct ModelT : ob_model {
             CorrectFusedP<T> P;
             memset(&P, 0, sizeof(P));
             P.g = g; P.u = fld(OB_FIELD_U); P.v = fld(OB_FIELD_V); P.w = fld(OB_FIELD_W); P.p = fld(OB_FIELD_PNHS);
-            P.sol = (const T *)solver->storage();
-            P.ldx = g.N[0]; P.ldxy = (long)g.N[0] * g.N[1];
+            P.sol = (const T *)solver->solution();
+            P.ldx = solver->solution_ldx(); P.ldxy = P.ldx * g.N[1];
             P.cplx = solver->real_storage() ? 0 : 1;
             P.zperm = solver->z_permuted() ? 1 : 0;
+            P.west = solver->has_west_column() ? 1 : 0;
             P.scale = (T)solver->scale();
             P.denom = std::max(std::numeric_limits<T>::epsilon(), (T)dtau);
-            correct_fused_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            if (vector_ok({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W, OB_FIELD_PNHS}, 2)) {
+                constexpr int ROWS = 2;
+                const int ngx = g.N[0] / 2 + 1;
+                correct_pair_kernel<T, ROWS><<<nblk(ngx, 128) * (unsigned)((g.N[1] + ROWS - 1) / ROWS) * (unsigned)g.N[2], 128, 0, ctx->stream>>>(P, ngx);
+            } else {
+                correct_fused_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            }
             launches++;
         }
-        OB_TRY(fill_halos({OB_FIELD_PNHS}, true));   // halos of the final p: copies of interior values, as after the reference's rescale
+        // halos of the final p: copies of interior values, as after the reference's rescale.  Distributed: nothing reads the x
+        // halos of p before the next update_state!, so its slabs join that exchange instead of synchronising the ranks here
+        OB_TRY(fill_halos({OB_FIELD_PNHS}, true, false, dist ? &x_none : nullptr));
+        if (dist) pending_x_ids.push_back(OB_FIELD_PNHS);
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }
@@ -1426,7 +1496,13 @@ struct ModelT : ob_model {
             P.times_dz = solver->tridiag ? 1 : 0;
             P.cplx = solver->real_storage() ? 0 : 1;
             P.zperm = solver->z_permuted() ? 1 : 0;
-            source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            if (vector_ok({OB_FIELD_U, OB_FIELD_V, OB_FIELD_W}, 2)) {
+                constexpr int ROWS = 2;
+                const int ngx = g.N[0] / 2 + 1;
+                source_pair_kernel<T, ROWS><<<nblk(ngx, 128) * (unsigned)((g.N[1] + ROWS - 1) / ROWS) * (unsigned)g.N[2], 128, 0, ctx->stream>>>(P, ngx);
+            } else {
+                source_term_kernel<T><<<grid, bs, 0, ctx->stream>>>(P);
+            }
             launches++;
         }
         {
@@ -1604,6 +1680,7 @@ extern "C" int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t valu
         case OB_OPT_TENDENCY_KERNEL: m->opt_tendency_kernel = value; return OB_OK;
         case OB_OPT_FUSE_PROJECTION: m->opt_fuse = value; return OB_OK;
         case OB_OPT_OVERLAP_HALO: m->opt_overlap = value; return OB_OK;
+        case OB_OPT_VECTOR_STREAMS: m->opt_vector = value; return OB_OK;
     }
     return fail(OB_ERR_INVALID, "unknown option %d", option);
 }

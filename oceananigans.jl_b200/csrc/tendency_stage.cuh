@@ -309,22 +309,19 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
     // ---- what this pass stages and computes (CTA-uniform) ----------------------------------------------------------------
     // tendency slot q: active?  MT: q = 0..2 momentum (pass 0), q = 3 tracer `pass`;  MN: q = 0..2;  TT: q = 0, 1 tracers 2*pass, 2*pass+1
     const int trA = MODE == STAGE_MT ? pass : 2 * pass, trB = 2 * pass + 1;
-    bool act[4];
+    const bool a012 = MODE == STAGE_MT ? pass == 0 : true;
+    const bool act[4] = {MODE == STAGE_TT ? true : a012, MODE == STAGE_TT ? trB < P.ntr : a012, MODE == STAGE_TT ? false : a012, MODE == STAGE_MT ? trA < P.ntr : false};
     const T *slotp[4];   // parent array of each slot (cp.async path, and which slots exist)
     if constexpr (MODE == STAGE_MT) {
-        act[0] = act[1] = act[2] = pass == 0; act[3] = trA < P.ntr;
         slotp[0] = P.u.p; slotp[1] = P.v.p; slotp[2] = P.w.p; slotp[3] = act[3] ? P.c[trA].p : nullptr;
     } else if constexpr (MODE == STAGE_MN) {
-        act[0] = act[1] = act[2] = true; act[3] = false;
         slotp[0] = P.u.p; slotp[1] = P.v.p; slotp[2] = P.w.p; slotp[3] = P.nue[0].p;
     } else {
-        act[0] = true; act[1] = trB < P.ntr; act[2] = act[3] = false;
         slotp[0] = P.c[trA].p; slotp[1] = KL == CL_AMD ? P.kappae[0][trA].p : P.nue[0].p;
         slotp[2] = act[1] ? P.c[trB].p : nullptr; slotp[3] = act[1] ? (KL == CL_AMD ? P.kappae[0][trB].p : P.nue[0].p) : nullptr;
     }
-    int nfields = 0;
-#pragma unroll
-    for (int f = 0; f < 4; f++) nfields += slotp[f] != nullptr;
+    const bool have[4] = {true, true, MODE != STAGE_TT || act[1], MODE == STAGE_MT ? act[3] : MODE == STAGE_MN ? true : act[1]};   // which slots are staged
+    const int nfields = (int)have[0] + (int)have[1] + (int)have[2] + (int)have[3];
 
     // tile origin in parent coordinates (0-based); the box starts on a 16-byte boundary of the row
     const int cxu = i0 - N + gg.H[0] - 1;
@@ -336,9 +333,14 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
         unsigned char *dst = smem + s * C::LEVEL_BYTES;
         mbar_expect_tx(&full[s], nfields * C::BOX_BYTES);
         const int cz = Lv + gg.H[2] - 1;
+        // (static indices into the __grid_constant__ maps: a run-time index would make the compiler copy them to local memory)
 #pragma unroll
-        for (int f = 0; f < 4; f++)
-            if (slotp[f]) tma_load_3d(dst + f * C::PLANE_BYTES, &M.m[pass][f], &full[s], cx0, cy0, cz);
+        for (int p = 0; p < OB_STAGE_MAXPASS; p++) {
+            if (p != pass) continue;
+#pragma unroll
+            for (int f = 0; f < 4; f++)
+                if (have[f]) tma_load_3d(dst + f * C::PLANE_BYTES, &M.m[p][f], &full[s], cx0, cy0, cz);
+        }
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < D; s++) { mbar_init(&full[s], use_tma ? 1 : nfields * 32); mbar_init(&empty[s], W + C::NH); done[s] = 0; }
@@ -389,7 +391,9 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
     int fed = kfirst - 1;
     auto feed = [&](bool blocking, int upto) {
         const int Px = P.u.sy, Py = (int)(P.u.sz / P.u.sy);
-        const T *base = hq == 0 ? slotp[0] : hq == 1 ? slotp[1] : hq == 2 ? slotp[2] : slotp[3];
+        const T *base;
+        if constexpr (MODE == STAGE_MT) base = (hq == 0 ? P.u : hq == 1 ? P.v : hq == 2 ? P.w : P.c[trA]).p;
+        else base = hq == 0 ? slotp[0] : hq == 1 ? slotp[1] : hq == 2 ? slotp[2] : slotp[3];
         while (fed < upto && fed < klast) {
             const int Lv = fed + 1, n = Lv - kfirst, s = n % D;
             if (n >= D) {
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
             fed = Lv;
         }
     };
-    const bool feeder = !use_tma && helper && (hq == 0 ? slotp[0] : hq == 1 ? slotp[1] : hq == 2 ? slotp[2] : slotp[3]) != nullptr;
+    const bool feeder = !use_tma && helper && (hq == 0 ? have[0] : hq == 1 ? have[1] : hq == 2 ? have[2] : have[3]);
     if (feeder) feed(true, kfirst + N - 1);
     for (int n = 0; n < N; n++) mbar_wait(&full[n], 0);
 
@@ -435,9 +439,9 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
         for (int d = 0; d <= N; d++) { int s = sk + d; if (s >= D) s -= D; lev[d] = ring + s * C::LEVEL; }
         const int e = k - k0, xs = e & 1, xp = (e >> 1) & 1;
         const bool full_level = k >= k0;
-        View VY, VX;
+        View VY;
 #pragma unroll
-        for (int d = 0; d <= N; d++) { VY.pl[d] = lev[d] + ownY; VX.pl[d] = lev[d] + ownX; }
+        for (int d = 0; d <= N; d++) VY.pl[d] = lev[d] + ownY;
         Terms FY{P, g, VY, h[0], h[1], h[2], h[3], eoY + k * g.sz, k, trA, 0, ixp, iyp};
         // TT: the advecting velocities at the own points, from global memory (u at the west-flux point, v at the south-flux
         // point, w one level up)
@@ -469,6 +473,9 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
             }
             if (helper) {
                 // ---- helper phase B: west fluxes at the tile's east edge, lanes = rows -----------------------------------
+                View VX;
+#pragma unroll
+                for (int d = 0; d <= N; d++) VX.pl[d] = lev[d] + ownX;
                 Terms FX{P, g, VX, h[0], h[1], h[2], h[3], eoX + k * g.sz, k, trA, 0, ixp, iyp};
                 auto west_edge = [&](auto qtag) {
                     constexpr int Q = decltype(qtag)::value;
@@ -550,8 +557,8 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
         // level k becomes k-1: history shift (helpers, MT / MN: u at the west-flux point, v at the south-flux point) and (MN) the
         // face interpolants of nu_e that next level's wx / wy need
         if constexpr (MODE == STAGE_MN) {
-            ixp = T(0.5) * (VX.at(3, 0, -1, 0) + VX.at(3, 0, 0, 0));
-            iyp = T(0.5) * (VY.at(3, 0, 0, -1) + VY.at(3, 0, 0, 0));
+            ixp = T(0.5) * (lev[0][3 * PL + ownX - 1] + lev[0][3 * PL + ownX]);
+            iyp = T(0.5) * (lev[0][3 * PL + ownY - TW] + lev[0][3 * PL + ownY]);
         }
 #pragma unroll
         for (int f = 0; f < 4; f++) {
