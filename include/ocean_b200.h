@@ -117,7 +117,7 @@ typedef struct {
 typedef struct {
     ob_grid_desc grid;
     int32_t advection_kind;   /* ob_advection_kind */
-    int32_t advection_order;  /* WENO: 3,5,7,9 ; Centered: 2,4,6 (anything else: OB_ERR_UNSUPPORTED) */
+    int32_t advection_order;  /* WENO: 3,5,7,9,11 ; Centered: 2,4,...,12 -- the buffers 1..6 of src/Advection/Advection.jl:52 (anything else: OB_ERR_UNSUPPORTED) */
     int32_t weno_division;    /* ob_weno_division */
     int32_t n_closures;
     ob_closure_desc closures[OB_MAX_CLOSURES];

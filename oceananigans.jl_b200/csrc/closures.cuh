@@ -70,11 +70,22 @@ template <typename T>
 __device__ __forceinline__ T interp4(const T (&f)[2][2]) {  // ℑ_outer(ℑ_inner f), f[inner][outer]
     return T(0.5) * (T(0.5) * (f[0][0] + f[1][0]) + T(0.5) * (f[0][1] + f[1][1]));
 }
+// Per-level metric ratios of the normalised gradients (velocity_tracer_gradients.jl:126-260: Δᶠxᶜᶜᶜ = 2Δx etc.), tabulated on the
+// host with the reference's own IEEE divisions: the kernel would otherwise evaluate 18 Float64 divisions per cell (a third of
+// its instructions) to re-derive numbers that depend on the level only.  Row r of `tab` holds Nz + 2 values for k = 0 .. Nz+1:
+//   0: fz = 2 Δzᶜ(k)   1: fx / fz   2: fz / fx   3: fy / fz   4: fz / fy   5: Δ² = 3 / (1/fx² + 1/fy² + 1/fz²)
+template <typename T>
+struct AmdGeom {
+    const T *tab;
+    int stride;      // Nz + 2
+    T rxy, ryx;      // fx / fy, fy / fx
+    __device__ __forceinline__ T at(int r, int k) const { return __ldg(tab + r * stride + k); }
+};
 #ifndef OB_AMD_MINB
 #define OB_AMD_MINB 4   // resident CTAs per SM the register budget is set for (tuning knob; see profiles/r2_les_kernels.txt)
 #endif
 template <typename T>
-__global__ void __launch_bounds__(128, OB_AMD_MINB) amd_kernel(const __grid_constant__ TendP<T> P, int m) {
+__global__ void __launch_bounds__(128, OB_AMD_MINB) amd_kernel(const __grid_constant__ TendP<T> P, int m, const AmdGeom<T> A) {
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const GridD<T> &g = P.g;
@@ -94,14 +105,15 @@ __global__ void __launch_bounds__(128, OB_AMD_MINB) amd_kernel(const __grid_cons
     auto at = [&](const Cur &f, int a, int b, int c) -> T { return __ldg(f.p + (a * ox + b * f.oy + c * f.oz)); };
     const T rdx = g.rdx, rdy = g.rdy;
     const T fx = 2 * g.dx, fy = 2 * g.dy;
-    T fz[2], rdzf[2];
+    T fz[2], rdzf[2], rxz[2], rzx[2], ryz[2], rzy[2];
 #pragma unroll
-    for (int c = 0; c < 2; c++) { const int kc = g.topo[2] == FLAT ? k : k + c; fz[c] = 2 * g.dzC(kc); rdzf[c] = g.rdzF(kc); }
-    const T rxy = fx / fy, ryx = fy / fx;
-    T rxz[2], rzx[2], ryz[2], rzy[2];
-#pragma unroll
-    for (int c = 0; c < 2; c++) { rxz[c] = fx / fz[c]; rzx[c] = fz[c] / fx; ryz[c] = fy / fz[c]; rzy[c] = fz[c] / fy; }
-    const T delta2 = 3 / (1 / (fx * fx) + 1 / (fy * fy) + 1 / (fz[0] * fz[0]));
+    for (int c = 0; c < 2; c++) {
+        const int kc = g.topo[2] == FLAT ? k : k + c;
+        rdzf[c] = g.rdzF(kc);
+        fz[c] = A.at(0, kc); rxz[c] = A.at(1, kc); rzx[c] = A.at(2, kc); ryz[c] = A.at(3, kc); rzy[c] = A.at(4, kc);
+    }
+    const T rxy = A.rxy, ryx = A.ryx;
+    const T delta2 = A.at(5, k);
     // ccc
     const T ux = (at(cu, 1, 0, 0) - at(cu, 0, 0, 0)) * rdx;
     const T vy = (at(cv, 0, 1, 0) - at(cv, 0, 0, 0)) * rdy;

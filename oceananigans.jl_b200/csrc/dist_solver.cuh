@@ -102,9 +102,14 @@ __global__ void __launch_bounds__(256) pull_x_to_z_kernel(const __grid_constant_
     const long n = (long)nx * Ny * Nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const int xl = (int)(t % nx), y = (int)((t / nx) % Ny), z = (int)(t / ((long)nx * Ny));
-    const int r = z / nz, zl = z - r * nz;
-    S[t] = peers.p[r][(rank * nx + xl) + (long)NxG * (y + (long)Ny * zl)];     // peer r's z-local layout (Nx, Ny, nz)
+    // the slowest index walks the peers starting from this rank, so that at any moment the ranks read from DIFFERENT peers
+    // (walking 0 .. R-1 everywhere makes all of them pull on one peer's links at a time)
+    const int xl = (int)(t % nx), y = (int)((t / nx) % Ny), q = (int)(t / ((long)nx * Ny));
+    const int R = Nz / nz;
+    int r = rank + q / nz;
+    if (r >= R) r -= R;
+    const int zl = q % nz;
+    S[xl + (long)nx * (y + (long)Ny * (r * nz + zl))] = peers.p[r][(rank * nx + xl) + (long)NxG * (y + (long)Ny * zl)];     // peer r's z-local layout (Nx, Ny, nz)
 }
 
 // the same with one extra column in front of every row: column 0 of the output is global column rank*nx - 1 (periodic), the
@@ -117,11 +122,70 @@ __global__ void __launch_bounds__(256) pull_x_to_z_west_kernel(const __grid_cons
     const long n = (long)nx1 * Ny * Nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const int xl = (int)(t % nx1), y = (int)((t / nx1) % Ny), z = (int)(t / ((long)nx1 * Ny));
-    const int r = z / nz, zl = z - r * nz;
+    const int xl = (int)(t % nx1), y = (int)((t / nx1) % Ny), q = (int)(t / ((long)nx1 * Ny));
+    const int R = Nz / nz;
+    int r = rank + q / nz;   // peers in rotated order (see pull_x_to_z_kernel)
+    if (r >= R) r -= R;
+    const int zl = q % nz;
     int xg = rank * nx + xl - 1;
     if (xg < 0) xg += NxG;
-    S[t] = peers.p[r][xg + (long)NxG * (y + (long)Ny * zl)];
+    S[xl + (long)nx1 * (y + (long)Ny * (r * nz + zl))] = peers.p[r][xg + (long)NxG * (y + (long)Ny * zl)];
+}
+
+// Level-chunked forms of the two pulls and of the eigenvalue division (pipelined solve: the transposition of one chunk of
+// local levels overlaps the (x, y) transforms of another).  Levels zl0 .. zl0 + len - 1 of the z-local layout.
+// Both are grid-stride kernels launched with a bounded number of CTAs (4 loads in flight per thread): they run on the low-
+// priority stream next to the transforms of the main stream and must not fill every CTA slot of the device.
+template <typename C>
+__global__ void __launch_bounds__(256) pull_z_to_x_chunk_kernel(const __grid_constant__ PeerPtrs<C> peers, C *__restrict__ Tz, int nx, int NxG, int Ny,
+                                                                int nz, int rank, int zl0, int len) {
+    const long plane = (long)NxG * Ny, n = plane * len, stride = (long)gridDim.x * blockDim.x;
+    for (long t0 = (long)blockIdx.x * blockDim.x + threadIdx.x; t0 < n; t0 += 4 * stride) {
+        C v[4];
+        long dst[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const long t = t0 + q * stride;
+            dst[q] = -1;
+            if (t < n) {
+                const int x = (int)(t % NxG), y = (int)((t / NxG) % Ny), zl = zl0 + (int)(t / plane);
+                const int r = x / nx, xl = x - r * nx;
+                dst[q] = x + (long)NxG * (y + (long)Ny * zl);
+                v[q] = peers.p[r][xl + (long)nx * (y + (long)Ny * (rank * nz + zl))];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (dst[q] >= 0) Tz[dst[q]] = v[q];
+    }
+}
+// rows of nx + west columns (west = 1: the west neighbour's last column in front, see pull_x_to_z_west_kernel)
+template <typename C>
+__global__ void __launch_bounds__(256) pull_x_to_z_chunk_kernel(const __grid_constant__ PeerPtrs<C> peers, C *__restrict__ S, int nx, int NxG, int Ny,
+                                                                int nz, int R, int rank, int west, int zl0, int len) {
+    const int nxo = nx + west;
+    const long row = (long)nxo * Ny, n = row * len * R, stride = (long)gridDim.x * blockDim.x;
+    for (long t0 = (long)blockIdx.x * blockDim.x + threadIdx.x; t0 < n; t0 += 4 * stride) {
+        C v[4];
+        long dst[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            const long t = t0 + q4 * stride;
+            dst[q4] = -1;
+            if (t < n) {
+                const int xl = (int)(t % nxo), y = (int)((t / nxo) % Ny);
+                const int q = (int)(t / row);            // (peer in rotated order, level of the chunk)
+                int r = rank + q / len;
+                if (r >= R) r -= R;
+                const int zl = zl0 + q % len;
+                int xg = rank * nx + xl - west;
+                if (xg < 0) xg += NxG;
+                dst[q4] = xl + (long)nxo * (y + (long)Ny * (r * nz + zl));
+                v[q4] = peers.p[r][xg + (long)NxG * (y + (long)Ny * zl)];
+            }
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) if (dst[q4] >= 0) S[dst[q4]] = v[q4];
+    }
 }
 
 // Stream-ordered barrier across the ranks without a collective: lane r publishes this rank's epoch into peer r's flag
@@ -190,6 +254,16 @@ struct DistSolverT : ob_solver {
     ob::PeerFlags peerF;
     int bar_epoch = 0;
     C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
+    // pipelined solve (IPC pulls): the local levels of the z-local layout are split into chunks; a second stream runs the pulls
+    // (and the per-chunk barriers of the closing transposition) while the main stream transforms the chunks already there
+    static constexpr int MAXCH = 4;
+    bool pipelined = false;
+    int nch = 0, ch0[MAXCH], chlen[MAXCH];
+    cufftHandle plan_xy_ch[2] = {0, 0};   // plans for the two chunk lengths that occur
+    int plan_xy_len[2] = {0, 0};
+    cudaStream_t st2 = nullptr;
+    int pull_ctas = 592;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_pull[MAXCH], ev_fft[MAXCH];
     // west-column mode (enable_west_column): the closing transposition writes rows of nx + 1 columns into S2 and the inverse z
     // transform runs on those (Rr2: its real output when zr)
     bool west = false;
@@ -315,6 +389,11 @@ struct DistSolverT : ob_solver {
             has_x = true;
         }
         if (zx && !getenv("OB_DIST_NO_IPC")) OB_TRY(setup_ipc());
+        // pipelined transposes pay where the pulls are NVLink-bound (7/8 of a pull is remote on 8 ranks); on 2 ranks they are
+        // HBM-bound like the transforms they would hide behind (measured: +0.03 ms per solve), so the default is R >= 4
+        const char *pe = getenv("OB_DIST_PIPELINE");
+        const bool want_pipe = pe ? atoi(pe) != 0 : (R >= 4 && !getenv("OB_DIST_NO_PIPELINE"));
+        if (zx && use_ipc && nz >= 2 && R > 1 && want_pipe) OB_TRY(setup_pipeline());
         if (tridiag) {  // diagonal in the transposed layout (fourier_tridiagonal_poisson_solver.jl:199-229)
             const int Nz = N[2], Hz = g->H[2];
             const T *dzf = (const T *)g->dzf_host, *dzc = (const T *)g->dzc_host;
@@ -377,6 +456,95 @@ struct DistSolverT : ob_solver {
         use_ipc = ok != 0;
         return OB_OK;
     }
+    int32_t setup_pipeline() {
+        nch = std::min((int)MAXCH, nz);
+        int z = 0;
+        for (int c = 0; c < nch; c++) { chlen[c] = nz / nch + (c < nz % nch ? 1 : 0); ch0[c] = z; z += chlen[c]; }
+        int nn[2] = {N[1], NxG};
+        for (int c = 0; c < nch; c++) {
+            int slot = plan_xy_len[0] == chlen[c] ? 0 : plan_xy_len[1] == chlen[c] ? 1 : plan_xy_len[0] == 0 ? 0 : 1;
+            if (plan_xy_len[slot] == chlen[c]) continue;
+            CUFFT_TRY(cufftPlanMany(&plan_xy_ch[slot], 2, nn, nullptr, 1, NxG * N[1], nullptr, 1, NxG * N[1], CT, chlen[c]));
+            CUFFT_TRY(cufftSetStream(plan_xy_ch[slot], ctx->stream));
+            plan_xy_len[slot] = chlen[c];
+        }
+        // the pulls run at the lowest priority (the context's stream has the highest: ob_init), so the transforms of the main
+        // stream get the CTA slots they ask for and the pulls fill what is left
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, least));
+        pull_ctas = (ctx->sm_count > 0 ? ctx->sm_count : 148) * 4;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+        for (int c = 0; c < nch; c++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_pull[c], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_fft[c], cudaEventDisableTiming));
+        }
+        pipelined = true;
+        return OB_OK;
+    }
+    // forward pull, (x, y) transforms + eigenvalue division, closing pull -- chunk by chunk on two streams.  Every rank issues
+    // the same sequence of barriers (one on the main stream, then one per chunk on the second stream), so the epochs agree.
+    int32_t pipelined_middle() {
+        cudaStream_t st = ctx->stream;
+        const long plane = (long)NxG * N[1];
+        OB_TRY(barrier());        // every peer's z transform is complete
+        CUDA_TRY(cudaEventRecord(ev_ready, st));
+        CUDA_TRY(cudaStreamWaitEvent(st2, ev_ready, 0));
+        for (int c = 0; c < nch; c++) {
+            pull_z_to_x_chunk_kernel<C><<<std::min((unsigned)pull_ctas, nblk(plane * chlen[c], 1024)), 256, 0, st2>>>(peerS, Tt, nx, NxG, N[1], nz, rank, ch0[c], chlen[c]);
+            CUDA_TRY(cudaEventRecord(ev_pull[c], st2));
+        }
+        const int nxo = nx + (west ? 1 : 0);
+        // (never S: a peer may still be pulling this rank's z-transformed slab out of it when the first chunk comes back)
+        C *out = west ? S2 : buf_b;
+        for (int c = 0; c < nch; c++) {
+            CUDA_TRY(cudaStreamWaitEvent(st, ev_pull[c], 0));
+            C *chunk = Tt + plane * ch0[c];
+            cufftHandle pl = plan_xy_len[0] == chlen[c] ? plan_xy_ch[0] : plan_xy_ch[1];
+            OB_TRY(exec(pl, chunk, CUFFT_FORWARD));
+            eigen_divide_zslab_kernel<T, C><<<nblk(plane * chlen[c], 256), 256, 0, st>>>(chunk, lam[0], lam[1], lam[2], NxG, N[1], chlen[c], rank * nz + ch0[c],
+                                                                                         zr ? Nzh : N[2], (rank == 0 && c == 0) ? 1 : 0);
+            OB_TRY(exec(pl, chunk, CUFFT_INVERSE));
+            CUDA_TRY(cudaEventRecord(ev_fft[c], st));
+            // closing transposition of this chunk: every peer's chunk c must be transformed
+            CUDA_TRY(cudaStreamWaitEvent(st2, ev_fft[c], 0));
+            ipc_barrier_kernel<<<1, 32, 0, st2>>>(peerF, d_bflags, R, rank, ++bar_epoch);
+            pull_x_to_z_chunk_kernel<C><<<std::min((unsigned)pull_ctas, nblk((long)nxo * N[1] * chlen[c] * R, 1024)), 256, 0, st2>>>(peerT, out, nx, NxG, N[1], nz, R, rank, west ? 1 : 0,
+                                                                                                      ch0[c], chlen[c]);
+            launches += 4;
+        }
+        CUDA_TRY(cudaEventRecord(ev_done, st2));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
+        launches += nch;
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    // inverse z transform of the slab layout, reading the transposed spectrum from `in`; rows of nx columns (result in S / Rr) or
+    // nx + 1 columns (`in` = S2, result in S2 / Rr2)
+    int32_t inverse_z(C *in, bool wide) {
+        cudaStream_t st = ctx->stream;
+        const bool z_dct = !tridiag && topo[2] == OB_BOUNDED;
+        const int nxo = nx + (wide ? 1 : 0);
+        const unsigned nbo = nblk((long)nxo * N[1] * NzT, 256);
+        C *dst = wide ? S2 : S, *tmp = wide ? buf_a2 : buf_a;
+        if (z_dct) {
+            twiddle_bwd_kernel<T, C><<<nbo, 256, 0, st>>>(in, tmp, tw_b, nxo, N[1], N[2], 2);
+            OB_TRY(exec(wide ? plan_z2 : plan_z, tmp, CUFFT_INVERSE));
+            unpermute_kernel<C><<<nbo, 256, 0, st>>>(tmp, dst, nxo, N[1], N[2], 2);
+            launches += 2;
+        } else if (zr) {
+            launches++;
+            if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2D(wide ? plan_zc2r2 : plan_zc2r, in, wide ? Rr2 : Rr));
+            else CUFFT_TRY(cufftExecC2R(wide ? plan_zc2r2 : plan_zc2r, in, wide ? Rr2 : Rr));
+        } else {
+            launches++;
+            if constexpr (std::is_same<T, double>::value) CUFFT_TRY(cufftExecZ2Z(wide ? plan_z2 : plan_z, in, dst, CUFFT_INVERSE));
+            else CUFFT_TRY(cufftExecC2C(wide ? plan_z2 : plan_z, in, dst, CUFFT_INVERSE));
+        }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
     bool enable_west_column() override {
         if (west) return true;
         if (!zx || !use_ipc || getenv("OB_DIST_NO_WEST_COLUMN")) return false;
@@ -428,6 +596,12 @@ struct DistSolverT : ob_solver {
         if (has_x) cufftDestroy(plan_x);
         if (has_xy) cufftDestroy(plan_xy);
         if (zr) { cufftDestroy(plan_zr2c); cufftDestroy(plan_zc2r); cudaFree(Rr); }
+        if (pipelined) {
+            cudaStreamSynchronize(st2); cudaStreamDestroy(st2);
+            cudaEventDestroy(ev_ready); cudaEventDestroy(ev_done);
+            for (int c = 0; c < nch; c++) { cudaEventDestroy(ev_pull[c]); cudaEventDestroy(ev_fft[c]); }
+            for (int q = 0; q < 2; q++) if (plan_xy_ch[q]) cufftDestroy(plan_xy_ch[q]);
+        }
         if (plan_zc2r2) cufftDestroy(plan_zc2r2);
         if (plan_z2) cufftDestroy(plan_z2);
         cudaFree(S2); cudaFree(buf_a2); cudaFree(Rr2);
@@ -475,6 +649,10 @@ struct DistSolverT : ob_solver {
                 else CUFFT_TRY(cufftExecR2C(plan_zr2c, Rr, S));
             } else {
                 OB_TRY(exec(plan_z, S, CUFFT_FORWARD));
+            }
+            if (pipelined) {
+                OB_TRY(pipelined_middle());
+                return inverse_z(west ? S2 : buf_b, west);
             }
             if (use_ipc) {
                 OB_TRY(barrier());        // every peer's z transform is complete

@@ -184,6 +184,12 @@ struct IvdP {
     Fld<T> f[3 + OB_MAXTR];
     T nu[OB_MAXCL];                 // the vertically-implicit closures only, in closure order
     T kappa[OB_MAXCL][OB_MAXTR];
+    // eddy-viscosity closures (Smagorinsky, AMD) with VerticallyImplicitTimeDiscretization: the coefficients are nu_e / kappa_e
+    // interpolated to the node (abstract_scalar_diffusivity_closure.jl:137-151, 330-351)
+    int kind[OB_MAXCL];
+    T Pr[OB_MAXCL][OB_MAXTR];
+    Fld<T> nue[OB_MAXCL];
+    Fld<T> kappae[OB_MAXCL][OB_MAXTR];
     T dt;
     T *scratch;                     // nfields x (Nz+1) x Ny x Nx
 };
@@ -207,17 +213,35 @@ struct IvdCol {
                 }
         return r;
     }
-    __device__ __forceinline__ T coef(int m) const { return which < 3 ? P.nu[m] : P.kappa[m][which - 3]; }
+    // two-point interpolation of a ccc array to the face below / west / south (interpolation_operators.jl:8-28), nested as the
+    // reference nests them: ℑxzᶠᵃᶠ = ℑzᵃᵃᶠ(ℑxᶠᵃᵃ), ℑyzᵃᶠᶠ = ℑzᵃᵃᶠ(ℑyᵃᶠᵃ); Flat => identity
+    __device__ __forceinline__ T i1(const Fld<T> &f, int d, int a, int b, int c) const {
+        if (P.g.topo[d] == FLAT) return f.ld(a, b, c);
+        return T(0.5) * (f.ld(a - (d == 0), b - (d == 1), c - (d == 2)) + f.ld(a, b, c));
+    }
+    __device__ __forceinline__ T i2z(const Fld<T> &f, int d1, int a, int b, int c) const {
+        if (P.g.topo[2] == FLAT) return i1(f, d1, a, b, c);
+        return T(0.5) * (i1(f, d1, a, b, c - 1) + i1(f, d1, a, b, c));
+    }
+    // νzᶠᶜᶠ / νzᶜᶠᶠ / νzᶜᶜᶜ / κzᶜᶜᶠ of closure m at level kk
+    __device__ __forceinline__ T coef(int m, int kk) const {
+        if (P.kind[m] == CL_SCALAR) return which < 3 ? P.nu[m] : P.kappa[m][which - 3];
+        if (which == 0) return i2z(P.nue[m], 0, i, j, kk);
+        if (which == 1) return i2z(P.nue[m], 1, i, j, kk);
+        if (which == 2) return P.nue[m].ld(i, j, kk);
+        if (P.kind[m] == CL_SMAG) return i1(P.nue[m], 2, i, j, kk) / P.Pr[m][which - 3];
+        return i1(P.kappae[m][which - 3], 2, i, j, kk);
+    }
     __device__ __forceinline__ T upper(int k) const {
         T sum = 0;
         for (int m = 0; m < P.nvi; m++) {
             T d;
             if (!lz) {
-                const T kap = node(k + 1, 1, false) ? T(0) : coef(m);
+                const T kap = node(k + 1, 1, false) ? T(0) : coef(m, k + 1);
                 d = -P.dt * kap * (P.g.rdzC(k) * P.g.rdzF(k + 1));
                 if (node(k + 1, 1, true)) d = 0;
             } else {
-                const T nu = node(k, 0, false) ? T(0) : coef(m);
+                const T nu = node(k, 0, false) ? T(0) : coef(m, k);
                 d = -P.dt * nu * (P.g.rdzC(k) * P.g.rdzF(k));
                 if (node(k, 0, true)) d = 0;
             }
@@ -231,11 +255,11 @@ struct IvdCol {
             T d;
             if (!lz) {
                 const int k = kk + 1;
-                const T kap = node(k, 1, false) ? T(0) : coef(m);
+                const T kap = node(k, 1, false) ? T(0) : coef(m, k);
                 d = -P.dt * kap * (P.g.rdzC(k) * P.g.rdzF(k));
             } else {
                 const int kp = kk + 2;
-                const T nu = node(kp - 1, 0, false) ? T(0) : coef(m);
+                const T nu = node(kp - 1, 0, false) ? T(0) : coef(m, kp - 1);
                 d = -P.dt * nu * (P.g.rdzC(kp) * P.g.rdzF(kp - 1));
             }
             if (node(kk, 0, true)) d = 0;

@@ -94,7 +94,11 @@ extern "C" int32_t ob_init(int32_t device, ob_ctx **out) {
     ob_ctx *ctx = new ob_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // highest priority: helper streams of the library (distributed transposes) run below it
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest));
+    }
     CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));
     *out = ctx;
     return OB_OK;
@@ -799,7 +803,7 @@ struct ModelT : ob_model {
             cudaIpcCloseMemHandle(west_stage); cudaIpcCloseMemHandle(west_flags);
             if (east != west) { cudaIpcCloseMemHandle(east_stage); cudaIpcCloseMemHandle(east_flags); }
         }
-        cudaFree(d_stage); cudaFree(d_flags); cudaFree(d_blockctr); cudaFree(d_ivd);
+        cudaFree(d_stage); cudaFree(d_flags); cudaFree(d_blockctr); cudaFree(d_ivd); cudaFree(d_amd_tab);
         delete solver;
         for (auto e : pool) cudaEventDestroy(e);
     }
@@ -872,10 +876,11 @@ struct ModelT : ob_model {
         ncl = d->n_closures;
         if (ntr > OB_MAXTR || ncl > OB_MAXCL) return fail(OB_ERR_INVALID, "too many tracers/closures");
         // scope validation: anything else must be rejected, never silently approximated
-        if (d->advection_kind == OB_ADV_WENO && (d->advection_order < 3 || d->advection_order > 9 || d->advection_order % 2 == 0))
-            return fail(OB_ERR_UNSUPPORTED, "WENO order %d not supported (3,5,7,9)", d->advection_order);
-        if (d->advection_kind == OB_ADV_CENTERED && (d->advection_order < 2 || d->advection_order > 6 || d->advection_order % 2))
-            return fail(OB_ERR_UNSUPPORTED, "Centered order %d not supported (2,4,6)", d->advection_order);
+        // every order the reference builds buffers for (src/Advection/Advection.jl:52: buffers 1 .. 6)
+        if (d->advection_kind == OB_ADV_WENO && (d->advection_order < 3 || d->advection_order > 11 || d->advection_order % 2 == 0))
+            return fail(OB_ERR_UNSUPPORTED, "WENO order %d not supported (3, 5, 7, 9, 11)", d->advection_order);
+        if (d->advection_kind == OB_ADV_CENTERED && (d->advection_order < 2 || d->advection_order > 12 || d->advection_order % 2))
+            return fail(OB_ERR_UNSUPPORTED, "Centered order %d not supported (2, 4, ..., 12)", d->advection_order);
         const int nb = d->advection_kind == OB_ADV_WENO ? (d->advection_order + 1) / 2 : d->advection_kind == OB_ADV_CENTERED ? d->advection_order / 2 : 0;
         for (int k = 0; k < 3; k++) {
             if (g.topo[k] != FLAT && g.N[k] < nb) return fail(OB_ERR_UNSUPPORTED, "grid size %d along %d is smaller than the advection buffer %d (adapt_advection_order path)", g.N[k], k, nb);
@@ -885,8 +890,6 @@ struct ModelT : ob_model {
         }
         for (int m = 0; m < d->n_closures; m++)
             if (d->closures[m].vertically_implicit) {
-                if (d->closures[m].kind != OB_CLOSURE_SCALAR_DIFFUSIVITY)
-                    return fail(OB_ERR_UNSUPPORTED, "VerticallyImplicitTimeDiscretization is implemented for ScalarDiffusivity only");
                 if (g.topo[2] != BOUNDED)
                     return fail(OB_ERR_INVALID, "VerticallyImplicitTimeDiscretization can only be specified on grids that are Bounded in the z-direction");
             }
@@ -1202,11 +1205,33 @@ struct ModelT : ob_model {
                 smagorinsky_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m);
                 launches++;
             } else {
-                amd_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m);
+                OB_TRY(amd_geometry());
+                amd_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m, amd_geom);
                 launches++;
             }
         }
         CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    // level-dependent metric ratios of the AMD kernel (closures.cuh: AmdGeom), evaluated once with the divisions the reference
+    // performs per cell
+    AmdGeom<T> amd_geom = {nullptr, 0, T(0), T(0)};
+    T *d_amd_tab = nullptr;
+    int32_t amd_geometry() {
+        if (amd_geom.tab) return OB_OK;
+        const int Nz = g.N[2], n = Nz + 2;
+        std::vector<T> h(6 * (size_t)n);
+        const T fx = 2 * g.dx, fy = 2 * g.dy;
+        for (int k = 0; k <= Nz + 1; k++) {
+            const int kk = g.topo[2] == FLAT ? 1 : k;
+            const T fz = 2 * hDZC(kk);
+            h[0 * n + k] = fz; h[1 * n + k] = fx / fz; h[2 * n + k] = fz / fx; h[3 * n + k] = fy / fz; h[4 * n + k] = fz / fy;
+            h[5 * n + k] = 3 / (1 / (fx * fx) + 1 / (fy * fy) + 1 / (fz * fz));
+        }
+        CUDA_TRY(cudaMalloc(&d_amd_tab, sizeof(T) * h.size()));
+        CUDA_TRY(cudaMemcpyAsync(d_amd_tab, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        amd_geom.tab = d_amd_tab; amd_geom.stride = n; amd_geom.rxy = fx / fy; amd_geom.ryx = fy / fx;
         return OB_OK;
     }
     int32_t update_hydrostatic_pressure() override { return hydrostatic_pressure(false); }
@@ -1436,7 +1461,11 @@ struct ModelT : ob_model {
         for (int m = 0; m < ncl; m++) {
             if (!desc.closures[m].vertically_implicit) continue;
             P.nu[P.nvi] = (T)desc.closures[m].nu;
-            for (int t = 0; t < OB_MAXTR; t++) P.kappa[P.nvi][t] = (T)desc.closures[m].kappa[t];
+            P.kind[P.nvi] = desc.closures[m].kind;
+            for (int t = 0; t < OB_MAXTR; t++) { P.kappa[P.nvi][t] = (T)desc.closures[m].kappa[t]; P.Pr[P.nvi][t] = (T)desc.closures[m].Pr[t]; }
+            if (desc.closures[m].kind != OB_CLOSURE_SCALAR_DIFFUSIVITY) P.nue[P.nvi] = fld(OB_FIELD_NUE0 + m);
+            if (desc.closures[m].kind == OB_CLOSURE_AMD)
+                for (int t = 0; t < ntr; t++) P.kappae[P.nvi][t] = fld(OB_FIELD_KAPPAE0 + m * OB_MAX_TRACERS + t);
             P.nvi++;
         }
         for (int n = 0; n < P.nfields; n++) P.f[n] = fld(n < 3 ? n : OB_FIELD_TRACER0 + (n - 3));

@@ -284,6 +284,10 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     (void)sm_count;
     done = false;
     if (mode == 1) return cudaSuccess;
+    // WENO-11: the one-thread-per-cell kernel only (the marching form of a 12-point stencil spills 10 KB per thread and takes
+    // seven minutes to compile; the scheme is outside BASELINE.json's configurations)
+    if constexpr (S::kind == ADV_WENO && S::n >= 6) return cudaSuccess;
+    else {
     done = true;
     const bool whole = tx_lo == 0 && tx_hi < 0 && !invert;
     if constexpr (StageSel<T, S>::built) {
@@ -316,6 +320,7 @@ static cudaError_t try_tiled_tendency(const TendP<T> &P, int fast, int mode, cud
     if (mode == 7) return launch_march<T, S, 8, 16, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
 #endif
     return launch_march<T, S, 8, 32, 4>(P, fast, st, nlaunch, tx_lo, tx_hi, invert);
+    }
 }
 
 }  // namespace ob

@@ -229,10 +229,12 @@ function closure_desc(c::Smagorinsky, names)
     cs = lilly ? coeff.smagorinsky : coeff
     cb = lilly ? coeff.reduction_factor : 0.0
     (cs isa Number) || unsupported("DynamicSmagorinsky")
-    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0, 0)
+    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0,
+                         Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization))
 end
 closure_desc(c::AnisotropicMinimumDissipation, names) =
-    ObClosureDesc(3, 0.0, pad8(()), 0.0, 0, c.Cb === nothing ? 0.0 : Float64(c.Cb), pad8(()), Float64(c.Cν), pad8(values(c.Cκ)), Int32(c.Cb !== nothing), 0)
+    ObClosureDesc(3, 0.0, pad8(()), 0.0, 0, c.Cb === nothing ? 0.0 : Float64(c.Cb), pad8(()), Float64(c.Cν), pad8(values(c.Cκ)), Int32(c.Cb !== nothing),
+                  Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization))
 closure_desc(c, names) = unsupported("closure $(typeof(c))")
 closure_tuple(model) = model.closure === nothing ? () : model.closure isa Tuple ? model.closure : (model.closure,)
 

@@ -62,20 +62,36 @@ class ScalarDiffusivity:
         self.required_halo = 1
 
 
+def _time_discretization(td):
+    if isinstance(td, type):
+        td = td()
+    if td is not None and not isinstance(td, (ExplicitTimeDiscretization, VerticallyImplicitTimeDiscretization)):
+        raise TypeError("time_discretization must be ExplicitTimeDiscretization() or VerticallyImplicitTimeDiscretization()")
+    return td or ExplicitTimeDiscretization()
+
+
 class Smagorinsky:
-    def __init__(self, coefficient=0.16, Pr=1.0):
+    """Smagorinsky([time_discretization]; coefficient, Pr) (smagorinsky.jl:76-84)"""
+
+    def __init__(self, time_discretization=None, coefficient=0.16, Pr=1.0):
+        self.time_discretization = _time_discretization(time_discretization)
+        self.vertically_implicit = isinstance(self.time_discretization, VerticallyImplicitTimeDiscretization)
         self.cs, self.Pr, self.lilly, self.cb = coefficient, Pr, False, 0.0
         self.required_halo = 2
 
 
-def SmagorinskyLilly(C=0.16, Cb=1.0, Pr=1.0):
-    s = Smagorinsky(coefficient=C, Pr=Pr)
+def SmagorinskyLilly(time_discretization=None, C=0.16, Cb=1.0, Pr=1.0):
+    s = Smagorinsky(time_discretization, coefficient=C, Pr=Pr)
     s.lilly, s.cb = True, Cb
     return s
 
 
 class AnisotropicMinimumDissipation:
-    def __init__(self, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None, Cν=None, Cκ=None):
+    """AnisotropicMinimumDissipation([time_discretization]; C, Cν, Cκ, Cb) (anisotropic_minimum_dissipation.jl:124-139)"""
+
+    def __init__(self, time_discretization=None, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None, Cν=None, Cκ=None):
+        self.time_discretization = _time_discretization(time_discretization)
+        self.vertically_implicit = isinstance(self.time_discretization, VerticallyImplicitTimeDiscretization)
         Cnu = Cν if Cν is not None else Cnu
         Ckappa = Cκ if Cκ is not None else Ckappa
         self.Cnu = C if Cnu is None else Cnu
@@ -212,15 +228,19 @@ class NonhydrostaticModel:
                     cd.kappa[t] = float(FT(kv))
             elif isinstance(c, Smagorinsky):
                 cd.kind, cd.cs, cd.lilly, cd.cb = _abi.OB_CLOSURE_SMAGORINSKY, float(FT(c.cs)), int(c.lilly), float(FT(c.cb))
+                cd.vertically_implicit = int(c.vertically_implicit)
                 for t in range(nt):
                     cd.Pr[t] = float(FT(_per_tracer(c.Pr, self.tracer_names, t)))
             elif isinstance(c, AnisotropicMinimumDissipation):
                 cd.kind, cd.Cnu = _abi.OB_CLOSURE_AMD, float(FT(c.Cnu))
+                cd.vertically_implicit = int(c.vertically_implicit)
                 cd.amd_has_cb, cd.cb = (0, 0.0) if c.Cb is None else (1, float(FT(c.Cb)))
                 for t in range(nt):
                     cd.Ckappa[t] = float(FT(_per_tracer(c.Ckappa, self.tracer_names, t)))
             else:
                 raise _abi.OceanB200Error(-3, "closure %r is outside the B200 hot path" % (c,))
+            if getattr(c, "vertically_implicit", False) and g.topo[2] != _abi.OB_BOUNDED:
+                raise ValueError("VerticallyImplicitTimeDiscretization can only be specified on grids that are Bounded in the z-direction.")
         if buoyancy is None:
             d.buoyancy_kind = _abi.OB_BUOYANCY_NONE
         elif isinstance(buoyancy, BuoyancyTracer):

@@ -608,7 +608,15 @@ static int node_test(P g, int i, int j, int k, int fx, int fy, int fz, int any) 
     return r;
 }
 static FT strong(FT x, int keep) { return keep ? x : (FT)0; } /* x * Bool */
-static FT ivd_coefficient(P g, int m, int which) { return which < 3 ? g->nu[m] : g->kappa[m][which - 3]; }
+/* νzᶠᶜᶠ / νzᶜᶠᶠ / νzᶜᶜᶜ / κzᶜᶜᶠ at level kk (abstract_scalar_diffusivity_closure.jl:137-151): the constants of a ScalarDiffusivity, or
+ * the eddy viscosity / diffusivity of Smagorinsky and AMD interpolated to the node the coefficient belongs to */
+static FT ivd_coefficient(P g, int m, int which, int i, int j, int kk) {
+    if (g->closure_kind[m] == CL_SCALAR) return which < 3 ? g->nu[m] : g->kappa[m][which - 3];
+    if (which == 0) return nu_fcf(g, m, i, j, kk);
+    if (which == 1) return nu_cff(g, m, i, j, kk);
+    if (which == 2) return nu_ccc(g, m, i, j, kk);
+    return kap(g, m, which - 3, 2, i, j, kk);
+}
 static FT ivd_upper(P g, int which, int lx, int ly, int lz, int i, int j, int k, FT dt) {
     FT sum = 0;
     int first = 1;
@@ -616,11 +624,11 @@ static FT ivd_upper(P g, int which, int lx, int ly, int lz, int i, int j, int k,
         if (!g->closure_vi[m]) continue;
         FT d;
         if (!lz) {
-            FT kap = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, k + 1, lx, ly, 1, 0));
+            FT kap = strong(ivd_coefficient(g, m, which, i, j, k + 1), !node_test(g, i, j, k + 1, lx, ly, 1, 0));
             d = -dt * kap * ((1 / dzc(k)) * (1 / dzf(k + 1)));
             d = strong(d, !node_test(g, i, j, k + 1, lx, ly, 1, 1));
         } else {
-            FT nu = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, k, lx, ly, 0, 0));
+            FT nu = strong(ivd_coefficient(g, m, which, i, j, k), !node_test(g, i, j, k, lx, ly, 0, 0));
             d = -dt * nu * ((1 / dzc(k)) * (1 / dzf(k)));
             d = strong(d, !node_test(g, i, j, k, lx, ly, 0, 1));
         }
@@ -637,12 +645,12 @@ static FT ivd_lower(P g, int which, int lx, int ly, int lz, int i, int j, int kk
         FT d;
         if (!lz) {
             int k = kk + 1;
-            FT kap = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, k, lx, ly, 1, 0));
+            FT kap = strong(ivd_coefficient(g, m, which, i, j, k), !node_test(g, i, j, k, lx, ly, 1, 0));
             d = -dt * kap * ((1 / dzc(k)) * (1 / dzf(k)));
             d = strong(d, !node_test(g, i, j, kk, lx, ly, 0, 1));
         } else {
             int kp = kk + 2;
-            FT nu = strong(ivd_coefficient(g, m, which), !node_test(g, i, j, kp - 1, lx, ly, 0, 0));
+            FT nu = strong(ivd_coefficient(g, m, which, i, j, kp - 1), !node_test(g, i, j, kp - 1, lx, ly, 0, 0));
             d = -dt * nu * ((1 / dzc(kp)) * (1 / dzf(kp - 1)));
             d = strong(d, !node_test(g, i, j, kk, lx, ly, 0, 1));
         }

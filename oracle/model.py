@@ -445,19 +445,26 @@ class ScalarDiffusivity:
 
 
 class Smagorinsky:
-    def __init__(self, coefficient=0.16, Pr=1.0, lilly=False, Cb=1.0):
+    """Smagorinsky([time_discretization]; coefficient, Pr) (smagorinsky.jl:76-84); vertically_implicit =
+    VerticallyImplicitTimeDiscretization(): the implicit step takes nu_e interpolated to the nodes of its coefficients"""
+
+    def __init__(self, coefficient=0.16, Pr=1.0, lilly=False, Cb=1.0, vertically_implicit=False):
         self.cs, self.Pr, self.lilly, self.cb = coefficient, Pr, lilly, Cb
+        self.vertically_implicit = bool(vertically_implicit)
 
 
-def SmagorinskyLilly(C=0.16, Cb=1.0, Pr=1.0):
-    return Smagorinsky(coefficient=C, Pr=Pr, lilly=True, Cb=Cb)
+def SmagorinskyLilly(C=0.16, Cb=1.0, Pr=1.0, vertically_implicit=False):
+    return Smagorinsky(coefficient=C, Pr=Pr, lilly=True, Cb=Cb, vertically_implicit=vertically_implicit)
 
 
 class AnisotropicMinimumDissipation:
-    def __init__(self, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None):
+    """AnisotropicMinimumDissipation([time_discretization]; C, Cν, Cκ, Cb) (anisotropic_minimum_dissipation.jl:124-139)"""
+
+    def __init__(self, C=1.0 / 3.0, Cnu=None, Ckappa=None, Cb=None, vertically_implicit=False):
         self.Cnu = C if Cnu is None else Cnu
         self.Ckappa = C if Ckappa is None else Ckappa
         self.Cb = Cb
+        self.vertically_implicit = bool(vertically_implicit)
 
 
 class Model:
@@ -545,12 +552,14 @@ class Model:
                     p.kappa[m][t] = ft(_per_tracer(c.kappa, self.tracer_names, t))
             elif isinstance(c, Smagorinsky):
                 p.closure_kind[m] = 2
+                p.closure_vi[m] = int(c.vertically_implicit)
                 p.cs[m], p.cb[m], p.lilly[m] = ft(c.cs), ft(c.cb), int(c.lilly)
                 for t in range(nt):
                     p.Pr[m][t] = ft(_per_tracer(c.Pr, self.tracer_names, t))
                 p.nue[m] = self.nue[m].ofield()
             else:
                 p.closure_kind[m] = 3
+                p.closure_vi[m] = int(c.vertically_implicit)
                 p.Cnu[m] = ft(c.Cnu)
                 p.amd_has_cb[m] = 0 if c.Cb is None else 1
                 p.cb[m] = ft(0 if c.Cb is None else c.Cb)

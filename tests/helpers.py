@@ -44,12 +44,12 @@ class Config:
                 cl.append(M.ScalarDiffusivity(nu=c[1], kappa=c[2]))
             elif c[0] == "vi_scalar":
                 cl.append(M.ScalarDiffusivity(nu=c[1], kappa=c[2], vertically_implicit=True))
-            elif c[0] == "smag":
-                cl.append(M.Smagorinsky(coefficient=c[1], Pr=c[2]))
-            elif c[0] == "lilly":
-                cl.append(M.SmagorinskyLilly(C=c[1], Cb=c[2], Pr=c[3]))
-            elif c[0] == "amd":
-                cl.append(M.AnisotropicMinimumDissipation(Cb=c[1] if len(c) > 1 else None))
+            elif c[0] in ("smag", "vi_smag"):
+                cl.append(M.Smagorinsky(coefficient=c[1], Pr=c[2], vertically_implicit=c[0] == "vi_smag"))
+            elif c[0] in ("lilly", "vi_lilly"):
+                cl.append(M.SmagorinskyLilly(C=c[1], Cb=c[2], Pr=c[3], vertically_implicit=c[0] == "vi_lilly"))
+            elif c[0] in ("amd", "vi_amd"):
+                cl.append(M.AnisotropicMinimumDissipation(Cb=c[1] if len(c) > 1 else None, vertically_implicit=c[0] == "vi_amd"))
         bcs = {}
         for name, sides in self.bcs.items():
             bcs[name] = {s: (k.lower(), v) for s, (k, v) in sides.items()}
@@ -78,12 +78,15 @@ class Config:
                 cl.append(ob.ScalarDiffusivity(nu=c[1], kappa=c[2]))
             elif c[0] == "vi_scalar":
                 cl.append(ob.ScalarDiffusivity(ob.VerticallyImplicitTimeDiscretization(), nu=c[1], kappa=c[2]))
-            elif c[0] == "smag":
-                cl.append(ob.Smagorinsky(coefficient=c[1], Pr=c[2]))
-            elif c[0] == "lilly":
-                cl.append(ob.SmagorinskyLilly(C=c[1], Cb=c[2], Pr=c[3]))
-            elif c[0] == "amd":
-                cl.append(ob.AnisotropicMinimumDissipation(Cb=c[1] if len(c) > 1 else None))
+            elif c[0] in ("smag", "vi_smag"):
+                td = (ob.VerticallyImplicitTimeDiscretization(),) if c[0] == "vi_smag" else ()
+                cl.append(ob.Smagorinsky(*td, coefficient=c[1], Pr=c[2]))
+            elif c[0] in ("lilly", "vi_lilly"):
+                td = (ob.VerticallyImplicitTimeDiscretization(),) if c[0] == "vi_lilly" else ()
+                cl.append(ob.SmagorinskyLilly(*td, C=c[1], Cb=c[2], Pr=c[3]))
+            elif c[0] in ("amd", "vi_amd"):
+                td = (ob.VerticallyImplicitTimeDiscretization(),) if c[0] == "vi_amd" else ()
+                cl.append(ob.AnisotropicMinimumDissipation(*td, Cb=c[1] if len(c) > 1 else None))
         b = self.buoyancy
         if b is None:
             buoy = None

@@ -38,3 +38,12 @@ def test_float64_rounding_of_the_headline_config_is_far_inside_the_tolerance():
     a, b = run_oracle("ppp_weno5", np.float64, 1e-3), run_oracle("ppp_weno5", np.longdouble, 1e-3)
     errs = {k: float(rel_l2(a[k], b[k].astype(np.float64))) for k in a}
     assert all(e < 1e-13 for e in errs.values()), errs
+
+
+def test_float64_pressure_of_the_2d_readme_case_sits_at_the_contract_tolerance():
+    """random velocities on 32 x 32, dt = 1e-3: the Float64 evaluation of pNHS is already half the 1e-11 tolerance away from the
+    exactly-rounded answer, which is why tests/test_gpu_parity.py holds that field to 3e-11 there"""
+    a, b = run_oracle("readme_2d", np.float64, 1e-3), run_oracle("readme_2d", np.longdouble, 1e-3)
+    errs = {k: float(rel_l2(a[k], b[k].astype(np.float64))) for k in a}
+    assert 2e-12 < errs["pNHS"] < 3e-11, errs
+    assert errs["u"] < 1e-14 and errs["v"] < 1e-14, errs

@@ -274,6 +274,34 @@ def test_oracle_vertically_implicit_diffusion_is_backward_euler():
     assert 1e-7 < d < 1e-3
 
 
+def test_oracle_vertically_implicit_smagorinsky_is_backward_euler_with_the_eddy_diffusivity():
+    """Smagorinsky(VerticallyImplicitTimeDiscretization()): the implicit step takes κzᶜᶜᶠ = ℑz(νₑ) / Pr
+    (abstract_scalar_diffusivity_closure.jl:149-151, smagorinsky.jl:41-42).  With u = S y the eddy viscosity of a column away
+    from the periodic seam is the constant cₛ² (Δx Δy Δz)^{2/3} |S| at every level, so one forward-Euler step of a z-only
+    tracer profile must equal the dense backward-Euler solve with that constant divided by Pr."""
+    Nz, S, cs, Pr, dt = 12, 0.9, 0.16, 2.0, 0.5
+    g = M.Grid((6, 8, Nz), ((0, 1.2), (0, 0.8), (-1.8, 0.0)), topology=("P", "P", "B"), halo=(3, 3, 3))
+    yc = g.nodes(1, "c")[None, :, None]
+    zc = g.nodes(2, "c")
+    prof = np.cos(np.pi * zc / 1.8) + 0.3 * np.cos(3 * np.pi * zc / 1.8)
+    m = M.Model(g, advection=None, closure=[M.Smagorinsky(coefficient=cs, Pr=Pr, vertically_implicit=True)], tracers=("c",), timestepper="ab2")
+    m.set(u=S * yc * np.ones((Nz, 1, 6)), c=np.broadcast_to(prof[:, None, None], (Nz, 8, 6)).copy())
+    m.time_step(dt, euler=True)
+    nue = cs ** 2 * (0.2 * 0.1 * 0.15) ** (2 / 3) * S
+    assert np.allclose(m.nue[0].interior[:, 3, 2], nue, rtol=1e-10)
+    kap, dz = nue / Pr, 0.15
+    A = np.eye(Nz)
+    for k in range(Nz):
+        for q in (k - 1, k + 1):
+            if 0 <= q < Nz:
+                A[k, q] -= dt * kap / dz ** 2
+                A[k, k] += dt * kap / dz ** 2
+    want = np.linalg.solve(A, prof)
+    got = m.tracers[0].interior[:, 3, 2]
+    assert np.allclose(got, want, rtol=1e-11, atol=1e-13)
+    assert np.abs(got - prof).max() > 1e-6      # the step did something
+
+
 def test_oracle_array_valued_boundary_conditions_reduce_to_constants():
     """getbc(condition::AbstractArray, i, j, ...) = condition[i, j]: a constant array must reproduce the constant condition
     bit for bit (Flux through compute_flux_bc_tendencies!, Value / Gradient through the halo fill)"""
