@@ -218,7 +218,9 @@ int32_t ob_time_step_ab2(ob_model *m, double dt, int32_t euler, int32_t first);
  * -- measured faster at 256^3 per GPU on NVLink, where an exchange costs ~50 us and the split launch ~70 us */
 #define OB_OPT_OVERLAP_HALO 3
 /* OB_OPT_VECTOR_STREAMS = 1 (default): the update, Poisson-source and fused-projection kernels use 128-bit accesses
- * (csrc/streaming.cuh); 0: the one-cell-per-thread forms (bit-identical results; kept for A/B checks) */
+ * (csrc/streaming.cuh), triply periodic halos are filled in one launch, and ob_time_step_rk3 swaps the roles of the two
+ * tendency sets between stages instead of copying; 0: the one-cell-per-thread kernels, the z / y / x fill sequence and the
+ * copies of the reference (bit-identical results; kept for A/B checks) */
 #define OB_OPT_VECTOR_STREAMS 4
 int32_t ob_model_set_option(ob_model *m, int32_t option, int32_t value);
 /* number of kernels/library launches issued by this model so far (bench.py's gpu_launches) */

@@ -81,11 +81,10 @@ struct AmdGeom {
     T rxy, ryx;      // fx / fy, fy / fx
     __device__ __forceinline__ T at(int r, int k) const { return __ldg(tab + r * stride + k); }
 };
-#ifndef OB_AMD_MINB
-#define OB_AMD_MINB 4   // resident CTAs per SM the register budget is set for (tuning knob; see profiles/r2_les_kernels.txt)
-#endif
-template <typename T>
-__global__ void __launch_bounds__(128, OB_AMD_MINB) amd_kernel(const __grid_constant__ TendP<T> P, int m, const AmdGeom<T> A) {
+// MINB: resident CTAs per SM the register budget is set for (4: 126 registers, no spills; 5: 96 registers, 0.3 KB of spills;
+// the host picks it -- OB_AMD_MINB in the environment overrides, for A/B timings)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(128, MINB) amd_kernel(const __grid_constant__ TendP<T> P, int m, const AmdGeom<T> A) {
     int i, j, k;
     if (!cell_from_block(P.g.N[0], P.g.N[1], i, j, k)) return;
     const GridD<T> &g = P.g;

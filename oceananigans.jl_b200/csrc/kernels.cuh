@@ -80,6 +80,44 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloB
 #undef AT
 }
 
+// Triply periodic fields: the three periodic fills (z, then y, then x, each over the full parent extent of the other two
+// directions: fill_halo_regions_periodic.jl:5-27) in ONE launch.  After the sequence every halo cell holds the interior value
+// its indices wrap to, so each thread of the shell copies that value directly -- bit-identical, and two launches fewer per fill.
+// The shell is enumerated as three disjoint slabs: k in the halo (full x-y planes), j in the halo (interior k), i in the halo
+// (interior j, k); x is the fastest index of each.
+template <typename T>
+__global__ void __launch_bounds__(256) halo_periodic3_kernel(const __grid_constant__ HaloBatch<T> B, int Nx, int Ny, int Nz, int Hx, int Hy, int Hz) {
+    const HaloTask<T> &t = B.t[blockIdx.y];
+    const int Px = t.P[0], Py = t.P[1];
+    const long nZ = (long)Px * Py * 2 * Hz, nY = (long)Px * 2 * Hy * Nz, nX = (long)2 * Hx * Ny * Nz;
+    long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int i, j, k;   // 0-based parent indices of the halo cell
+    if (q < nZ) {
+        i = (int)(q % Px); j = (int)((q / Px) % Py);
+        const int h = (int)(q / ((long)Px * Py));
+        k = h < Hz ? h : Nz + h;
+    } else if (q < nZ + nY) {
+        q -= nZ;
+        i = (int)(q % Px);
+        const int h = (int)((q / Px) % (2 * Hy));
+        j = h < Hy ? h : Ny + h;
+        k = Hz + (int)(q / ((long)Px * 2 * Hy));
+    } else if (q < nZ + nY + nX) {
+        q -= nZ + nY;
+        const int h = (int)(q % (2 * Hx));
+        i = h < Hx ? h : Nx + h;
+        j = Hy + (int)((q / (2 * Hx)) % Ny);
+        k = Hz + (int)(q / ((long)2 * Hx * Ny));
+    } else {
+        return;
+    }
+    const int si = i < Hx ? i + Nx : i >= Hx + Nx ? i - Nx : i;
+    const int sj = j < Hy ? j + Ny : j >= Hy + Ny ? j - Ny : j;
+    const int sk = k < Hz ? k + Nz : k >= Hz + Nz ? k - Nz : k;
+    const long sy = Px, sz = (long)Px * Py;
+    t.p[i + j * sy + k * sz] = t.p[si + sj * sy + sk * sz];
+}
+
 // Distributed west/east halo slabs: pack the H interior columns next to each x boundary of every field of the batch
 // into contiguous buffers, and unpack the neighbours' slabs into the halos.  Integer index work: bit-exact.
 template <typename T>

@@ -820,7 +820,14 @@ struct ModelT : ob_model {
         }
         f.bc = bc;
     }
+    // G-role swap (time_step_rk3): while set, the tendency fields Gⁿ and G⁻ trade places, so that "G⁻ <- Gⁿ" between two
+    // stages is a change of roles instead of a copy
+    bool gswap = false;
     Fld<T> fld(int id) const {
+        if (gswap) {
+            if (id >= OB_FIELD_GN0 && id < OB_FIELD_GN0 + 3 + OB_MAX_TRACERS) id += OB_FIELD_GM0 - OB_FIELD_GN0;
+            else if (id >= OB_FIELD_GM0 && id < OB_FIELD_GM0 + 3 + OB_MAX_TRACERS) id -= OB_FIELD_GM0 - OB_FIELD_GN0;
+        }
         const FieldInfo &f = F[id];
         Fld<T> v;
         v.p = (T *)f.ptr;
@@ -951,6 +958,34 @@ struct ModelT : ob_model {
     std::vector<int> pending_x_ids;
     int32_t fill_halos(const std::vector<int> &ids, bool fill_normal, bool defer_x = false, const std::vector<int> *x_ids = nullptr) {
         PhaseScope ps(this, PH_HALO);
+        // single device, triply periodic: one launch does the three periodic fills of every field (halo_periodic3_kernel)
+        bool all_periodic = !dist && opt_vector && g.topo[0] == PERIODIC && g.topo[1] == PERIODIC && g.topo[2] == PERIODIC && g.N[0] >= g.H[0] &&
+                            g.N[1] >= g.H[1] && g.N[2] >= g.H[2] && !ids.empty();
+        for (int id : ids)
+            for (int sd = 0; sd < 6; sd++) all_periodic = all_periodic && F[id].bc.kind[sd] == OB_BC_PERIODIC;
+        if (all_periodic) {
+            size_t pos = 0;
+            while (pos < ids.size()) {
+                HaloBatch<T> B;
+                B.count = 0; B.dir = 0; B.N = g.N[0]; B.H = g.H[0]; B.fill_normal = 0;
+                for (int k = 0; k < 3; k++) B.Hother[k] = g.H[k];
+                for (; pos < ids.size() && B.count < OB_MAX_HALO_TASKS; pos++) {
+                    const FieldInfo &f = F[ids[pos]];
+                    OB_TRY(need(ids[pos]));
+                    HaloTask<T> &t = B.t[B.count++];
+                    memset(&t, 0, sizeof(t));
+                    t.p = (T *)f.ptr;
+                    for (int k = 0; k < 3; k++) { t.P[k] = f.P[k]; t.n[k] = f.n[k]; }
+                }
+                if (B.count == 0) continue;
+                const FieldInfo &f0 = F[ids[0]];
+                const long shell = (long)f0.P[0] * f0.P[1] * 2 * g.H[2] + (long)f0.P[0] * 2 * g.H[1] * g.N[2] + (long)2 * g.H[0] * g.N[1] * g.N[2];
+                halo_periodic3_kernel<T><<<dim3(nblk(shell, 256), B.count), 256, 0, ctx->stream>>>(B, g.N[0], g.N[1], g.N[2], g.H[0], g.H[1], g.H[2]);
+                launches++;
+            }
+            CUDA_TRY(cudaGetLastError());
+            return OB_OK;
+        }
         for (int pass = 0; pass < 2; pass++)
             for (int d = 2; d >= 0; d--) {
                 if (g.topo[d] == FLAT) continue;
@@ -1206,7 +1241,10 @@ struct ModelT : ob_model {
                 launches++;
             } else {
                 OB_TRY(amd_geometry());
-                amd_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m, amd_geom);
+                static const int minb = getenv("OB_AMD_MINB") ? atoi(getenv("OB_AMD_MINB")) : 4;
+                if (minb == 5) amd_kernel<T, 5><<<grid, bs, 0, ctx->stream>>>(P, m, amd_geom);
+                else if (minb == 6) amd_kernel<T, 6><<<grid, bs, 0, ctx->stream>>>(P, m, amd_geom);
+                else amd_kernel<T, 4><<<grid, bs, 0, ctx->stream>>>(P, m, amd_geom);
                 launches++;
             }
         }
@@ -1576,9 +1614,17 @@ struct ModelT : ob_model {
         // RK3 coefficients are stored in the grid float type (runge_kutta_3.jl:66-75)
         const T g1 = (T)(8.0 / 15.0), g2 = (T)(5.0 / 12.0), g3 = (T)(3.0 / 4.0), z2 = (T)(-17.0 / 60.0), z3 = (T)(-5.0 / 12.0);
         if (first) OB_TRY(update_state());
-        OB_TRY(rk3_substep(dt, g1, 0, 0, true));
+        // cache_previous_tendencies! between the stages (runge_kutta_3.jl:125-152) is a copy G⁻ <- Gⁿ in the reference; here
+        // the two tendency sets swap roles after stages 1 and 2 (the next tendencies overwrite what was G⁻) and only stage 3
+        // copies, so that the step ends with Gⁿ and G⁻ where the host bound them.  Same values everywhere, 2(3+n) fewer
+        // field-sized writes per step.
+        const bool swap = opt_vector != 0;
+        struct Reset { bool &f; ~Reset() { f = false; } } reset{gswap};   // (an error return must not leave the roles swapped)
+        OB_TRY(rk3_substep(dt, g1, 0, 0, !swap));
+        gswap = swap;
         OB_TRY(update_state());
-        OB_TRY(rk3_substep(dt, g2, z2, 1, true));
+        OB_TRY(rk3_substep(dt, g2, z2, 1, !swap));
+        gswap = false;
         OB_TRY(update_state());
         OB_TRY(rk3_substep(dt, g3, z3, 1, true));
         OB_TRY(update_state());

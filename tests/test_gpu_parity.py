@@ -381,8 +381,9 @@ def test_fine_grained_entry_points_equal_fused_step(arch):
 @pytest.mark.parametrize("ft", [np.float64, np.float32])
 @pytest.mark.parametrize("name", ["ppp_weno5", "les_amd", "stretched", "lilly_bbb", "ragged_ppb", "wide_ppp", "array_bcs", "stage_ppp"])
 def test_vector_streaming_kernels_are_bit_identical(arch, name, ft):
-    """the 128-bit forms of the update / Poisson-source / projection kernels (csrc/streaming.cuh) reproduce the one-cell-per-
-    thread kernels bit for bit: even and odd Nx (both alignment phases of a row), Bounded and Periodic ends, RK3 and AB2"""
+    """the 128-bit forms of the update / Poisson-source / projection kernels (csrc/streaming.cuh), the one-launch triply periodic
+    halo fill and the role swap of the RK3 tendency sets reproduce the one-cell-per-thread kernels, the z / y / x fill sequence
+    and the G⁻ <- Gⁿ copies bit for bit: even and odd Nx (both alignment phases of a row), Bounded and Periodic ends, RK3 and AB2"""
     import ocean_b200 as ob
     from ocean_b200 import _abi
     for ts in ("rk3", "ab2"):
@@ -397,6 +398,9 @@ def test_vector_streaming_kernels_are_bit_identical(arch, name, ft):
         f1, f2 = b200_fields(m1), b200_fields(m2)
         for n in f1:
             assert np.array_equal(f1[n], f2[n]), (ts, n)
+        # the tendency sets end the step where the host bound them (RK3 swaps their roles between stages instead of copying)
+        for q, (a, b) in enumerate(zip(m1.Gn + m1.Gm, m2.Gn + m2.Gm)):
+            assert np.array_equal(a.interior(), b.interior()), (ts, "G", q)
 
 
 @pytest.mark.parametrize("name", ["ppp_weno5", "les_amd", "stretched", "lilly_bbb", "readme_2d"])
