@@ -256,7 +256,7 @@ struct DistSolverT : ob_solver {
     C *S = nullptr, *Tt = nullptr, *buf_a = nullptr, *buf_b = nullptr;
     // pipelined solve (IPC pulls): the local levels of the z-local layout are split into chunks; a second stream runs the pulls
     // (and the per-chunk barriers of the closing transposition) while the main stream transforms the chunks already there
-    static constexpr int MAXCH = 4;
+    static constexpr int MAXCH = 8;
     bool pipelined = false;
     int nch = 0, ch0[MAXCH], chlen[MAXCH];
     cufftHandle plan_xy_ch[2] = {0, 0};   // plans for the two chunk lengths that occur
@@ -457,7 +457,8 @@ struct DistSolverT : ob_solver {
         return OB_OK;
     }
     int32_t setup_pipeline() {
-        nch = std::min((int)MAXCH, nz);
+        const char *ce = getenv("OB_DIST_CHUNKS");   // tuning knob (default 4)
+        nch = std::max(1, std::min(std::min((int)MAXCH, nz), ce ? atoi(ce) : 4));
         int z = 0;
         for (int c = 0; c < nch; c++) { chlen[c] = nz / nch + (c < nz % nch ? 1 : 0); ch0[c] = z; z += chlen[c]; }
         int nn[2] = {N[1], NxG};

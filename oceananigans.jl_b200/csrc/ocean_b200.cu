@@ -1780,6 +1780,7 @@ extern "C" int32_t ob_phase_time_ms(ob_model *m, int32_t p, double *ms, int64_t 
     return OB_OK;
 }
 extern "C" int32_t ob_reset_timing(ob_model *m) {
+    if (!m) return fail(OB_ERR_INVALID, "null model");
     m->collect();
     for (int p = 0; p < PH_COUNT; p++) { m->phase_ms[p] = 0; m->phase_calls[p] = 0; }
     return OB_OK;

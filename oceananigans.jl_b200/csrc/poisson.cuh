@@ -148,29 +148,74 @@ __global__ void __launch_bounds__(128) thomas_kernel(C *__restrict__ A, const T 
     phi.x = f.x / beta;
     phi.y = f.y / beta;
     A[o] = phi;
-    for (int k = 1; k < Nz; k++) {
-        const T cm = upper[k - 1], am = lower[k - 1];
-        const T tk = cm / beta;
-        tscr[o + k * s] = tk;
-        beta = sub_rn(D[o + k * s], mul_rn(am, tk));
-        f = A[o + k * s];
-        const bool ok = fabs(beta) > eps10;
-        C star;
-        star.x = sub_rn(f.x, mul_rn(am, phi.x)) / beta;
-        star.y = sub_rn(f.y, mul_rn(am, phi.y)) / beta;
-        // not definitely diagonally dominant (the singular λ = 0 column): the reference leaves ϕ[k] untouched, i.e.
-        // an arbitrary stale value that only shifts the null-space constant removed by the mean subtraction; 0 here.
-        if (!ok) { star.x = 0; star.y = 0; }
-        phi = star;
-        A[o + k * s] = phi;
+    // The recurrences are serial in k but their operands are not: the diagonal and the right-hand side of the NEXT four levels are
+    // loaded while the current four are being eliminated (the sweep is latency-bound otherwise: one dependent miss per level).
+    constexpr int PF = 4;
+    T dn[PF];
+    C fn[PF];
+#pragma unroll
+    for (int q = 0; q < PF; q++) {
+        const int k = 1 + q;
+        if (k < Nz) { dn[q] = D[o + k * s]; fn[q] = A[o + k * s]; }
     }
-    for (int k = Nz - 2; k >= 0; k--) {
-        const T tk = tscr[o + (k + 1) * s];
-        C cur = A[o + k * s];
-        cur.x = sub_rn(cur.x, mul_rn(tk, phi.x));
-        cur.y = sub_rn(cur.y, mul_rn(tk, phi.y));
-        phi = cur;
-        A[o + k * s] = phi;
+    for (int k0 = 1; k0 < Nz; k0 += PF) {
+        T dc[PF];
+        C fc[PF];
+#pragma unroll
+        for (int q = 0; q < PF; q++) { dc[q] = dn[q]; fc[q] = fn[q]; }
+#pragma unroll
+        for (int q = 0; q < PF; q++) {
+            const int k = k0 + PF + q;
+            if (k < Nz) { dn[q] = D[o + k * s]; fn[q] = A[o + k * s]; }
+        }
+#pragma unroll
+        for (int q = 0; q < PF; q++) {
+            const int k = k0 + q;
+            if (k >= Nz) break;
+            const T cm = upper[k - 1], am = lower[k - 1];
+            const T tk = cm / beta;
+            tscr[o + k * s] = tk;
+            beta = sub_rn(dc[q], mul_rn(am, tk));
+            f = fc[q];
+            const bool ok = fabs(beta) > eps10;
+            C star;
+            star.x = sub_rn(f.x, mul_rn(am, phi.x)) / beta;
+            star.y = sub_rn(f.y, mul_rn(am, phi.y)) / beta;
+            // not definitely diagonally dominant (the singular λ = 0 column): the reference leaves ϕ[k] untouched, i.e.
+            // an arbitrary stale value that only shifts the null-space constant removed by the mean subtraction; 0 here.
+            if (!ok) { star.x = 0; star.y = 0; }
+            phi = star;
+            A[o + k * s] = phi;
+        }
+    }
+    // back substitution, operands of the next four levels in flight likewise
+    T tn[PF];
+    C an[PF];
+#pragma unroll
+    for (int q = 0; q < PF; q++) {
+        const int k = Nz - 2 - q;
+        if (k >= 0) { tn[q] = tscr[o + (k + 1) * s]; an[q] = A[o + k * s]; }
+    }
+    for (int k0 = Nz - 2; k0 >= 0; k0 -= PF) {
+        T tc[PF];
+        C ac[PF];
+#pragma unroll
+        for (int q = 0; q < PF; q++) { tc[q] = tn[q]; ac[q] = an[q]; }
+#pragma unroll
+        for (int q = 0; q < PF; q++) {
+            const int k = k0 - PF - q;
+            if (k >= 0) { tn[q] = tscr[o + (k + 1) * s]; an[q] = A[o + k * s]; }
+        }
+#pragma unroll
+        for (int q = 0; q < PF; q++) {
+            const int k = k0 - q;
+            if (k < 0) break;
+            C cur = ac[q];
+            cur.x = sub_rn(cur.x, mul_rn(tc[q], phi.x));
+            cur.y = sub_rn(cur.y, mul_rn(tc[q], phi.y));
+            phi = cur;
+            A[o + k * s] = phi;
+        }
     }
     if (remove_mean && o == 0) {
         T mx = 0, my = 0;

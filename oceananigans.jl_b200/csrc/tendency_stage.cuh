@@ -376,6 +376,7 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
     // point, h[1] = v at the south-flux point), lower-face fluxes, and (MN) the x / y face interpolants of nu_e one level below
     T h[4][N - 1], lower[4], lower_c[4][NCLR];
     T ixp = T(0), iyp = T(0);
+    T gun = T(0), gvn = T(0), gwn = T(0);   // TT: advecting velocities of the next level
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         lower[q] = T(0);
@@ -445,12 +446,14 @@ __global__ void __launch_bounds__((W + 4) * 32, 1) tendency_stage_kernel(const _
         Terms FY{P, g, VY, h[0], h[1], h[2], h[3], eoY + k * g.sz, k, trA, 0, ixp, iyp};
         // TT: the advecting velocities at the own points, from global memory (u at the west-flux point, v at the south-flux
         // point, w one level up)
+        // (loaded one level ahead: the three loads of level k+1 are in flight while level k is computed)
         T gu = T(0), gv = T(0), gw = T(0);
         if constexpr (MODE == STAGE_TT) {
-            if (k >= k0 - 1) {
-                gu = __ldg(P.u.p + P.u.off + eoX + k * g.sz);
-                gv = __ldg(P.v.p + P.v.off + eoY + k * g.sz);
-                gw = __ldg(P.w.p + P.w.off + eoY + (k + 1) * g.sz);
+            gu = gun; gv = gvn; gw = gwn;
+            if (k + 1 >= k0 - 1 && k + 1 <= k1) {
+                gun = __ldg(P.u.p + P.u.off + eoX + (k + 1) * g.sz);
+                gvn = __ldg(P.v.p + P.v.off + eoY + (k + 1) * g.sz);
+                gwn = __ldg(P.w.p + P.w.off + eoY + (k + 2) * g.sz);
             }
         }
         // one tendency slot q: kind of tendency, slot of its field, tracer index

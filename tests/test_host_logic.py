@@ -149,3 +149,35 @@ def test_time_interval_schedule_follows_the_reference():
         output_writers = {"w": type("W", (), {"schedule": s2})()}
     m.clock.time = 6.75
     assert S._aligned_time_step(_Sim(), 1.0) == pytest.approx(0.25)
+
+
+def test_closure_constructors_take_a_time_discretization_like_the_reference():
+    """Smagorinsky([time_discretization]; coefficient, Pr), AnisotropicMinimumDissipation([time_discretization]; C, Cν, Cκ, Cb),
+    ScalarDiffusivity([time_discretization]; ν, κ) (smagorinsky.jl:76-84, anisotropic_minimum_dissipation.jl:124-139,
+    scalar_diffusivity.jl:113-137): an instance or the type itself, first positional argument; anything else is a TypeError"""
+    import ocean_b200 as ob
+    VI, EX = ob.VerticallyImplicitTimeDiscretization, ob.ExplicitTimeDiscretization
+    for make in (lambda *a: ob.Smagorinsky(*a, coefficient=0.2, Pr=2.0), lambda *a: ob.SmagorinskyLilly(*a, C=0.2, Cb=1.0),
+                 lambda *a: ob.AnisotropicMinimumDissipation(*a, C=0.25), lambda *a: ob.ScalarDiffusivity(*a, nu=1e-3, kappa=1e-4)):
+        assert make().vertically_implicit is False
+        assert make(EX()).vertically_implicit is False
+        assert make(VI()).vertically_implicit is True
+        assert make(VI).vertically_implicit is True
+        with pytest.raises(TypeError):
+            make("implicit")
+    s = ob.SmagorinskyLilly(VI(), C=0.2, Cb=0.5, Pr=3.0)
+    assert (s.cs, s.cb, s.lilly, s.Pr) == (0.2, 0.5, True, 3.0)
+    a = ob.AnisotropicMinimumDissipation(Cν=0.3, Cκ=0.4)
+    assert (a.Cnu, a.Ckappa, a.Cb) == (0.3, 0.4, None)
+
+
+def test_advection_scheme_orders():
+    """every buffer the reference builds (src/Advection/Advection.jl:52): WENO 3 .. 11 (odd), Centered 2 .. 12 (even)"""
+    import ocean_b200 as ob
+    assert [ob.WENO(order=o).buffer for o in (3, 5, 7, 9, 11)] == [2, 3, 4, 5, 6]
+    assert [ob.Centered(order=o).buffer for o in (2, 4, 6, 8, 10, 12)] == [1, 2, 3, 4, 5, 6]
+    for bad in (4, 1):
+        with pytest.raises(ValueError):
+            ob.WENO(order=bad)
+    with pytest.raises(ValueError):
+        ob.Centered(order=3)

@@ -26,6 +26,10 @@ CASES = [
     ("config2 at 256^3 F32", Config((S(256),) * 3, ((0, TWO_PI),) * 3, "PPP", advection=("weno", 5), closure=[("scalar", 1e-3, 1e-3)], buoyancy=("tracer",), tracers=("b",), ft=np.float32), 1e-3, "rk3"),
     ("config3 ocean LES 512^3 PPB AMD+Scalar T,S FPlane F64 RK3", Config((S(512),) * 3, ((0, 512.0), (0, 512.0), (-256.0, 0.0)), "PPB", **LES), 2.0, "rk3"),
     ("config3 ocean LES 512^3 AB2", Config((S(512),) * 3, ((0, 512.0), (0, 512.0), (-256.0, 0.0)), "PPB", timestepper="ab2", **LES), 2.0, "ab2"),
+    # classes of models that run the round-1 marching / generic kernels (no staged-ring form): walls in every direction with a
+    # Centered scheme, and a higher-order WENO
+    ("BBB 256^3 Centered-4 SmagorinskyLilly b F64 (marching kernel, generic bodies)", Config((S(256),) * 3, ((0, 1.0),) * 3, "BBB", advection=("centered", 4), closure=[("lilly", 0.16, 1.0, 1.0)], buoyancy=("tracer",), tracers=("b",)), 1e-3, "rk3"),
+    ("PPB 256^3 WENO-7 b ScalarDiffusivity F64 (marching kernel, fast bodies)", Config((S(256),) * 3, ((0, 1.0),) * 3, "PPB", halo=(4, 4, 4), advection=("weno", 7), closure=[("scalar", 1e-3, 1e-3)], buoyancy=("tracer",), tracers=("b",)), 1e-3, "rk3"),
     ("config4 stretched-z 512^2x256 Fourier-tridiagonal F64", Config((S(512), S(512), S(256)), ((0, 512.0), (0, 512.0), stretched_faces(S(256), 256.0)), "PPB", **LES), 2.0, "rk3"),
     ("config4 stretched-z 512^2x256 Fourier-tridiagonal F32", Config((S(512), S(512), S(256)), ((0, 512.0), (0, 512.0), stretched_faces(S(256), 256.0)), "PPB", ft=np.float32, **LES), 2.0, "rk3"),
 ]

@@ -1,15 +1,18 @@
 #!/bin/bash
-# profiler visit (one GPU): launch list of the bench command, full capture of the staged-ring kernel, full captures of the LES
-# kernels (config-3 physics at 256^3: amd, tendency MN / TT, dct, thomas via the stretched case) -- summarised under profiles/
+# profiler visit (one GPU), sized to finish in ~4 minutes and to bring back < 20 MB: `ncu --set full` of the staged-ring kernel
+# (config 2) and of the LES kernels at 256^3 (config-3 physics: tendency MN / TT, amd, hydrostatic pressure, DCT solver kernels;
+# config-4 physics: thomas), converted to raw CSV on the box (the .ncu-rep files stay there)
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-echo "== launch list of the bench command"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/r2_launches_bench.log 2>&1; echo "rc=$?"
-python tools/summarize_launches.py gpurun_out/r2_launches.csv > gpurun_out/r2_launch_list.txt 2>&1; head -16 gpurun_out/r2_launch_list.txt
-echo "== staged-ring kernel, config 2"
-timeout 300 env OB_MODES=8 OB_FT=f64 ncu --set full --import-source on --clock-control none -k regex:tendency_stage --launch-skip 3 --launch-count 1 -f -o gpurun_out/r2_stage_final python tools/bench_tendency.py 256 2 > gpurun_out/ncu_r2_stage_final.log 2>&1; tail -2 gpurun_out/ncu_r2_stage_final.log
-echo "== one LES step (config-3 physics, 256^3): every kernel"
-timeout 900 ncu --set full --clock-control none --launch-skip 130 --launch-count 110 -f -o gpurun_out/r2_les_step python tools/les_step.py 256 regular > gpurun_out/ncu_r2_les_step.log 2>&1; tail -2 gpurun_out/ncu_r2_les_step.log
-echo "== one LES step on stretched z (config-4 physics, 256x256x128): every kernel"
-timeout 900 ncu --set full --clock-control none --launch-skip 130 --launch-count 110 -f -o gpurun_out/r2_les_stretched_step python tools/les_step.py 256 stretched > gpurun_out/ncu_r2_les_stretched.log 2>&1; tail -2 gpurun_out/ncu_r2_les_stretched.log
-ls -la gpurun_out/*.ncu-rep | tail -5
+cap() {  # cap <tag> <kernel regex> <count> <command...>
+  local tag=$1 rx=$2 cnt=$3; shift 3
+  timeout 240 ncu --set full --clock-control none -k "regex:$rx" --launch-skip 6 --launch-count $cnt -f -o /tmp/$tag "$@" > gpurun_out/ncu_$tag.log 2>&1
+  ncu -i /tmp/$tag.ncu-rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
+  echo "$tag rc=$? $(wc -c < gpurun_out/${tag}_raw.csv) bytes"
+}
+cap r2_stage_final 'tendency_stage' 1 env OB_MODES=8 OB_FT=f64 python tools/bench_tendency.py 256 4
+cap r2_les_tend 'tendency_stage|tendency_march' 3 python tools/les_step.py 256 regular
+cap r2_les_amd 'amd_kernel' 1 python tools/les_step.py 256 regular
+cap r2_les_misc 'hydrostatic_pressure|dct_z_real|update_vec|source_pair|correct_pair|halo_kernel|flux_bc' 10 python tools/les_step.py 256 regular
+cap r2_les_thomas 'thomas_kernel' 1 python tools/les_step.py 256 stretched
+ls -la gpurun_out/*_raw.csv | tail -6
