@@ -457,8 +457,8 @@ struct DistSolverT : ob_solver {
         return OB_OK;
     }
     int32_t setup_pipeline() {
-        const char *ce = getenv("OB_DIST_CHUNKS");   // tuning knob (default 4)
-        nch = std::max(1, std::min(std::min((int)MAXCH, nz), ce ? atoi(ce) : 4));
+        const char *ce = getenv("OB_DIST_CHUNKS");   // tuning knob; measured at N = 8, 256^3 per GPU: 2 chunks 9.78 ms/step, 4: 9.90, 8: 10.24
+        nch = std::max(1, std::min(std::min((int)MAXCH, nz), ce ? atoi(ce) : 2));
         int z = 0;
         for (int c = 0; c < nch; c++) { chlen[c] = nz / nch + (c < nz % nch ? 1 : 0); ch0[c] = z; z += chlen[c]; }
         int nn[2] = {N[1], NxG};

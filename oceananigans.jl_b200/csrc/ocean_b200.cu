@@ -416,7 +416,9 @@ struct SolverT : ob_solver {
         bool any_bounded = false;
         const int ndim_t = tridiag ? 2 : 3;
         for (int d = 0; d < ndim_t; d++) any_bounded |= topo[d] == OB_BOUNDED;
-        if (any_bounded) CUDA_TRY(cudaMalloc(&B, sizeof(C) * n));
+        // work array of the DCT passes, and of a Periodic y transform that is not part of a 2-D (x, y) plan
+        const bool y_alone = topo[1] == OB_PERIODIC && N[1] > 1 && !(topo[0] == OB_PERIODIC && N[0] > 1);
+        if (any_bounded || y_alone) CUDA_TRY(cudaMalloc(&B, sizeof(C) * n));
         // eigenvalues (poisson_eigenvalues.jl:8-32), computed in Float64 then converted to FT
         for (int d = 0; d < 3; d++) {
             std::vector<T> h(N[d]);
@@ -458,9 +460,9 @@ struct SolverT : ob_solver {
                 CUFFT_TRY(cufftSetStream(plan_x, ctx->stream));
                 has_x = true;
             }
-            if (transformed(1)) {  // one z-plane per call: stride Nx, dist 1, batch Nx
+            if (transformed(1)) {  // contiguous y lines of the y-fastest work layout (poisson.cuh: bidx), all Nx Nz of them in one call
                 int nn[1] = {N[1]};
-                CUFFT_TRY(cufftPlanMany(&plan_y, 1, nn, nn, N[0], 1, nn, N[0], 1, CT, N[0]));
+                CUFFT_TRY(cufftPlanMany(&plan_y, 1, nn, nn, 1, N[1], nn, 1, N[1], CT, N[0] * N[2]));
                 CUFFT_TRY(cufftSetStream(plan_y, ctx->stream));
                 has_y = true;
             }
@@ -520,7 +522,15 @@ struct SolverT : ob_solver {
     int32_t fft_dim(C *data, int d, int dir) {
         if (d == 0) return exec(plan_x, data, dir);
         if (d == 2) return exec(plan_z, data, dir);
-        for (int k = 0; k < N[2]; k++) OB_TRY(exec(plan_y, data + (long)k * N[0] * N[1], dir));
+        return exec(plan_y, data, dir);   // `data` is in the y-fastest layout
+    }
+    // 1-D FFT along a Periodic y outside the 2-D (x, y) plan: to the y-fastest layout, one batched call, and back
+    int32_t fft_y_periodic(int dir) {
+        const long n = (long)N[0] * N[1] * N[2];
+        transpose_y_kernel<C><<<nblk(n, 256), 256, 0, ctx->stream>>>(S, B, N[0], N[1], N[2], 0);
+        OB_TRY(exec(plan_y, B, dir));
+        transpose_y_kernel<C><<<nblk(n, 256), 256, 0, ctx->stream>>>(B, S, N[0], N[1], N[2], 1);
+        launches += 2;
         return OB_OK;
     }
     int32_t solve_in_storage() override {
@@ -567,15 +577,15 @@ struct SolverT : ob_solver {
         // forward: Bounded dims first (plan_transforms.jl:160-199), then Periodic
         for (int d = 0; d < ndim_t; d++)
             if (transformed(d) && topo[d] == OB_BOUNDED) {
-                permute_kernel<C><<<nb, 256, 0, st>>>(S, B, N[0], N[1], N[2], d);
+                permute_kernel<C><<<nb, 256, 0, st>>>(S, B, N[0], N[1], N[2], d, d == 1);
                 OB_TRY(fft_dim(B, d, CUFFT_FORWARD));
-                twiddle_fwd_kernel<T, C><<<nb, 256, 0, st>>>(B, S, tw_f[d], N[0], N[1], N[2], d);
+                twiddle_fwd_kernel<T, C><<<nb, 256, 0, st>>>(B, S, tw_f[d], N[0], N[1], N[2], d, d == 1);
                 launches += 2;
             }
         if (has_xy) OB_TRY(exec(plan_xy, S, CUFFT_FORWARD));
         else {
             if (transformed(0) && topo[0] == OB_PERIODIC) OB_TRY(fft_dim(S, 0, CUFFT_FORWARD));
-            if (transformed(1) && topo[1] == OB_PERIODIC) OB_TRY(fft_dim(S, 1, CUFFT_FORWARD));
+            if (transformed(1) && topo[1] == OB_PERIODIC) OB_TRY(fft_y_periodic(CUFFT_FORWARD));
         }
         if (transformed(2) && topo[2] == OB_PERIODIC) OB_TRY(fft_dim(S, 2, CUFFT_FORWARD));
         if (tridiag) {
@@ -589,14 +599,14 @@ struct SolverT : ob_solver {
         if (transformed(2) && topo[2] == OB_PERIODIC) OB_TRY(fft_dim(S, 2, CUFFT_INVERSE));
         if (has_xy) OB_TRY(exec(plan_xy, S, CUFFT_INVERSE));
         else {
-            if (transformed(1) && topo[1] == OB_PERIODIC) OB_TRY(fft_dim(S, 1, CUFFT_INVERSE));
+            if (transformed(1) && topo[1] == OB_PERIODIC) OB_TRY(fft_y_periodic(CUFFT_INVERSE));
             if (transformed(0) && topo[0] == OB_PERIODIC) OB_TRY(fft_dim(S, 0, CUFFT_INVERSE));
         }
         for (int d = ndim_t - 1; d >= 0; d--)
             if (transformed(d) && topo[d] == OB_BOUNDED) {
-                twiddle_bwd_kernel<T, C><<<nb, 256, 0, st>>>(S, B, tw_b[d], N[0], N[1], N[2], d);
+                twiddle_bwd_kernel<T, C><<<nb, 256, 0, st>>>(S, B, tw_b[d], N[0], N[1], N[2], d, d == 1);
                 OB_TRY(fft_dim(B, d, CUFFT_INVERSE));
-                unpermute_kernel<C><<<nb, 256, 0, st>>>(B, S, N[0], N[1], N[2], d);
+                unpermute_kernel<C><<<nb, 256, 0, st>>>(B, S, N[0], N[1], N[2], d, d == 1);
                 launches += 2;
             }
         CUDA_TRY(cudaGetLastError());

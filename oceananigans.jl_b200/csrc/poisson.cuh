@@ -24,27 +24,44 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 // Makhoul permutation (index_permutations.jl:18-36), 0-based: even i -> i/2 ; odd i -> N-1-(i-1)/2
 __device__ __forceinline__ int makhoul(int i, int N) { return (i & 1) ? N - 1 - (i - 1) / 2 : i / 2; }
 
+// Layout of the work array B of the y transform: `ty` = 1 stores it with y fastest, [k][i][j], so that the 1-D FFT along y is ONE
+// contiguous batched cuFFT call over all Nx Nz lines (in the natural layout a y line has stride Nx and cuFFT's single batch
+// dimension covers one z plane per call: Nz launches per transform).  The permute / twiddle passes around the FFT exist anyway;
+// they read or write B through this index.
+__device__ __forceinline__ long bidx(int i, int j, int k, int Nx, int Ny, int ty) {
+    return ty ? j + (long)Ny * (i + (long)Nx * k) : i + (long)Nx * (j + (long)Ny * k);
+}
+// plain change of layout (Periodic y outside the 2-D (x, y) plan): B[k][i][j] = A[k][j][i] and back
+template <typename C>
+__global__ void __launch_bounds__(256) transpose_y_kernel(const C *__restrict__ A, C *__restrict__ B, int Nx, int Ny, int Nz, int back) {
+    const long n = (long)Nx * Ny * Nz;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
+    if (back) B[t] = A[bidx(i, j, k, Nx, Ny, 1)];
+    else B[bidx(i, j, k, Nx, Ny, 1)] = A[t];
+}
 // B[perm_d(idx)] = A[idx] along dimension d
 template <typename C>
-__global__ void __launch_bounds__(256) permute_kernel(const C *__restrict__ A, C *__restrict__ B, int Nx, int Ny, int Nz, int d) {
+__global__ void __launch_bounds__(256) permute_kernel(const C *__restrict__ A, C *__restrict__ B, int Nx, int Ny, int Nz, int d, int ty = 0) {
     const long n = (long)Nx * Ny * Nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
     int ii = i, jj = j, kk = k;
     if (d == 0) ii = makhoul(i, Nx); else if (d == 1) jj = makhoul(j, Ny); else kk = makhoul(k, Nz);
-    B[ii + (long)Nx * (jj + (long)Ny * kk)] = A[t];
+    B[bidx(ii, jj, kk, Nx, Ny, ty)] = A[t];
 }
 // forward twiddle: A = 2 * real(ω_4N^k * B)   (discrete_transforms.jl:172-175; twiddles :48-78)
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) twiddle_fwd_kernel(const C *__restrict__ B, C *__restrict__ A, const C *__restrict__ w,
-                                                          int Nx, int Ny, int Nz, int d) {
+                                                          int Nx, int Ny, int Nz, int d, int ty = 0) {
     const long n = (long)Nx * Ny * Nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
     int q = d == 0 ? i : d == 1 ? j : k;
-    C v = cmul(w[q], B[t]);
+    C v = cmul(w[q], B[ty ? bidx(i, j, k, Nx, Ny, 1) : t]);
     C o;
     o.x = 2 * v.x;
     o.y = 0;
@@ -53,24 +70,24 @@ __global__ void __launch_bounds__(256) twiddle_fwd_kernel(const C *__restrict__ 
 // backward twiddle: B = A * ω_4N^{-k} (k = 0 halved)   (discrete_transforms.jl:177-183)
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) twiddle_bwd_kernel(const C *__restrict__ A, C *__restrict__ B, const C *__restrict__ w,
-                                                          int Nx, int Ny, int Nz, int d) {
+                                                          int Nx, int Ny, int Nz, int d, int ty = 0) {
     const long n = (long)Nx * Ny * Nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
     int q = d == 0 ? i : d == 1 ? j : k;
-    B[t] = cmul(A[t], w[q]);
+    B[ty ? bidx(i, j, k, Nx, Ny, 1) : t] = cmul(A[t], w[q]);
 }
 // unpermute + real: A[idx] = real(B[perm_d(idx)])
 template <typename C>
-__global__ void __launch_bounds__(256) unpermute_kernel(const C *__restrict__ B, C *__restrict__ A, int Nx, int Ny, int Nz, int d) {
+__global__ void __launch_bounds__(256) unpermute_kernel(const C *__restrict__ B, C *__restrict__ A, int Nx, int Ny, int Nz, int d, int ty = 0) {
     const long n = (long)Nx * Ny * Nz;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long)Nx * Ny));
     int ii = i, jj = j, kk = k;
     if (d == 0) ii = makhoul(i, Nx); else if (d == 1) jj = makhoul(j, Ny); else kk = makhoul(k, Nz);
-    C v = B[ii + (long)Nx * (jj + (long)Ny * kk)];
+    C v = B[bidx(ii, jj, kk, Nx, Ny, ty)];
     v.y = 0;
     A[t] = v;
 }
