@@ -110,6 +110,14 @@ typedef struct {
     int32_t amd_has_cb;
     int32_t vertically_implicit; /* ScalarDiffusivity(VerticallyImplicitTimeDiscretization(); ...) (scalar_diffusivity.jl:113-137):
                                   * z-Bounded grids only; the substeps then run implicit_step! on every prognostic field */
+    /* Smagorinsky(coefficient = DynamicCoefficient(averaging = dims; minimum_numerator)) -- DynamicSmagorinsky with a
+     * directionally averaged coefficient (dynamic_coefficient.jl:107-118, 208-212, 306-351).  dynamic != 0: `cs` is ignored and
+     * c_s^2 = max(<LM>, minimum_numerator) / <MM> is recomputed in every update_state! (schedule IterationInterval(1));
+     * averaging_dims: bit d-1 set = dimension d is averaged ((1, 2) -> 3, Colon / (1, 2, 3) -> 7).  LagrangianAveraging,
+     * other schedules, Flat directions and distributed grids: OB_ERR_UNSUPPORTED. */
+    int32_t dynamic;
+    int32_t averaging_dims;
+    double minimum_numerator;
 } ob_closure_desc;
 
 /* NonhydrostaticModel(grid; advection, closure, buoyancy, coriolis, tracers, timestepper)

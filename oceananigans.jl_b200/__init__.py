@@ -14,7 +14,7 @@ from .grids import B200, CPU, RectilinearGrid, Periodic, Bounded, Flat, Float32,
 from .fields import (Field, FieldBoundaryConditions, FluxBoundaryCondition, ValueBoundaryCondition,  # noqa: F401
                      GradientBoundaryCondition, OpenBoundaryCondition)
 from .models import (NonhydrostaticModel, Centered, WENO, ScalarDiffusivity, Smagorinsky, SmagorinskyLilly,  # noqa: F401
-                     AnisotropicMinimumDissipation, ExplicitTimeDiscretization,
+                     DynamicSmagorinsky, LagrangianAveraging, AnisotropicMinimumDissipation, ExplicitTimeDiscretization,
                      VerticallyImplicitTimeDiscretization, BuoyancyTracer, SeawaterBuoyancy, LinearEquationOfState, FPlane,
                      time_step, set, update_state)
 from .simulations import (Simulation, run, Callback, IterationInterval, TimeInterval, TimeStepWizard,  # noqa: F401

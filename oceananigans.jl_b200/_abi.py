@@ -45,6 +45,7 @@ class ClosureDesc(C.Structure):
         ("kind", C.c_int32), ("nu", C.c_double), ("kappa", C.c_double * OB_MAX_TRACERS),
         ("cs", C.c_double), ("lilly", C.c_int32), ("cb", C.c_double), ("Pr", C.c_double * OB_MAX_TRACERS),
         ("Cnu", C.c_double), ("Ckappa", C.c_double * OB_MAX_TRACERS), ("amd_has_cb", C.c_int32), ("vertically_implicit", C.c_int32),
+        ("dynamic", C.c_int32), ("averaging_dims", C.c_int32), ("minimum_numerator", C.c_double),
     ]
 
 

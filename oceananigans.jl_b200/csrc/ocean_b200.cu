@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <initializer_list>
 #include <cmath>
 #include <string>
 #include <type_traits>
@@ -28,6 +29,7 @@
 #include "stencils.cuh"
 #include "tendency.cuh"
 #include "closures.cuh"
+#include "dynsmag.cuh"
 #include "tend_launch.h"
 
 using namespace ob;
@@ -814,6 +816,10 @@ struct ModelT : ob_model {
             if (east != west) { cudaIpcCloseMemHandle(east_stage); cudaIpcCloseMemHandle(east_flags); }
         }
         cudaFree(d_stage); cudaFree(d_flags); cudaFree(d_blockctr); cudaFree(d_ivd); cudaFree(d_amd_tab);
+        for (int m = 0; m < OB_MAXCL; m++) {
+            T *dq[8] = {dynw[m].ub, dynw[m].vb, dynw[m].wb, dynw[m].Sg, dynw[m].Sb, dynw[m].LM, dynw[m].MM, dynw[m].J};
+            for (int q = 0; q < 8; q++) cudaFree(dq[q]);
+        }
         delete solver;
         for (auto e : pool) cudaEventDestroy(e);
     }
@@ -905,6 +911,16 @@ struct ModelT : ob_model {
             if (g.topo[k] != FLAT && g.H[k] < 1) return fail(OB_ERR_INVALID, "halo must be >= 1");
             if (g.topo[k] == PERIODIC && g.N[k] < g.H[k]) return fail(OB_ERR_INVALID, "periodic size smaller than halo");
         }
+        for (int m = 0; m < d->n_closures; m++)
+            if (d->closures[m].dynamic) {
+                if (d->closures[m].kind != OB_CLOSURE_SMAGORINSKY) return fail(OB_ERR_INVALID, "a dynamic coefficient belongs to a Smagorinsky closure");
+                if (d->closures[m].averaging_dims < 1 || d->closures[m].averaging_dims > 7) return fail(OB_ERR_INVALID, "DynamicSmagorinsky: averaging_dims must name at least one of the dimensions 1, 2, 3");
+                if (ctx->world > 1) return fail(OB_ERR_UNSUPPORTED, "DynamicSmagorinsky on a distributed grid is not supported");
+                for (int k = 0; k < 3; k++) {
+                    if (g.topo[k] == FLAT) return fail(OB_ERR_UNSUPPORTED, "DynamicSmagorinsky with a Flat direction is not supported");
+                    if (g.H[k] < 2) return fail(OB_ERR_INVALID, "DynamicSmagorinsky needs a halo of at least 2 cells");
+                }
+            }
         for (int m = 0; m < d->n_closures; m++)
             if (d->closures[m].vertically_implicit) {
                 if (g.topo[2] != BOUNDED)
@@ -1246,7 +1262,9 @@ struct ModelT : ob_model {
             if (kind == OB_CLOSURE_SCALAR_DIFFUSIVITY) continue;
             const int bs = 128;
             dim3 grid(nblk(g.N[0], bs) * (unsigned)g.N[1] * (unsigned)g.N[2], 1);
-            if (kind == OB_CLOSURE_SMAGORINSKY) {
+            if (kind == OB_CLOSURE_SMAGORINSKY && desc.closures[m].dynamic) {
+                OB_TRY(dynamic_smagorinsky(m));
+            } else if (kind == OB_CLOSURE_SMAGORINSKY) {
                 smagorinsky_kernel<T><<<grid, bs, 0, ctx->stream>>>(P, m);
                 launches++;
             } else {
@@ -1258,6 +1276,59 @@ struct ModelT : ob_model {
                 launches++;
             }
         }
+        CUDA_TRY(cudaGetLastError());
+        return OB_OK;
+    }
+    // DynamicSmagorinsky (dynsmag.cuh): library-owned work fields per closure -- the test-filtered velocities, Σ, Σ̄ (registered as
+    // fields OB_FIELD_INTERNAL0 + 2m, + 2m + 1 with the default centre boundary conditions, so that the ordinary halo fill serves
+    // them: fill_halo_regions!(Σ), fill_halo_regions!(Σ̄), dynamic_coefficient.jl:320-321), LM, MM and their averages
+    static constexpr int OB_FIELD_INTERNAL0 = 112;
+    struct DynWork { T *ub = nullptr, *vb = nullptr, *wb = nullptr, *Sg = nullptr, *Sb = nullptr, *LM = nullptr, *MM = nullptr, *J = nullptr; };
+    DynWork dynw[OB_MAXCL];
+    static DField<T> dview(const Fld<T> &f, const T *p) { DField<T> d; d.p = p; d.off = f.off; d.sy = f.sy; d.sz = f.sz; return d; }
+    int32_t dynamic_smagorinsky(int m) {
+        DynWork &w = dynw[m];
+        const int idS = OB_FIELD_INTERNAL0 + 2 * m, idB = idS + 1;
+        const int avg = desc.closures[m].averaging_dims, ax = avg & 1, ay = (avg >> 1) & 1, az = (avg >> 2) & 1;
+        const long nout = (long)(ax ? 1 : g.N[0]) * (ay ? 1 : g.N[1]) * (az ? 1 : g.N[2]);
+        if (!w.ub) {
+            ob_bc_desc bc;
+            memset(&bc, 0, sizeof(bc));
+            for (int d = 0; d < 3; d++)
+                for (int sd = 0; sd < 2; sd++) bc.kind[2 * d + sd] = g.topo[d] == PERIODIC ? OB_BC_PERIODIC : OB_BC_FLUX;   // NoFlux
+            setup_field(idS, 0, 0, 0, bc);
+            setup_field(idB, 0, 0, 0, bc);
+            const size_t nu_ = F[OB_FIELD_U].count(), nv_ = F[OB_FIELD_V].count(), nw_ = F[OB_FIELD_W].count(), nc_ = F[idS].count();
+            CUDA_TRY(cudaMalloc(&w.ub, sizeof(T) * nu_)); CUDA_TRY(cudaMalloc(&w.vb, sizeof(T) * nv_)); CUDA_TRY(cudaMalloc(&w.wb, sizeof(T) * nw_));
+            CUDA_TRY(cudaMemsetAsync(w.ub, 0, sizeof(T) * nu_, ctx->stream)); CUDA_TRY(cudaMemsetAsync(w.vb, 0, sizeof(T) * nv_, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(w.wb, 0, sizeof(T) * nw_, ctx->stream));
+            T **cq[4] = {&w.Sg, &w.Sb, &w.LM, &w.MM};
+            for (int q = 0; q < 4; q++) { CUDA_TRY(cudaMalloc(cq[q], sizeof(T) * nc_)); CUDA_TRY(cudaMemsetAsync(*cq[q], 0, sizeof(T) * nc_, ctx->stream)); }
+            CUDA_TRY(cudaMalloc(&w.J, sizeof(T) * 2 * nout));
+            F[idS].ptr = w.Sg; F[idB].ptr = w.Sb;
+        }
+        DynP<T> P;
+        memset(&P, 0, sizeof(P));
+        for (int d = 0; d < 3; d++) { P.N[d] = g.N[d]; P.H[d] = g.H[d]; }
+        P.dx = g.dx; P.dy = g.dy; P.rdx = g.rdx; P.rdy = g.rdy; P.dz = g.dz; P.rdz = g.rdz;
+        P.dzc = g.dzc; P.rdzc = g.rdzc; P.rdzf = g.rdzf;
+        const Fld<T> fu = fld(OB_FIELD_U), fv = fld(OB_FIELD_V), fw = fld(OB_FIELD_W), fc = fld(idS);
+        P.u = dview(fu, fu.p); P.v = dview(fv, fv.p); P.w = dview(fw, fw.p);
+        P.ub = dview(fu, w.ub); P.vb = dview(fv, w.vb); P.wb = dview(fw, w.wb);
+        P.Sg = dview(fc, w.Sg); P.Sb = dview(fc, w.Sb); P.LM = dview(fc, w.LM); P.MM = dview(fc, w.MM);
+        P.ub_w = w.ub; P.vb_w = w.vb; P.wb_w = w.wb; P.Sg_w = w.Sg; P.Sb_w = w.Sb; P.LM_w = w.LM; P.MM_w = w.MM;
+        const long next = (long)(g.N[0] + 2 * g.H[0] - 2) * (g.N[1] + 2 * g.H[1] - 2) * (g.N[2] + 2 * g.H[2] - 2);
+        const long ncell = (long)g.N[0] * g.N[1] * g.N[2];
+        dyn_filter_kernel<T><<<nblk(next, 128), 128, 0, ctx->stream>>>(P);
+        dyn_sigma_kernel<T><<<nblk(ncell, 128), 128, 0, ctx->stream>>>(P);
+        launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        OB_TRY(fill_halos({idS, idB}, true));
+        dyn_lmmm_kernel<T><<<nblk(ncell, 128), 128, 0, ctx->stream>>>(P);
+        dyn_average_kernel<T><<<(unsigned)nout, 256, 0, ctx->stream>>>(P, ax, ay, az, w.J);
+        const Fld<T> fn = fld(OB_FIELD_NUE0 + m);
+        dyn_viscosity_kernel<T><<<nblk(ncell, 128), 128, 0, ctx->stream>>>(P, ax, ay, az, w.J, (T)desc.closures[m].minimum_numerator, fn.p, fn.off, fn.sy, fn.sz);
+        launches += 3;
         CUDA_TRY(cudaGetLastError());
         return OB_OK;
     }

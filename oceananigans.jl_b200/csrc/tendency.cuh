@@ -229,7 +229,8 @@ template <typename T> __device__ __forceinline__ T Gu_finish(const TendP<T> &P, 
         T I = fy ? Ix(j) : mul_rn(T(0.5), add_rn(Ix(j), Ix(j + 1)));
         r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (DXF * DZC(k))));
     }
-    if (P.has_pHY) r = r - (P.g.topo[0] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i - 1, j, k)) * P.g.rdx;
+    // (-∂x pHY' rounded product by product, as the reference: every kernel form uses the same pinned expression)
+    if (P.has_pHY) r = sub_rn(r, mul_rn(P.g.topo[0] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i - 1, j, k), P.g.rdx));
     if (P.ncl > 0) {
         T t = div_tau1(P, 0, i, j, k);
         for (int m = 1; m < P.ncl; m++) t = t + div_tau1(P, m, i, j, k);
@@ -253,7 +254,7 @@ template <typename T> __device__ __forceinline__ T Gv_finish(const TendP<T> &P, 
         T I = fy ? Ix(j) : mul_rn(T(0.5), add_rn(Ix(j - 1), Ix(j)));
         r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (DYF * DZC(k))));
     }
-    if (P.has_pHY) r = r - (P.g.topo[1] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i, j - 1, k)) * P.g.rdy;
+    if (P.has_pHY) r = sub_rn(r, mul_rn(P.g.topo[1] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i, j - 1, k), P.g.rdy));
     if (P.ncl > 0) {
         T t = div_tau2(P, 0, i, j, k);
         for (int m = 1; m < P.ncl; m++) t = t + div_tau2(P, m, i, j, k);

@@ -237,7 +237,7 @@ struct FastTerms {
                 const T I = interp4_rn(A, ld(v, -1, 0, 0), ld(v, 0, 0, 0), ld(v, -1, 1, 0), ld(v, 0, 1, 0));
                 r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (G.dx * dzC(0))));
             }
-            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, -1, 0, 0)) * G.rdx; }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = sub_rn(r, mul_rn(ld(ph, 0, 0, 0) - ld(ph, -1, 0, 0), G.rdx)); }
         } else if constexpr (WHICH == 1) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
@@ -245,7 +245,7 @@ struct FastTerms {
                 const T I = interp4_rn(A, ld(u, 0, -1, 0), ld(u, 1, -1, 0), ld(u, 0, 0, 0), ld(u, 1, 0, 0));
                 r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (G.dy * dzC(0))));
             }
-            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ld(ph, 0, 0, 0) - ld(ph, 0, -1, 0)) * G.rdy; }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = sub_rn(r, mul_rn(ld(ph, 0, 0, 0) - ld(ph, 0, -1, 0), G.rdy)); }
         } else if constexpr (WHICH == 2) {
             if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
         }

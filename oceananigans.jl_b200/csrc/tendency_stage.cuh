@@ -261,7 +261,7 @@ struct StageTerms {
                 const T I = interp4_rn(A, slot(1, -1, 0, 0), slot(1, 0, 0, 0), slot(1, -1, 1, 0), slot(1, 0, 1, 0));
                 r = sub_rn(r, mul_rn(mul_rn(-fbar, I), 1 / (G.dx * dzC(0))));
             }
-            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, -1, 0, 0)) * G.rdx; }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = sub_rn(r, mul_rn(ldg(ph, 0, 0, 0) - ldg(ph, -1, 0, 0), G.rdx)); }
         } else if constexpr (WHICH == 1) {
             if (P.has_cor) {
                 const T fbar = T(0.5) * (P.f + P.f);
@@ -269,7 +269,7 @@ struct StageTerms {
                 const T I = interp4_rn(A, slot(0, 0, -1, 0), slot(0, 1, -1, 0), slot(0, 0, 0, 0), slot(0, 1, 0, 0));
                 r = sub_rn(r, mul_rn(mul_rn(fbar, I), 1 / (G.dy * dzC(0))));
             }
-            if (P.has_pHY) { const T *ph = at(P.pHY); r = r - (ldg(ph, 0, 0, 0) - ldg(ph, 0, -1, 0)) * G.rdy; }
+            if (P.has_pHY) { const T *ph = at(P.pHY); r = sub_rn(r, mul_rn(ldg(ph, 0, 0, 0) - ldg(ph, 0, -1, 0), G.rdy)); }
         } else if constexpr (WHICH == 2) {
             if (!P.has_pHY && P.buoy != BUOY_NONE) r = r + T(0.5) * (bpert(-1) + bpert(0));
         }

@@ -152,6 +152,7 @@ struct ObBcDesc; kind::NTuple{6, Int32}; value::NTuple{6, Float64}; end
 struct ObClosureDesc
     kind::Int32; nu::Float64; kappa::NTuple{8, Float64}; cs::Float64; lilly::Int32; cb::Float64; Pr::NTuple{8, Float64}
     Cnu::Float64; Ckappa::NTuple{8, Float64}; amd_has_cb::Int32; vertically_implicit::Int32
+    dynamic::Int32; averaging_dims::Int32; minimum_numerator::Float64
 end
 struct ObModelDesc
     grid::ObGridDesc
@@ -218,23 +219,31 @@ bc_array_ptrs(bcs::FieldBoundaryConditions) =
     [(bc isa BoundaryCondition && bc.condition isa B200Array) ? pointer(bc.condition) : C_NULL for bc in sides(bcs)]
 
 pad8(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, 8)
-const NO_CLOSURE = ObClosureDesc(0, 0.0, pad8(()), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0, 0)
+const NO_CLOSURE = ObClosureDesc(0, 0.0, pad8(()), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0, 0, 0, 0, 0.0)
 closure_desc(c::ScalarDiffusivity, names) =
     (c.ν isa Number && all(κ -> κ isa Number, values(c.κ))) ?
         ObClosureDesc(1, Float64(c.ν), pad8(values(c.κ)), 0.0, 0, 0.0, pad8(()), 0.0, pad8(()), 0,
-                      Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization)) : unsupported("a function-valued diffusivity")
+                      Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization), 0, 0, 0.0) : unsupported("a function-valued diffusivity")
 function closure_desc(c::Smagorinsky, names)
     coeff = c.coefficient
+    vi = Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization)
+    if coeff isa TC.Smagorinskys.DynamicCoefficient   # DynamicSmagorinsky: directional averaging only, updated every iteration
+        avg = coeff.averaging
+        (avg isa TC.Smagorinskys.LagrangianAveraging) && unsupported("DynamicSmagorinsky with LagrangianAveraging")
+        (coeff.schedule isa Oceananigans.Utils.IterationInterval && coeff.schedule.interval == 1 && coeff.schedule.offset == 0) ||
+            unsupported("DynamicCoefficient schedules other than IterationInterval(1)")
+        dims = avg isa Colon ? (1, 2, 3) : avg
+        mask = Int32(sum(1 << (d - 1) for d in dims))
+        return ObClosureDesc(2, 0.0, pad8(()), 0.0, 0, 0.0, pad8(values(c.Pr)), 0.0, pad8(()), 0, vi, 1, mask, Float64(coeff.minimum_numerator))
+    end
     lilly = !(coeff isa Number)
     cs = lilly ? coeff.smagorinsky : coeff
     cb = lilly ? coeff.reduction_factor : 0.0
-    (cs isa Number) || unsupported("DynamicSmagorinsky")
-    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0,
-                         Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization))
+    return ObClosureDesc(2, 0.0, pad8(()), Float64(cs), Int32(lilly), Float64(cb), pad8(values(c.Pr)), 0.0, pad8(()), 0, vi, 0, 0, 0.0)
 end
 closure_desc(c::AnisotropicMinimumDissipation, names) =
     ObClosureDesc(3, 0.0, pad8(()), 0.0, 0, c.Cb === nothing ? 0.0 : Float64(c.Cb), pad8(()), Float64(c.Cν), pad8(values(c.Cκ)), Int32(c.Cb !== nothing),
-                  Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization))
+                  Int32(TC.time_discretization(c) isa VerticallyImplicitTimeDiscretization), 0, 0, 0.0)
 closure_desc(c, names) = unsupported("closure $(typeof(c))")
 closure_tuple(model) = model.closure === nothing ? () : model.closure isa Tuple ? model.closure : (model.closure,)
 

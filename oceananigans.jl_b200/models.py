@@ -77,7 +77,32 @@ class Smagorinsky:
         self.time_discretization = _time_discretization(time_discretization)
         self.vertically_implicit = isinstance(self.time_discretization, VerticallyImplicitTimeDiscretization)
         self.cs, self.Pr, self.lilly, self.cb = coefficient, Pr, False, 0.0
+        self.dynamic = None   # DynamicSmagorinsky(): {"averaging": dims, "schedule": ..., "minimum_numerator": ...}
         self.required_halo = 2
+
+
+class LagrangianAveraging:
+    """averaging = LagrangianAveraging() of DynamicCoefficient: outside the B200 hot path (rejected at model construction)"""
+
+
+def DynamicSmagorinsky(time_discretization=None, averaging=None, Pr=1.0, schedule=None, minimum_numerator=1e-32):
+    """DynamicSmagorinsky([time_discretization]; averaging, Pr, schedule, minimum_numerator) (dynamic_coefficient.jl:107-118): a
+    Smagorinsky closure whose coefficient is computed from the flow (Bou-Zeid et al. 2005, scale-invariant).  `averaging`: an
+    integer or a tuple of integers (dimensions averaged over), or `slice(None)` / "colon" for all three; the reference default,
+    LagrangianAveraging(), is not on the B200 hot path.  Only the default schedule (every iteration) is supported."""
+    s = Smagorinsky(time_discretization, coefficient=0.0, Pr=Pr)
+    if averaging is None or isinstance(averaging, LagrangianAveraging):
+        averaging = LagrangianAveraging()
+    elif isinstance(averaging, int):
+        averaging = (averaging,)
+    elif averaging == "colon" or averaging == slice(None):
+        averaging = (1, 2, 3)
+    else:
+        averaging = tuple(int(d) for d in averaging)
+    if not isinstance(averaging, LagrangianAveraging) and (not averaging or any(d not in (1, 2, 3) for d in averaging)):
+        raise ValueError("averaging dimensions must be a subset of (1, 2, 3)")
+    s.dynamic = {"averaging": averaging, "schedule": schedule, "minimum_numerator": minimum_numerator}
+    return s
 
 
 def SmagorinskyLilly(time_discretization=None, C=0.16, Cb=1.0, Pr=1.0):
@@ -229,6 +254,15 @@ class NonhydrostaticModel:
             elif isinstance(c, Smagorinsky):
                 cd.kind, cd.cs, cd.lilly, cd.cb = _abi.OB_CLOSURE_SMAGORINSKY, float(FT(c.cs)), int(c.lilly), float(FT(c.cb))
                 cd.vertically_implicit = int(c.vertically_implicit)
+                if c.dynamic is not None:
+                    if isinstance(c.dynamic["averaging"], LagrangianAveraging):
+                        raise _abi.OceanB200Error(-3, "DynamicSmagorinsky with LagrangianAveraging is outside the B200 hot path "
+                                                      "(directional averaging, e.g. averaging=(1, 2), is supported)")
+                    if c.dynamic["schedule"] is not None:
+                        raise _abi.OceanB200Error(-3, "DynamicCoefficient schedules other than IterationInterval(1) are not supported")
+                    cd.dynamic = 1
+                    cd.averaging_dims = sum(1 << (d - 1) for d in {*c.dynamic["averaging"]})   # (`set` is set!(model; ...) in this module)
+                    cd.minimum_numerator = float(FT(c.dynamic["minimum_numerator"]))
                 for t in range(nt):
                     cd.Pr[t] = float(FT(_per_tracer(c.Pr, self.tracer_names, t)))
             elif isinstance(c, AnisotropicMinimumDissipation):

@@ -448,9 +448,19 @@ class Smagorinsky:
     """Smagorinsky([time_discretization]; coefficient, Pr) (smagorinsky.jl:76-84); vertically_implicit =
     VerticallyImplicitTimeDiscretization(): the implicit step takes nu_e interpolated to the nodes of its coefficients"""
 
-    def __init__(self, coefficient=0.16, Pr=1.0, lilly=False, Cb=1.0, vertically_implicit=False):
+    def __init__(self, coefficient=0.16, Pr=1.0, lilly=False, Cb=1.0, vertically_implicit=False, dynamic=None):
         self.cs, self.Pr, self.lilly, self.cb = coefficient, Pr, lilly, Cb
         self.vertically_implicit = bool(vertically_implicit)
+        # DynamicCoefficient(averaging = dims; minimum_numerator) (dynamic_coefficient.jl:208-212): {"averaging": (1, 2), ...}
+        self.dynamic = None if dynamic is None else {"averaging": tuple(dynamic.get("averaging", (1, 2))),
+                                                     "minimum_numerator": dynamic.get("minimum_numerator", 1e-32)}
+
+
+def DynamicSmagorinsky(averaging=(1, 2), Pr=1.0, minimum_numerator=1e-32, vertically_implicit=False):
+    """DynamicSmagorinsky(; averaging, Pr, minimum_numerator) with a directional average (dynamic_coefficient.jl:107-118)"""
+    averaging = (averaging,) if isinstance(averaging, int) else tuple(averaging)
+    return Smagorinsky(coefficient=0.0, Pr=Pr, vertically_implicit=vertically_implicit,
+                       dynamic={"averaging": averaging, "minimum_numerator": minimum_numerator})
 
 
 def SmagorinskyLilly(C=0.16, Cb=1.0, Pr=1.0, vertically_implicit=False):
@@ -496,6 +506,7 @@ class Model:
         locs = ("fcc", "cfc", "ccf") + ("ccc",) * len(self.tracers)
         self.Gn = [Field(g, l, name="Gn_" + n) for n, l in zip(names, locs)]
         self.Gm = [Field(g, l, name="Gm_" + n) for n, l in zip(names, locs)]
+        self.dynamic_fields = {}   # DynamicSmagorinsky: closure index -> {Sigma, Sigmabar, LM, MM, JLM, JMM} (oracle/dynsmag.py)
         self.nue = [mk("nue%d" % m, "ccc", aux=True) if not isinstance(c, ScalarDiffusivity) else None
                     for m, c in enumerate(self.closures)]
         self.kappae = [[mk("kappae%d_%s" % (m, n), "ccc", aux=True) for n in self.tracer_names]
@@ -610,7 +621,10 @@ class Model:
     def compute_closure_fields(self):
         p = None
         for m, c in enumerate(self.closures):
-            if isinstance(c, Smagorinsky):
+            if isinstance(c, Smagorinsky) and c.dynamic is not None:
+                from .dynsmag import compute_dynamic_smagorinsky
+                compute_dynamic_smagorinsky(self, m)
+            elif isinstance(c, Smagorinsky):
                 p = p or self.params()
                 self._fn("orc_smagorinsky_viscosity")(C.byref(p), m)
             elif isinstance(c, AnisotropicMinimumDissipation):

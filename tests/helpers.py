@@ -50,6 +50,8 @@ class Config:
                 cl.append(M.SmagorinskyLilly(C=c[1], Cb=c[2], Pr=c[3], vertically_implicit=c[0] == "vi_lilly"))
             elif c[0] in ("amd", "vi_amd"):
                 cl.append(M.AnisotropicMinimumDissipation(Cb=c[1] if len(c) > 1 else None, vertically_implicit=c[0] == "vi_amd"))
+            elif c[0] in ("dynsmag", "vi_dynsmag"):   # ("dynsmag", averaging dims, Pr)
+                cl.append(M.DynamicSmagorinsky(averaging=c[1], Pr=c[2], vertically_implicit=c[0] == "vi_dynsmag"))
         bcs = {}
         for name, sides in self.bcs.items():
             bcs[name] = {s: (k.lower(), v) for s, (k, v) in sides.items()}
@@ -87,6 +89,9 @@ class Config:
             elif c[0] in ("amd", "vi_amd"):
                 td = (ob.VerticallyImplicitTimeDiscretization(),) if c[0] == "vi_amd" else ()
                 cl.append(ob.AnisotropicMinimumDissipation(*td, Cb=c[1] if len(c) > 1 else None))
+            elif c[0] in ("dynsmag", "vi_dynsmag"):
+                td = (ob.VerticallyImplicitTimeDiscretization(),) if c[0] == "vi_dynsmag" else ()
+                cl.append(ob.DynamicSmagorinsky(*td, averaging=c[1], Pr=c[2]))
         b = self.buoyancy
         if b is None:
             buoy = None
@@ -117,6 +122,13 @@ class Config:
         for name, loc in (("u", "fcc"), ("v", "cfc"), ("w", "ccf")):
             d = "uvw".index(name)
             a = amp * rng.uniform(-1, 1, shape(loc))
+            if any(c[0] in ("dynsmag", "vi_dynsmag") for c in self.closure):
+                # a resolved large-scale flow under the noise: the dynamic procedure returns c_s = 0 for pure noise (<LM> < 0)
+                kk, jj, ii = np.meshgrid(*(np.arange(n) / max(n - 1, 1) for n in shape(loc)), indexing="ij")
+                ph = 2 * np.pi
+                a = a + 5 * amp * [np.sin(ph * ii) * np.cos(ph * jj) * np.cos(ph * kk) + 0.3 * np.sin(2 * ph * ii + 1) * np.cos(3 * ph * jj) * np.cos(2 * ph * kk),
+                                   -np.cos(ph * ii) * np.sin(ph * jj) * np.cos(ph * kk) + 0.3 * np.cos(2 * ph * ii) * np.sin(3 * ph * jj + 2) * np.cos(ph * kk),
+                                   0.4 * np.cos(2 * ph * ii) * np.cos(ph * jj) * np.sin(2 * ph * kk)][d]
             if self.topology[d] == "F":
                 a[...] = 0  # no flow in a Flat direction
             out[name] = a.astype(self.ft)
