@@ -162,19 +162,19 @@ template <typename T> struct VFlux {
 template <typename T> __device__ __forceinline__ T div_tau1(const TendP<T> &P, int m, int i, int j, int k) {
     VFlux<T> F(P, m);
     T Vi = P.g.rVc(k);
-    return Vi * (DELTA_(F.ux(i, j, k), F.ux(i - 1, j, k), 0) + DELTA_(F.uy(i, j + 1, k), F.uy(i, j, k), 1) +
+    return mul_rn(Vi, DELTA_(F.ux(i, j, k), F.ux(i - 1, j, k), 0) + DELTA_(F.uy(i, j + 1, k), F.uy(i, j, k), 1) +
                  DELTA_(F.uz(i, j, k + 1), F.uz(i, j, k), 2));
 }
 template <typename T> __device__ __forceinline__ T div_tau2(const TendP<T> &P, int m, int i, int j, int k) {
     VFlux<T> F(P, m);
     T Vi = P.g.rVc(k);
-    return Vi * (DELTA_(F.vx(i + 1, j, k), F.vx(i, j, k), 0) + DELTA_(F.vy(i, j, k), F.vy(i, j - 1, k), 1) +
+    return mul_rn(Vi, DELTA_(F.vx(i + 1, j, k), F.vx(i, j, k), 0) + DELTA_(F.vy(i, j, k), F.vy(i, j - 1, k), 1) +
                  DELTA_(F.vz(i, j, k + 1), F.vz(i, j, k), 2));
 }
 template <typename T> __device__ __forceinline__ T div_tau3(const TendP<T> &P, int m, int i, int j, int k) {
     VFlux<T> F(P, m);
     T Vi = P.g.rVf(k);
-    return Vi * (DELTA_(F.wx(i + 1, j, k), F.wx(i, j, k), 0) + DELTA_(F.wy(i, j + 1, k), F.wy(i, j, k), 1) +
+    return mul_rn(Vi, DELTA_(F.wx(i + 1, j, k), F.wx(i, j, k), 0) + DELTA_(F.wy(i, j + 1, k), F.wy(i, j, k), 1) +
                  DELTA_(F.wz(i, j, k), F.wz(i, j, k - 1), 2));
 }
 
@@ -197,7 +197,7 @@ template <typename T, int D> __device__ __forceinline__ T qflux(const TendP<T> &
 }
 template <typename T> __device__ __forceinline__ T div_q(const TendP<T> &P, int m, int t, int i, int j, int k) {
     T Vi = P.g.rVc(k);
-    return Vi * (DELTA_((qflux<T, 0>(P, m, t, i + 1, j, k)), (qflux<T, 0>(P, m, t, i, j, k)), 0) +
+    return mul_rn(Vi, DELTA_((qflux<T, 0>(P, m, t, i + 1, j, k)), (qflux<T, 0>(P, m, t, i, j, k)), 0) +
                  DELTA_((qflux<T, 1>(P, m, t, i, j + 1, k)), (qflux<T, 1>(P, m, t, i, j, k)), 1) +
                  DELTA_((qflux<T, 2>(P, m, t, i, j, k + 1)), (qflux<T, 2>(P, m, t, i, j, k)), 2));
 }
@@ -233,7 +233,7 @@ template <typename T> __device__ __forceinline__ T Gu_finish(const TendP<T> &P, 
     if (P.has_pHY) r = sub_rn(r, mul_rn(P.g.topo[0] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i - 1, j, k), P.g.rdx));
     if (P.ncl > 0) {
         T t = div_tau1(P, 0, i, j, k);
-        for (int m = 1; m < P.ncl; m++) t = t + div_tau1(P, m, i, j, k);
+        for (int m = 1; m < P.ncl; m++) t = add_rn(t, div_tau1(P, m, i, j, k));
         r = r - t;
     }
     return r;
@@ -257,7 +257,7 @@ template <typename T> __device__ __forceinline__ T Gv_finish(const TendP<T> &P, 
     if (P.has_pHY) r = sub_rn(r, mul_rn(P.g.topo[1] == FLAT ? T(0) : P.pHY.ld(i, j, k) - P.pHY.ld(i, j - 1, k), P.g.rdy));
     if (P.ncl > 0) {
         T t = div_tau2(P, 0, i, j, k);
-        for (int m = 1; m < P.ncl; m++) t = t + div_tau2(P, m, i, j, k);
+        for (int m = 1; m < P.ncl; m++) t = add_rn(t, div_tau2(P, m, i, j, k));
         r = r - t;
     }
     return r;
@@ -275,7 +275,7 @@ template <typename T> __device__ __forceinline__ T Gw_finish(const TendP<T> &P, 
     }
     if (P.ncl > 0) {
         T t = div_tau3(P, 0, i, j, k);
-        for (int m = 1; m < P.ncl; m++) t = t + div_tau3(P, m, i, j, k);
+        for (int m = 1; m < P.ncl; m++) t = add_rn(t, div_tau3(P, m, i, j, k));
         r = r - t;
     }
     return r;
@@ -291,7 +291,7 @@ template <typename T> __device__ __forceinline__ T Gc_finish(const TendP<T> &P, 
     T r = -adv;
     if (P.ncl > 0) {
         T q = div_q(P, 0, t, i, j, k);
-        for (int m = 1; m < P.ncl; m++) q = q + div_q(P, m, t, i, j, k);
+        for (int m = 1; m < P.ncl; m++) q = add_rn(q, div_q(P, m, t, i, j, k));
         r = r - q;
     }
     return r;

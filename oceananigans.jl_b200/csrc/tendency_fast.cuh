@@ -173,11 +173,11 @@ struct FastTerms {
     template <int WHICH> __device__ __forceinline__ T div_tau(int m) const {
         const T *ne = nue_ptr(m);
         if constexpr (WHICH == 0)
-            return G.rVc(k) * ((ux(m, ne, 0, 0, 0) - ux(m, ne, -1, 0, 0)) + (uy(m, ne, 0, 1, 0) - uy(m, ne, 0, 0, 0)) + (uz(m, ne, 0, 0, 1) - uz(m, ne, 0, 0, 0)));
+            return mul_rn(G.rVc(k), (ux(m, ne, 0, 0, 0) - ux(m, ne, -1, 0, 0)) + (uy(m, ne, 0, 1, 0) - uy(m, ne, 0, 0, 0)) + (uz(m, ne, 0, 0, 1) - uz(m, ne, 0, 0, 0)));
         else if constexpr (WHICH == 1)
-            return G.rVc(k) * ((vx(m, ne, 1, 0, 0) - vx(m, ne, 0, 0, 0)) + (vy(m, ne, 0, 0, 0) - vy(m, ne, 0, -1, 0)) + (vz(m, ne, 0, 0, 1) - vz(m, ne, 0, 0, 0)));
+            return mul_rn(G.rVc(k), (vx(m, ne, 1, 0, 0) - vx(m, ne, 0, 0, 0)) + (vy(m, ne, 0, 0, 0) - vy(m, ne, 0, -1, 0)) + (vz(m, ne, 0, 0, 1) - vz(m, ne, 0, 0, 0)));
         else
-            return G.rVf(k) * ((wx(m, ne, 1, 0, 0) - wx(m, ne, 0, 0, 0)) + (wy(m, ne, 0, 1, 0) - wy(m, ne, 0, 0, 0)) + (wz(m, ne, 0, 0, 0) - wz(m, ne, 0, 0, -1)));
+            return mul_rn(G.rVf(k), (wx(m, ne, 1, 0, 0) - wx(m, ne, 0, 0, 0)) + (wy(m, ne, 0, 1, 0) - wy(m, ne, 0, 0, 0)) + (wz(m, ne, 0, 0, 0) - wz(m, ne, 0, 0, -1)));
     }
     // diffusive flux of tracer t along D at the face (a, b, c) (abstract_scalar_diffusivity_closure.jl:260-262)
     __device__ __forceinline__ T qflux(int m, int t, const T *cp, const T *kf, int D, int a, int b, int c) const {
@@ -191,8 +191,8 @@ struct FastTerms {
     __device__ __forceinline__ T div_q(int m, int t, const T *cp) const {
         const int kind = P.cl[m].kind;
         const T *kf = kind == CL_SCALAR ? nullptr : kind == CL_SMAG ? at(P.nue[m]) : at(P.kappae[m][t]);
-        return G.rVc(k) * ((qflux(m, t, cp, kf, 0, 1, 0, 0) - qflux(m, t, cp, kf, 0, 0, 0, 0)) + (qflux(m, t, cp, kf, 1, 0, 1, 0) - qflux(m, t, cp, kf, 1, 0, 0, 0)) +
-                             (qflux(m, t, cp, kf, 2, 0, 0, 1) - qflux(m, t, cp, kf, 2, 0, 0, 0)));
+        return mul_rn(G.rVc(k), (qflux(m, t, cp, kf, 0, 1, 0, 0) - qflux(m, t, cp, kf, 0, 0, 0, 0)) + (qflux(m, t, cp, kf, 1, 0, 1, 0) - qflux(m, t, cp, kf, 1, 0, 0, 0)) +
+                                    (qflux(m, t, cp, kf, 2, 0, 0, 1) - qflux(m, t, cp, kf, 2, 0, 0, 0)));
     }
     __device__ __forceinline__ T bpert(int c) const {
         if (P.buoy == BUOY_TRACER) return ld(at(P.c[P.ib]), 0, 0, c);
@@ -254,11 +254,11 @@ struct FastTerms {
                 r = r - closure_term;
             } else if constexpr (WHICH == 3) {
                 T q = div_q(0, t, cp);
-                for (int m = 1; m < P.ncl; m++) q = q + div_q(m, t, cp);
+                for (int m = 1; m < P.ncl; m++) q = add_rn(q, div_q(m, t, cp));
                 r = r - q;
             } else {
                 T tt = div_tau<WHICH>(0);
-                for (int m = 1; m < P.ncl; m++) tt = tt + div_tau<WHICH>(m);
+                for (int m = 1; m < P.ncl; m++) tt = add_rn(tt, div_tau<WHICH>(m));
                 r = r - tt;
             }
         }
@@ -338,8 +338,10 @@ __device__ __forceinline__ void march_fast_body(const TendP<T> &P, int t, int i,
                 for (int m = 0; m < OB_SHARED_CL; m++)
                     if (m < ncl) {
                         const T cy1 = sv_buf[buf][m][ty + 1][tx];
-                        const T d = Vi * ((cx1[m] - cx[m]) + (cy1 - cy[m]) + (cup[m] - lower_c[m]));
-                        term = m == 0 ? d : term + d;
+                        // every closure's flux divergence rounded on its own, then summed (the reference adds ∇·τ of the closures
+                        // of a tuple one by one): the same pinned form in every kernel
+                        const T d = mul_rn(Vi, (cx1[m] - cx[m]) + (cy1 - cy[m]) + (cup[m] - lower_c[m]));
+                        term = m == 0 ? d : add_rn(term, d);
                     }
                 r = F.template finish<WHICH, true>(adv, t, pq, term);
             } else {

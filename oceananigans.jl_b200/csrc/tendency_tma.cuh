@@ -189,8 +189,8 @@ __device__ __forceinline__ void march_tma_body(const TendP<T> &P, const TmaMaps 
                 for (int m = 0; m < OB_SHARED_CL; m++)
                     if (m < ncl) {
                         const T cy1 = sv_buf[buf][m][ty + 1][tx];
-                        const T d = Vi * ((cx1[m] - cx[m]) + (cy1 - cy[m]) + (cup[m] - lower_c[m]));
-                        term = m == 0 ? d : term + d;
+                        const T d = mul_rn(Vi, (cx1[m] - cx[m]) + (cy1 - cy[m]) + (cup[m] - lower_c[m]));
+                        term = m == 0 ? d : add_rn(term, d);
                     }
                 r = F.template finish<WHICH, true>(adv, t, pq, term);
             } else {
