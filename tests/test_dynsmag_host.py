@@ -51,7 +51,8 @@ def test_laminar_shear_has_no_resolved_stress_and_a_known_MM():
 
 
 def test_coefficient_follows_the_averaging_dimensions():
-    for dims, shape in (((1, 2), (10, 1, 1)), ((1, 2, 3), (1, 1, 1)), ((1,), (10, 6, 1)), ((3,), (1, 6, 8))):
+    """sizes of 𝒥ᴸᴹ, 𝒥ᴹᴹ for averaging = 1, (1, 2), (2, 3), Colon (test/test_turbulence_closures.jl:421-448; numpy order (k, j, i))"""
+    for dims, shape in (((1, 2), (10, 1, 1)), ((1, 2, 3), (1, 1, 1)), ((1,), (10, 6, 1)), ((3,), (1, 6, 8)), ((2, 3), (1, 1, 8))):
         om = _model((8, 6, 10), "PPB", averaging=dims)
         cf = om.dynamic_fields[0]
         assert cf["JLM"].shape == shape and cf["JMM"].shape == shape

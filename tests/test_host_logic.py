@@ -181,3 +181,22 @@ def test_advection_scheme_orders():
             ob.WENO(order=bad)
     with pytest.raises(ValueError):
         ob.Centered(order=3)
+
+
+def test_dynamic_smagorinsky_constructor():
+    """DynamicSmagorinsky(; averaging, Pr, schedule, minimum_numerator) (dynamic_coefficient.jl:107-118): the averaging
+    dimensions as an integer, a tuple or a colon; LagrangianAveraging (the reference default) is representable but rejected
+    when a model is built from it"""
+    import ocean_b200 as ob
+    assert ob.DynamicSmagorinsky(averaging=1).dynamic["averaging"] == (1,)
+    assert ob.DynamicSmagorinsky(averaging=(1, 2), Pr=2.0).dynamic["averaging"] == (1, 2)
+    assert ob.DynamicSmagorinsky(averaging="colon").dynamic["averaging"] == (1, 2, 3)
+    assert ob.DynamicSmagorinsky(averaging=slice(None)).dynamic["averaging"] == (1, 2, 3)
+    d = ob.DynamicSmagorinsky()
+    assert isinstance(d.dynamic["averaging"], ob.LagrangianAveraging) and d.dynamic["minimum_numerator"] == 1e-32
+    assert ob.DynamicSmagorinsky(ob.VerticallyImplicitTimeDiscretization(), averaging=(1, 2)).vertically_implicit is True
+    assert ob.Smagorinsky().dynamic is None and ob.SmagorinskyLilly().dynamic is None
+    with pytest.raises(ValueError):
+        ob.DynamicSmagorinsky(averaging=(1, 4))
+    with pytest.raises(ValueError):
+        ob.DynamicSmagorinsky(averaging=())
