@@ -26,3 +26,34 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_recorded_gpu_lines_carry_the_contract_keys():
+    """the bench lines committed under profiles/ (written by `python bench.py [--gpus N]` on the GPU box) carry every key the
+    measurement contract asks for, and their derived numbers are consistent with each other"""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = sorted(glob.glob(os.path.join(root, "profiles", "r2l_bench_n1.json")) + glob.glob(os.path.join(root, "profiles", "r2k_n8*_bench.json")))
+    assert paths, "no recorded bench lines"
+    for path in paths:
+        line = [l for l in open(path) if l.strip().startswith("{")][-1]
+        d = json.loads(line)
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                    "dtype", "data", "config", "gpu_launches", "clocks", "roofline"):
+            assert key in d, (path, key)
+        assert d["metric"] == "cell-updates/sec" and d["dtype"] == "f64" and d["higher_is_better"] is True
+        assert d["vs_baseline"] is None and "workload" in d["config"] and d["gpu_launches"] > 0
+        r = d["roofline"]
+        for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert key in r, (path, key)
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+        # value = cells of all ranks * steps / time
+        cells = 256 ** 3 * d["n_gpus"]
+        assert abs(d["value"] - cells / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+            e = d["e2e"]
+            assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
