@@ -82,7 +82,7 @@ def test_weno5_beta_explicit_formula():
 
 def test_weno_reconstructs_polynomials_exactly():
     """a WENO-(2n-1) face value of a degree <= n-1 polynomial is exact whatever the weights (all sub-stencils agree)"""
-    for order, halo in ((3, 2), (5, 3), (7, 4), (9, 5)):
+    for order, halo in ((3, 2), (5, 3), (7, 4), (9, 5), (11, 6)):
         n = (order + 1) // 2
         cfg = Config((16, 4, 4), ((0, 16.0), (0, 4.0), (0, 4.0)), "PPP", halo=(halo,) * 3, advection=("weno", order))
         om = cfg.oracle_model()
@@ -101,6 +101,26 @@ def test_weno_reconstructs_polynomials_exactly():
         for left in (1, 0):
             got = fn(C.byref(p), n, 0, left, C.byref(of), 8, 2, 2)  # face i = 8 is at x = 7
             assert abs(got - P(7.0)) < 1e-12, (order, left, got, P(7.0))
+
+
+def test_centered_reconstructs_polynomials_exactly():
+    """Centered(order = 2n): the symmetric face value from the 2n surrounding cell averages is exact for polynomials of degree
+    <= 2n - 1 (reconstruction_coefficients.jl:62-77 with a stencil of 2n cells), orders 2 .. 12"""
+    for order in (2, 4, 6, 8, 10, 12):
+        n = order // 2
+        cfg = Config((20, 4, 4), ((0, 20.0), (0, 4.0), (0, 4.0)), "PPP", halo=(n,) * 3, advection=("centered", order))
+        om = cfg.oracle_model()
+        x = np.arange(-n, 20 + n) + 0.5
+        P = np.polynomial.Polynomial([0.3 * (q + 1) / 20 ** q for q in range(order)])
+        avg = (P.integ()(x + 0.5) - P.integ()(x - 0.5))
+        f = M.Field(om.grid, "ccc")
+        f.data[...] = avg[None, None, :]
+        p = om.params()
+        fn = M.lib().orc_sym_interp_f64
+        fn.restype = C.c_double
+        of = f.ofield()
+        got = fn(C.byref(p), 0, 0, C.byref(of), 10, 2, 2)   # face i = 10 is at x = 9
+        assert abs(got - P(9.0)) < 1e-11 * max(1.0, abs(P(9.0))), (order, got, P(9.0))
 
 
 # ---- closure flux divergences (test/test_turbulence_closures.jl:27-58) ---------------------------------------------
